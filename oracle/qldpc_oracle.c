@@ -332,7 +332,7 @@ static inline void rule_in(rule_f32 *u, int j, float x)
     const float a = fabsf(x);
     u->sign ^= signbit(x) ? 1 : 0;
     if (u->rule == ORA_RULE_SPA) {
-        const float t = tanhf(a * 0.5f);
+        const float t = (float)tanh((double)(a * 0.5f));   /* correctly rounded float tanh, see DESIGN.md */
         const float r = (t != 0.0f) ? t : 1e-12f;
         u->product *= r;
         u->values[j] = r;
@@ -360,7 +360,7 @@ static inline float rule_out(const rule_f32 *u, int j, float x)
     if (u->rule == ORA_RULE_SPA) {
         float r = u->product / u->values[j];
         r = (r < 1.0f) ? r : 1.0f - FLT_EPSILON;
-        mag = 2.0f * atanhf(r);
+        mag = 2.0f * (float)atanh((double)r);
     } else {
         mag = (fabsf(x) == u->min1) ? u->cst1 : u->cst2;
     }

@@ -1,0 +1,663 @@
+// C ABI of libqldpc_b200 (see include/qldpc.h for the reference interface each entry point replaces).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "kernels.hpp"
+
+namespace qldpc {
+
+thread_local std::string CudaCheck::last;
+
+int CudaCheck::fail(cudaError_t e, const char *what)
+{
+    last = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();   // clear the sticky-less error state
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? QLDPC_ERR_NO_DEVICE : QLDPC_ERR_CUDA;
+}
+
+namespace {
+
+enum { KF_NONE = 0, KF_LAYERED_I8 = 1, KF_LAYERED_GENERIC = 2, KF_FLOODING = 3 };
+
+int dtype_size(int dtype) { return dtype == QLDPC_DTYPE_F32 ? 4 : (dtype == QLDPC_DTYPE_I16 ? 2 : 1); }
+
+// selector that rotates the packing bytes {0,2,4,6} left by rho byte positions
+uint16_t pack_selector(int rho)
+{
+    static const int src[4] = {0, 2, 4, 6};
+    unsigned sel = 0;
+    for (int m = 0; m < 4; ++m) sel |= (unsigned)src[(m - rho) & 3] << (4 * m);
+    return (uint16_t)sel;
+}
+uint16_t unpack_selector(int rho)   // bytes rho, rho+1 -> low bytes of the two halves; high bytes zero
+{
+    return (uint16_t)((rho & 3) | (4 << 4) | (((rho + 1) & 3) << 8) | (4 << 12));
+}
+
+int build_qc_tables(qldpc_decoder *d)
+{
+    const HostCode &c = d->code;
+    std::vector<QcEdge> edges;
+    std::vector<QcEdgeAux> aux;
+    std::vector<QcLayer> layers;
+    const int W = c.z / 4;
+    for (int r = 0; r < c.base_rows; ++r) {
+        QcLayer ly{(int32_t)edges.size(), 0};
+        for (int col = 0; col < c.base_cols; ++col) {
+            const int s = c.base[r * c.base_cols + col];
+            if (s < 0) continue;
+            QcEdge e{};
+            QcEdgeAux a{};
+            a.col = (int16_t)col;
+            a.shift = (int16_t)s;
+            if (W > 0 && c.z % 4 == 0) {
+                const int q = s / W, rr = s % W;
+                e.off0 = (col * W + rr) * 4;
+                e.off1 = (col * W + rr - W) * 4;
+                e.thresh = W - rr;
+                e.selA0 = unpack_selector(q);
+                e.selA1 = unpack_selector(q + 1);
+                a.selW0 = pack_selector(q);
+                a.selW1 = pack_selector(q + 1);
+            }
+            edges.push_back(e);
+            aux.push_back(a);
+            ++ly.degree;
+        }
+        layers.push_back(ly);
+    }
+    if (int r = d->d_qc_edges.upload(edges)) return r;
+    if (int r = d->d_qc_aux.upload(aux)) return r;
+    if (int r = d->d_qc_layers.upload(layers)) return r;
+    return QLDPC_OK;
+}
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// shared-memory geometry of the layered int8 kernel; returns false when one frame does not fit
+bool plan_layered_i8(qldpc_decoder *d, LayeredI8Params &p)
+{
+    const HostCode &c = d->code;
+    if (c.z <= 0 || c.z % 4 != 0 || c.max_chk_degree > 20) return false;
+    const int W = c.z / 4, ZW32 = (c.z + 31) / 32;
+    const int nnz = c.edges / c.z;
+    const int tpg = round_up(W, 32);
+    if (tpg > layered_i8_max_threads()) return false;
+    p.Z = c.z; p.W = W; p.ZW32 = ZW32;
+    p.brows = c.base_rows; p.bcols = c.base_cols; p.nnz = nnz; p.N = c.n;
+    p.tab_bytes = round_up(nnz * (16 + 16 + (int)sizeof(QcEdgeAux)) + c.base_rows * (int)sizeof(QcLayer), 16);
+    const int L_bytes = c.base_cols * W * 4;
+    const int R_bytes = nnz * W * 4;
+    const int hd_bytes = round_up(c.base_cols * ZW32 * 4, 16);
+    const int syn_bytes = round_up(c.base_rows * ZW32 * 4, 16);
+    p.off_R = round_up(L_bytes, 16);
+    p.off_hd = p.off_R + round_up(R_bytes, 16);
+    p.off_syn = p.off_hd + hd_bytes;
+    p.slot_bytes = p.off_syn + syn_bytes;
+    const int avail = d->max_smem_optin - p.tab_bytes;
+    int slots = avail / p.slot_bytes;
+    slots = std::min(slots, layered_i8_max_threads() / tpg);
+    slots = std::min(slots, 15);   // named barriers 1..15
+    if (slots < 1) return false;
+    p.slots = slots;
+    p.tpg = tpg;
+    d->li8_slots = slots;
+    d->li8_tpg = tpg;
+    d->li8_smem = p.tab_bytes + slots * p.slot_bytes;
+    return true;
+}
+
+struct Lane {   // per-stream staging of the host-pointer entry points
+    cudaStream_t st = nullptr;
+    DevBuf<uint8_t> in, post;
+    DevBuf<uint32_t> syn, out;
+    DevBuf<uint8_t> ok;
+    DevBuf<uint16_t> iters;
+};
+
+}  // namespace
+}  // namespace qldpc
+
+using namespace qldpc;
+
+struct qldpc_decoder_lanes {
+    Lane lane[2];
+};
+
+// ---------------------------------------------------------------------------------------- codes
+
+extern "C" int qldpc_code_from_alist_file(const char *path, qldpc_code **out)
+{
+    if (!path || !out) return QLDPC_ERR_ARG;
+    qldpc_code *c = new (std::nothrow) qldpc_code();
+    if (!c) return QLDPC_ERR_NOMEM;
+    const int r = parse_alist(path, c->h);
+    if (r) { delete c; return r; }
+    *out = c;
+    return QLDPC_OK;
+}
+
+extern "C" int qldpc_code_from_qc_file(const char *path, qldpc_code **out)
+{
+    if (!path || !out) return QLDPC_ERR_ARG;
+    qldpc_code *c = new (std::nothrow) qldpc_code();
+    if (!c) return QLDPC_ERR_NOMEM;
+    const int r = parse_qc(path, c->h);
+    if (r) { delete c; return r; }
+    *out = c;
+    return QLDPC_OK;
+}
+
+extern "C" int qldpc_code_from_qc(const int32_t *base, int32_t rows, int32_t cols, int32_t z, qldpc_code **out)
+{
+    if (!base || !out) return QLDPC_ERR_ARG;
+    qldpc_code *c = new (std::nothrow) qldpc_code();
+    if (!c) return QLDPC_ERR_NOMEM;
+    const int r = build_qc(base, rows, cols, z, c->h);
+    if (r) { delete c; return r; }
+    *out = c;
+    return QLDPC_OK;
+}
+
+extern "C" int qldpc_code_from_csr(int32_t n, int32_t m, const int32_t *row_ptr, const int32_t *col_idx, qldpc_code **out)
+{
+    if (!row_ptr || !col_idx || !out || n <= 0 || m <= 0) return QLDPC_ERR_ARG;
+    if (row_ptr[0] != 0) return QLDPC_ERR_ARG;
+    for (int c = 0; c < m; ++c)
+        if (row_ptr[c + 1] < row_ptr[c]) return QLDPC_ERR_ARG;
+    for (int e = 0; e < row_ptr[m]; ++e)
+        if (col_idx[e] < 0 || col_idx[e] >= n) return QLDPC_ERR_ARG;
+    qldpc_code *c = new (std::nothrow) qldpc_code();
+    if (!c) return QLDPC_ERR_NOMEM;
+    c->h.n = n;
+    c->h.m = m;
+    c->h.row_ptr.assign(row_ptr, row_ptr + m + 1);
+    c->h.col_idx.assign(col_idx, col_idx + row_ptr[m]);
+    c->h.finalize_from_csr();
+    *out = c;
+    return QLDPC_OK;
+}
+
+extern "C" int qldpc_code_set_info_bits_pos(qldpc_code *code, const int32_t *pos, int32_t k)
+{
+    if (!code || !pos || k <= 0 || k > code->h.n) return QLDPC_ERR_ARG;
+    for (int i = 0; i < k; ++i)
+        if (pos[i] < 0 || pos[i] >= code->h.n) return QLDPC_ERR_ARG;
+    code->h.info_pos.assign(pos, pos + k);
+    code->h.k = k;
+    return QLDPC_OK;
+}
+
+extern "C" int qldpc_code_get_info(const qldpc_code *code, qldpc_code_info *info)
+{
+    if (!code || !info) return QLDPC_ERR_ARG;
+    const HostCode &h = code->h;
+    info->n = h.n; info->m = h.m; info->k = h.k; info->edges = h.edges; info->z = h.z;
+    info->base_rows = h.base_rows; info->base_cols = h.base_cols;
+    info->max_chk_degree = h.max_chk_degree; info->max_var_degree = h.max_var_degree;
+    return QLDPC_OK;
+}
+
+extern "C" void qldpc_code_free(qldpc_code *code) { delete code; }
+
+// ------------------------------------------------------------------------------------- decoders
+
+extern "C" void qldpc_decoder_config_default(qldpc_decoder_config *cfg)
+{
+    if (!cfg) return;
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->schedule = QLDPC_SCHED_FLOODING;   // the reference's live configuration: flooding SPA,
+    cfg->rule = QLDPC_RULE_SPA;             // B=int, Q=float (BOOT/src/main.cpp:113,193)
+    cfg->dtype = QLDPC_DTYPE_F32;
+    cfg->max_iter = 100;                    // BOOT/src/main.cpp:100
+    cfg->early_stop = 1;                    // :101
+    cfg->syndrome_depth = 1;                // :102
+    cfg->norm_factor = 1.0f;                // :98
+    cfg->offset = 0.0f;                     // :99
+    cfg->out_mode = QLDPC_OUT_INFO;
+    cfg->device = 0;
+}
+
+struct qldpc_decoder_full : qldpc_decoder {
+    qldpc_decoder_lanes lanes;
+    DevBuf<int32_t> d_base;
+    DevBuf<uint32_t> d_mask_known, d_mask_punct, d_tmp_bits;
+    size_t scratch_msg_bytes = 0, scratch_app_bytes = 0;
+    DevBuf<uint8_t> d_scratch2;
+    int gen_grid = 0;
+    int flood_block = 0, flood_smem = 0, flood_use_smem = 0;
+};
+
+static qldpc_decoder_full *full(qldpc_decoder *d) { return static_cast<qldpc_decoder_full *>(d); }
+
+extern "C" int qldpc_decoder_create(const qldpc_code *code, const qldpc_decoder_config *cfg, qldpc_decoder **out)
+{
+    if (!code || !cfg || !out) return QLDPC_ERR_ARG;
+    if (cfg->max_iter < 0 || cfg->max_iter > 65535) return QLDPC_ERR_ARG;
+    if (cfg->schedule != QLDPC_SCHED_FLOODING && cfg->schedule != QLDPC_SCHED_LAYERED) return QLDPC_ERR_ARG;
+    if (cfg->rule < QLDPC_RULE_SPA || cfg->rule > QLDPC_RULE_OMS) return QLDPC_ERR_ARG;
+    if (cfg->dtype < QLDPC_DTYPE_F32 || cfg->dtype > QLDPC_DTYPE_I8) return QLDPC_ERR_ARG;
+    if (cfg->out_mode != QLDPC_OUT_INFO && cfg->out_mode != QLDPC_OUT_ALL) return QLDPC_ERR_ARG;
+    const bool is_int = cfg->dtype != QLDPC_DTYPE_F32;
+    if (is_int && cfg->rule == QLDPC_RULE_SPA) return QLDPC_ERR_UNSUPPORTED;   // SPA is float only (as in AFF3CT)
+    if (cfg->schedule == QLDPC_SCHED_LAYERED && code->h.z <= 0) return QLDPC_ERR_UNSUPPORTED;
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return QLDPC_ERR_NO_DEVICE; }
+    if (cfg->device < 0 || cfg->device >= ndev) return QLDPC_ERR_ARG;
+    QLDPC_CUDA(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    QLDPC_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) return QLDPC_ERR_NO_DEVICE;   // kernels are built for sm_100a only
+
+    qldpc_decoder_full *d = new (std::nothrow) qldpc_decoder_full();
+    if (!d) return QLDPC_ERR_NOMEM;
+    d->code = code->h;
+    d->cfg = *cfg;
+    if (d->cfg.syndrome_depth < 1) d->cfg.syndrome_depth = 1;
+    d->sm_count = prop.multiProcessorCount;
+    d->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    const HostCode &c = d->code;
+
+    int rc = QLDPC_OK;
+    auto bail = [&](int r) { delete d; return r; };
+
+    if (is_int) {
+        if (cfg->rule == QLDPC_RULE_NMS) {
+            const float k8 = cfg->norm_factor * 8.0f;
+            const int k = (int)lrintf(k8);
+            if (k < 1 || k > 8 || std::fabs(k8 - (float)k) > 1e-4f) return bail(QLDPC_ERR_ARG);
+            d->norm_eighths = k;
+        } else {
+            const int o = (int)lrintf(cfg->offset);
+            if (o < 0 || std::fabs(cfg->offset - (float)o) > 1e-4f) return bail(QLDPC_ERR_ARG);
+            d->offset_int = o;
+        }
+        if (d->cfg.msg_max <= 0) d->cfg.msg_max = cfg->dtype == QLDPC_DTYPE_I8 ? 31 : 511;
+        if (d->cfg.app_max <= 0) d->cfg.app_max = cfg->dtype == QLDPC_DTYPE_I8 ? 127 : 8191;
+        if (cfg->dtype == QLDPC_DTYPE_I8 && (d->cfg.msg_max > 126 || d->cfg.app_max > 127)) return bail(QLDPC_ERR_ARG);
+        if (d->cfg.msg_max > 32766 || d->cfg.app_max > (1 << 24)) return bail(QLDPC_ERR_ARG);
+    }
+
+    d->cw_words = (c.n + 31) / 32;
+    d->syn_words = (c.m + 31) / 32;
+    d->out_bits = cfg->out_mode == QLDPC_OUT_ALL ? c.n : c.k;
+    d->out_words = (d->out_bits + 31) / 32;
+    d->info_is_prefix = true;
+    for (int i = 0; i < c.k; ++i)
+        if (c.info_pos[i] != i) { d->info_is_prefix = false; break; }
+
+    if ((rc = d->d_row_ptr.upload(c.row_ptr))) return bail(rc);
+    if ((rc = d->d_col_idx.upload(c.col_idx))) return bail(rc);
+    if ((rc = d->d_var_ptr.upload(c.var_ptr))) return bail(rc);
+    if ((rc = d->d_var_edge.upload(c.var_edge))) return bail(rc);
+    if ((rc = d->d_info_pos.upload(c.info_pos))) return bail(rc);
+    if (c.z > 0) {
+        if ((rc = build_qc_tables(d))) return bail(rc);
+        if ((rc = d->d_base.upload(c.base))) return bail(rc);
+    }
+    if ((rc = d->d_stats.ensure(1))) return bail(rc);
+    if (cudaMemset(d->d_stats.p, 0, sizeof(DevStats)) != cudaSuccess) return bail(QLDPC_ERR_CUDA);
+
+    if (cfg->schedule == QLDPC_SCHED_LAYERED) {
+        LayeredI8Params p{};
+        const bool fast = cfg->dtype == QLDPC_DTYPE_I8 && d->cfg.app_max == 127 && d->cfg.msg_max <= 63 &&
+                          plan_layered_i8(d, p);
+        if (fast) {
+            d->kernel_family = KF_LAYERED_I8;
+            d->kernel_name = "layered_i8_zpack4";
+        } else {
+            d->kernel_family = KF_LAYERED_GENERIC;
+            d->kernel_name = "layered_generic";
+        }
+        // the generic kernel also serves posterior requests of the fast family
+        d->gen_grid = d->sm_count * 2;
+        const size_t esz = 4;
+        d->scratch_msg_bytes = (size_t)d->gen_grid * c.edges * esz;
+        d->scratch_app_bytes = (size_t)d->gen_grid * c.n * esz;
+    } else {
+        d->kernel_family = KF_FLOODING;
+        d->kernel_name = "flooding_csr";
+        const size_t need = (size_t)(c.edges + c.n) * 4;
+        d->flood_use_smem = need + 1024 <= (size_t)d->max_smem_optin;
+        d->flood_smem = d->flood_use_smem ? (int)need : 0;
+        const int work = std::max(c.n, c.m);
+        d->flood_block = std::min(1024, std::max(128, round_up(work / 2, 32)));
+        d->gen_grid = d->flood_use_smem ? d->sm_count * std::max(1, std::min(8, d->max_smem_optin / (int)(need + 1024)))
+                                        : d->sm_count * 2;
+        if (!d->flood_use_smem) {
+            d->scratch_msg_bytes = (size_t)d->gen_grid * c.edges * 4;
+            d->scratch_app_bytes = (size_t)d->gen_grid * c.n * 4;
+        }
+    }
+    for (auto &ln : d->lanes.lane)
+        if (cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking) != cudaSuccess) return bail(QLDPC_ERR_CUDA);
+    *out = d;
+    return QLDPC_OK;
+}
+
+extern "C" void qldpc_decoder_free(qldpc_decoder *dec)
+{
+    if (!dec) return;
+    qldpc_decoder_full *d = full(dec);
+    cudaSetDevice(d->cfg.device);
+    cudaDeviceSynchronize();
+    for (auto &ln : d->lanes.lane)
+        if (ln.st) cudaStreamDestroy(ln.st);
+    delete d;
+}
+
+extern "C" int32_t qldpc_out_words(const qldpc_decoder *dec) { return dec ? dec->out_words : 0; }
+extern "C" int32_t qldpc_syndrome_words(const qldpc_decoder *dec) { return dec ? dec->syn_words : 0; }
+extern "C" int32_t qldpc_codeword_words(const qldpc_decoder *dec) { return dec ? dec->cw_words : 0; }
+extern "C" const char *qldpc_decoder_kernel_name(const qldpc_decoder *dec) { return dec ? dec->kernel_name : "none"; }
+
+// scratch for kernels whose state does not fit on chip (lazy: the tuned int8 path never needs it)
+static int ensure_scratch(qldpc_decoder_full *d)
+{
+    if (d->scratch_msg_bytes && d->d_scratch.n < d->scratch_msg_bytes)
+        if (int r = d->d_scratch.ensure(d->scratch_msg_bytes)) return r;
+    if (d->scratch_app_bytes && d->d_scratch2.n < d->scratch_app_bytes)
+        if (int r = d->d_scratch2.ensure(d->scratch_app_bytes)) return r;
+    return QLDPC_OK;
+}
+
+extern "C" int qldpc_decode_device(qldpc_decoder *dec, const void *d_llr, const uint32_t *d_syndrome, int32_t n_frames,
+                                   uint32_t *d_out_bits, uint8_t *d_ok, uint16_t *d_iters, void *d_posterior,
+                                   void *cuda_stream)
+{
+    if (!dec || !d_llr || !d_out_bits || n_frames < 0) return QLDPC_ERR_ARG;
+    if (n_frames == 0) return QLDPC_OK;
+    qldpc_decoder_full *d = full(dec);
+    const HostCode &c = d->code;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    QLDPC_CUDA(cudaSetDevice(d->cfg.device));
+    const qldpc_decoder_config &cfg = d->cfg;
+    int rc;
+
+    int family = d->kernel_family;
+    if (family == KF_LAYERED_I8 && d_posterior) family = KF_LAYERED_GENERIC;
+
+    if (family == KF_LAYERED_I8) {
+        LayeredI8Params p{};
+        if (!plan_layered_i8(d, p)) return QLDPC_ERR_UNSUPPORTED;
+        const bool direct = cfg.out_mode == QLDPC_OUT_ALL || d->info_is_prefix;
+        if (!direct)
+            if ((rc = d->d_allbits.ensure((size_t)n_frames * d->cw_words))) return rc;
+        p.llr = (const int8_t *)d_llr;
+        p.syn = d_syndrome;
+        p.out = direct ? d_out_bits : d->d_allbits.p;
+        p.ok = d_ok; p.iters = d_iters; p.stats = d->d_stats.p;
+        p.edges = d->d_qc_edges.p; p.aux = d->d_qc_aux.p; p.layers = d->d_qc_layers.p;
+        p.F = n_frames;
+        p.out_cols = (direct && cfg.out_mode == QLDPC_OUT_INFO) ? c.base_cols - c.base_rows : c.base_cols;
+        p.out_words = (p.out_cols * c.z + 31) / 32;
+        p.syn_words = d->syn_words;
+        p.max_iter = cfg.max_iter; p.early_stop = cfg.early_stop;
+        p.rule = cfg.rule; p.offset = d->offset_int; p.norm_eighths = d->norm_eighths; p.msg_max = cfg.msg_max;
+        const int grid = std::min(d->sm_count, (n_frames + p.slots - 1) / p.slots);
+        if ((rc = launch_layered_i8(p, grid, d->li8_smem, st))) return rc;
+        d->kernel_launches++;
+        if (!direct) {
+            if ((rc = launch_gather_bits(d->d_allbits.p, d_out_bits, n_frames, d->cw_words, d->out_words, c.k,
+                                         d->d_info_pos.p, st))) return rc;
+            d->kernel_launches++;
+        }
+        return QLDPC_OK;
+    }
+
+    // families that write all n hard decisions and may need an info-bit gather
+    if ((rc = ensure_scratch(d))) return rc;
+    const bool direct = cfg.out_mode == QLDPC_OUT_ALL;
+    uint32_t *allbits = d_out_bits;
+    if (!direct) {
+        if ((rc = d->d_allbits.ensure((size_t)n_frames * d->cw_words))) return rc;
+        allbits = d->d_allbits.p;
+    }
+    if (family == KF_LAYERED_GENERIC) {
+        LayeredGenParams p{};
+        p.llr = d_llr; p.syn = d_syndrome; p.allbits = allbits; p.ok = d_ok; p.iters = d_iters;
+        p.posterior = d_posterior; p.stats = d->d_stats.p;
+        p.aux = d->d_qc_aux.p; p.layers = d->d_qc_layers.p;
+        p.msg = d->d_scratch.p; p.app = d->d_scratch2.p;
+        p.F = n_frames; p.Z = c.z; p.brows = c.base_rows; p.bcols = c.base_cols; p.nnz = c.edges / c.z;
+        p.N = c.n; p.M = c.m; p.cw_words = d->cw_words; p.syn_words = d->syn_words;
+        p.max_iter = cfg.max_iter; p.early_stop = cfg.early_stop; p.syndrome_depth = cfg.syndrome_depth;
+        p.rule = cfg.rule; p.dtype = cfg.dtype; p.norm = cfg.norm_factor; p.offset = cfg.offset;
+        p.offset_int = d->offset_int; p.norm_eighths = d->norm_eighths; p.msg_max = cfg.msg_max; p.app_max = cfg.app_max;
+        if ((rc = launch_layered_generic(p, std::min(d->gen_grid, n_frames), st))) return rc;
+    } else {
+        FloodParams p{};
+        p.llr = d_llr; p.syn = d_syndrome; p.allbits = allbits; p.ok = d_ok; p.iters = d_iters;
+        p.posterior = d_posterior; p.stats = d->d_stats.p;
+        p.row_ptr = d->d_row_ptr.p; p.col_idx = d->d_col_idx.p; p.var_ptr = d->d_var_ptr.p; p.var_edge = d->d_var_edge.p;
+        p.c2v = d->d_scratch.p; p.post = d->d_scratch2.p;
+        p.F = n_frames; p.N = c.n; p.M = c.m; p.E = c.edges; p.cw_words = d->cw_words; p.syn_words = d->syn_words;
+        p.max_iter = cfg.max_iter; p.early_stop = cfg.early_stop; p.syndrome_depth = cfg.syndrome_depth;
+        p.rule = cfg.rule; p.dtype = cfg.dtype; p.norm = cfg.norm_factor; p.offset = cfg.offset;
+        p.offset_int = d->offset_int; p.norm_eighths = d->norm_eighths;
+        p.vmax = cfg.dtype == QLDPC_DTYPE_I16 ? 32767 : 127;
+        p.use_smem = d->flood_use_smem;
+        if ((rc = launch_flooding(p, std::min(d->gen_grid, n_frames), d->flood_block, d->flood_smem, st))) return rc;
+    }
+    d->kernel_launches++;
+    if (!direct) {
+        if ((rc = launch_gather_bits(allbits, d_out_bits, n_frames, d->cw_words, d->out_words, c.k, d->d_info_pos.p, st)))
+            return rc;
+        d->kernel_launches++;
+    }
+    return QLDPC_OK;
+}
+
+// Host-pointer entry point: frames are cut into chunks that ping-pong over two streams so the
+// H2D copy of chunk i+1 overlaps the decode of chunk i and the D2H of chunk i-1.
+extern "C" int qldpc_decode(qldpc_decoder *dec, const void *llr, const uint32_t *syndrome, int32_t n_frames,
+                            uint32_t *out_bits, uint8_t *ok, uint16_t *iters, void *posterior)
+{
+    if (!dec || !llr || !out_bits || n_frames < 0) return QLDPC_ERR_ARG;
+    if (n_frames == 0) return QLDPC_OK;
+    qldpc_decoder_full *d = full(dec);
+    const HostCode &c = d->code;
+    QLDPC_CUDA(cudaSetDevice(d->cfg.device));
+    const size_t esz = dtype_size(d->cfg.dtype);
+    const size_t frame_in = (size_t)c.n * esz;
+    // chunk: ~64 MiB of LLRs, at least one wave of the persistent grid
+    int chunk = (int)std::max<size_t>(1, (64u << 20) / frame_in);
+    chunk = std::max(chunk, d->sm_count * std::max(1, d->li8_slots));
+    chunk = std::min(chunk, n_frames);
+    // the scratch of the gather path is shared: those configurations run on one lane only
+    const bool shared_scratch = !(d->kernel_family == KF_LAYERED_I8 && !posterior &&
+                                  (d->cfg.out_mode == QLDPC_OUT_ALL || d->info_is_prefix));
+    int rc = QLDPC_OK;
+    for (auto &ln : d->lanes.lane) {
+        if ((rc = ln.in.ensure((size_t)chunk * frame_in))) return rc;
+        if ((rc = ln.out.ensure((size_t)chunk * d->out_words))) return rc;
+        if ((rc = ln.ok.ensure(chunk))) return rc;
+        if ((rc = ln.iters.ensure(chunk))) return rc;
+        if (syndrome && (rc = ln.syn.ensure((size_t)chunk * d->syn_words))) return rc;
+        if (posterior && (rc = ln.post.ensure((size_t)chunk * c.n * 4))) return rc;
+    }
+    int idx = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += chunk, ++idx) {
+        Lane &ln = d->lanes.lane[shared_scratch ? 0 : (idx & 1)];
+        const int nf = std::min(chunk, n_frames - f0);
+        QLDPC_CUDA(cudaMemcpyAsync(ln.in.p, (const char *)llr + (size_t)f0 * frame_in, (size_t)nf * frame_in,
+                                   cudaMemcpyHostToDevice, ln.st));
+        if (syndrome)
+            QLDPC_CUDA(cudaMemcpyAsync(ln.syn.p, syndrome + (size_t)f0 * d->syn_words, (size_t)nf * d->syn_words * 4,
+                                       cudaMemcpyHostToDevice, ln.st));
+        rc = qldpc_decode_device(dec, ln.in.p, syndrome ? ln.syn.p : nullptr, nf, ln.out.p, ln.ok.p, ln.iters.p,
+                                 posterior ? ln.post.p : nullptr, ln.st);
+        if (rc) break;
+        QLDPC_CUDA(cudaMemcpyAsync(out_bits + (size_t)f0 * d->out_words, ln.out.p, (size_t)nf * d->out_words * 4,
+                                   cudaMemcpyDeviceToHost, ln.st));
+        if (ok) QLDPC_CUDA(cudaMemcpyAsync(ok + f0, ln.ok.p, nf, cudaMemcpyDeviceToHost, ln.st));
+        if (iters) QLDPC_CUDA(cudaMemcpyAsync(iters + f0, ln.iters.p, (size_t)nf * 2, cudaMemcpyDeviceToHost, ln.st));
+        if (posterior)
+            QLDPC_CUDA(cudaMemcpyAsync((char *)posterior + (size_t)f0 * c.n * 4, ln.post.p, (size_t)nf * c.n * 4,
+                                       cudaMemcpyDeviceToHost, ln.st));
+    }
+    for (auto &ln : d->lanes.lane) {
+        cudaError_t e = cudaStreamSynchronize(ln.st);
+        if (e != cudaSuccess && rc == QLDPC_OK) rc = CudaCheck::fail(e, "cudaStreamSynchronize");
+    }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------- bit-level helpers
+
+extern "C" int qldpc_syndrome_device(qldpc_decoder *dec, const uint32_t *d_bits, int32_t n_frames, uint32_t *d_syndrome,
+                                     void *cuda_stream)
+{
+    if (!dec || !d_bits || !d_syndrome || n_frames < 0) return QLDPC_ERR_ARG;
+    qldpc_decoder_full *d = full(dec);
+    QLDPC_CUDA(cudaSetDevice(d->cfg.device));
+    const int rc = launch_syndrome_csr(d_bits, d_syndrome, n_frames, d->code.n, d->code.m, d->cw_words, d->syn_words,
+                                       d->d_row_ptr.p, d->d_col_idx.p, (cudaStream_t)cuda_stream);
+    if (!rc && n_frames) d->kernel_launches++;
+    return rc;
+}
+
+extern "C" int qldpc_syndrome(qldpc_decoder *dec, const uint32_t *bits, int32_t n_frames, uint32_t *syndrome)
+{
+    if (!dec || !bits || !syndrome || n_frames < 0) return QLDPC_ERR_ARG;
+    if (n_frames == 0) return QLDPC_OK;
+    qldpc_decoder_full *d = full(dec);
+    QLDPC_CUDA(cudaSetDevice(d->cfg.device));
+    Lane &ln = d->lanes.lane[0];
+    int rc;
+    if ((rc = d->d_tmp_bits.ensure((size_t)n_frames * d->cw_words))) return rc;
+    if ((rc = ln.syn.ensure((size_t)n_frames * d->syn_words))) return rc;
+    QLDPC_CUDA(cudaMemcpyAsync(d->d_tmp_bits.p, bits, (size_t)n_frames * d->cw_words * 4, cudaMemcpyHostToDevice, ln.st));
+    if ((rc = qldpc_syndrome_device(dec, d->d_tmp_bits.p, n_frames, ln.syn.p, ln.st))) return rc;
+    QLDPC_CUDA(cudaMemcpyAsync(syndrome, ln.syn.p, (size_t)n_frames * d->syn_words * 4, cudaMemcpyDeviceToHost, ln.st));
+    QLDPC_CUDA(cudaStreamSynchronize(ln.st));
+    return QLDPC_OK;
+}
+
+extern "C" int qldpc_make_llr_device(qldpc_decoder *dec, const uint32_t *d_bits, const uint32_t *d_known_mask,
+                                     const uint32_t *d_punct_mask, float llr_noisy, float llr_known, int32_t n_frames,
+                                     void *d_llr_out, void *cuda_stream)
+{
+    if (!dec || !d_bits || !d_llr_out || n_frames < 0) return QLDPC_ERR_ARG;
+    qldpc_decoder_full *d = full(dec);
+    QLDPC_CUDA(cudaSetDevice(d->cfg.device));
+    const int rc = launch_make_llr(d_bits, d_known_mask, d_punct_mask, llr_noisy, llr_known, n_frames, d->code.n,
+                                   d->cw_words, d->cfg.dtype, d_llr_out, (cudaStream_t)cuda_stream);
+    if (!rc && n_frames) d->kernel_launches++;
+    return rc;
+}
+
+extern "C" int qldpc_make_llr(qldpc_decoder *dec, const uint32_t *bits, const uint32_t *known_mask,
+                              const uint32_t *punct_mask, float llr_noisy, float llr_known, int32_t n_frames, void *llr_out)
+{
+    if (!dec || !bits || !llr_out || n_frames < 0) return QLDPC_ERR_ARG;
+    if (n_frames == 0) return QLDPC_OK;
+    qldpc_decoder_full *d = full(dec);
+    QLDPC_CUDA(cudaSetDevice(d->cfg.device));
+    Lane &ln = d->lanes.lane[0];
+    const size_t esz = dtype_size(d->cfg.dtype);
+    int rc;
+    if ((rc = d->d_tmp_bits.ensure((size_t)n_frames * d->cw_words))) return rc;
+    if ((rc = ln.in.ensure((size_t)n_frames * d->code.n * esz))) return rc;
+    QLDPC_CUDA(cudaMemcpyAsync(d->d_tmp_bits.p, bits, (size_t)n_frames * d->cw_words * 4, cudaMemcpyHostToDevice, ln.st));
+    const uint32_t *dk = nullptr, *dp = nullptr;
+    if (known_mask) {
+        if ((rc = d->d_mask_known.ensure(d->cw_words))) return rc;
+        QLDPC_CUDA(cudaMemcpyAsync(d->d_mask_known.p, known_mask, (size_t)d->cw_words * 4, cudaMemcpyHostToDevice, ln.st));
+        dk = d->d_mask_known.p;
+    }
+    if (punct_mask) {
+        if ((rc = d->d_mask_punct.ensure(d->cw_words))) return rc;
+        QLDPC_CUDA(cudaMemcpyAsync(d->d_mask_punct.p, punct_mask, (size_t)d->cw_words * 4, cudaMemcpyHostToDevice, ln.st));
+        dp = d->d_mask_punct.p;
+    }
+    if ((rc = qldpc_make_llr_device(dec, d->d_tmp_bits.p, dk, dp, llr_noisy, llr_known, n_frames, ln.in.p, ln.st))) return rc;
+    QLDPC_CUDA(cudaMemcpyAsync(llr_out, ln.in.p, (size_t)n_frames * d->code.n * esz, cudaMemcpyDeviceToHost, ln.st));
+    QLDPC_CUDA(cudaStreamSynchronize(ln.st));
+    return QLDPC_OK;
+}
+
+extern "C" int qldpc_encode_nr_device(qldpc_decoder *dec, const uint32_t *d_msg, int32_t n_frames, uint32_t *d_cword,
+                                      void *cuda_stream)
+{
+    if (!dec || !d_msg || !d_cword || n_frames < 0) return QLDPC_ERR_ARG;
+    qldpc_decoder_full *d = full(dec);
+    if (!d->code.has_nr_core()) return QLDPC_ERR_UNSUPPORTED;
+    QLDPC_CUDA(cudaSetDevice(d->cfg.device));
+    const HostCode &c = d->code;
+    const int kbits = (c.base_cols - c.base_rows) * c.z;
+    const int rc = launch_encode_nr(d_msg, d_cword, n_frames, c.z, c.base_rows, c.base_cols, d->d_base.p, (kbits + 31) / 32,
+                                    d->cw_words, (cudaStream_t)cuda_stream);
+    if (!rc && n_frames) d->kernel_launches++;
+    return rc;
+}
+
+extern "C" int qldpc_encode_nr(qldpc_decoder *dec, const uint32_t *msg, int32_t n_frames, uint32_t *cword)
+{
+    if (!dec || !msg || !cword || n_frames < 0) return QLDPC_ERR_ARG;
+    if (n_frames == 0) return QLDPC_OK;
+    qldpc_decoder_full *d = full(dec);
+    if (!d->code.has_nr_core()) return QLDPC_ERR_UNSUPPORTED;
+    QLDPC_CUDA(cudaSetDevice(d->cfg.device));
+    const HostCode &c = d->code;
+    const int msg_words = ((c.base_cols - c.base_rows) * c.z + 31) / 32;
+    Lane &ln = d->lanes.lane[0];
+    int rc;
+    if ((rc = d->d_tmp_bits.ensure((size_t)n_frames * msg_words))) return rc;
+    if ((rc = ln.out.ensure((size_t)n_frames * d->cw_words))) return rc;
+    QLDPC_CUDA(cudaMemcpyAsync(d->d_tmp_bits.p, msg, (size_t)n_frames * msg_words * 4, cudaMemcpyHostToDevice, ln.st));
+    if ((rc = qldpc_encode_nr_device(dec, d->d_tmp_bits.p, n_frames, ln.out.p, ln.st))) return rc;
+    QLDPC_CUDA(cudaMemcpyAsync(cword, ln.out.p, (size_t)n_frames * d->cw_words * 4, cudaMemcpyDeviceToHost, ln.st));
+    QLDPC_CUDA(cudaStreamSynchronize(ln.st));
+    return QLDPC_OK;
+}
+
+// ----------------------------------------------------------------------------------- statistics
+
+extern "C" int qldpc_get_stats(qldpc_decoder *dec, qldpc_stats *out)
+{
+    if (!dec || !out) return QLDPC_ERR_ARG;
+    qldpc_decoder_full *d = full(dec);
+    QLDPC_CUDA(cudaSetDevice(d->cfg.device));
+    QLDPC_CUDA(cudaDeviceSynchronize());
+    DevStats h;
+    QLDPC_CUDA(cudaMemcpy(&h, d->d_stats.p, sizeof(h), cudaMemcpyDeviceToHost));
+    out->frames = h.frames;
+    out->failures = h.failures;
+    out->iter_sum = h.iter_sum;
+    for (int i = 0; i < QLDPC_ITER_HIST_BINS; ++i) out->iter_hist[i] = h.hist[i];
+    out->kernel_launches = d->kernel_launches;
+    return QLDPC_OK;
+}
+
+extern "C" int qldpc_reset_stats(qldpc_decoder *dec)
+{
+    if (!dec) return QLDPC_ERR_ARG;
+    qldpc_decoder_full *d = full(dec);
+    QLDPC_CUDA(cudaSetDevice(d->cfg.device));
+    QLDPC_CUDA(cudaDeviceSynchronize());
+    QLDPC_CUDA(cudaMemset(d->d_stats.p, 0, sizeof(DevStats)));
+    d->kernel_launches = 0;
+    return QLDPC_OK;
+}
+
+extern "C" const char *qldpc_strerror(int code)
+{
+    switch (code) {
+    case QLDPC_OK: return "ok";
+    case QLDPC_ERR_ARG: return "invalid argument";
+    case QLDPC_ERR_IO: return "cannot open matrix file";
+    case QLDPC_ERR_FORMAT: return "malformed matrix file";
+    case QLDPC_ERR_NOMEM: return "out of memory";
+    case QLDPC_ERR_CUDA: return "CUDA error";
+    case QLDPC_ERR_UNSUPPORTED: return "unsupported schedule / rule / dtype / code combination";
+    case QLDPC_ERR_NO_DEVICE: return "no sm_100 CUDA device";
+    default: return "unknown error";
+    }
+}
+
+extern "C" const char *qldpc_last_cuda_error(void) { return CudaCheck::last.c_str(); }
+extern "C" int qldpc_version(void) { return QLDPC_VERSION; }

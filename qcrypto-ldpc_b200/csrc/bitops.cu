@@ -1,0 +1,200 @@
+// Bit-packed helpers around the decoders: syndrome, info-bit gather, LLR synthesis, NR encoder.
+// All bit vectors are MSB-first in 32-bit words (errorcorrection/subcomponents/helpers.h:65-68).
+#include "kernels.hpp"
+
+namespace qldpc {
+
+namespace {
+
+__device__ __forceinline__ unsigned get_bit(const uint32_t *w, int i) { return (w[i >> 5] >> (31 - (i & 31))) & 1u; }
+
+// syndrome = H * bits (ML/check_cword.m:9-19).  One thread per output word: 32 checks, each the
+// XOR of its variables' bits; popc parity of the assembled word is what early termination tests.
+__global__ void syndrome_csr_kernel(const uint32_t *__restrict__ bits, uint32_t *__restrict__ syn, int F, int M,
+                                    int cw_words, int syn_words, const int32_t *__restrict__ row_ptr,
+                                    const int32_t *__restrict__ col_idx)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)F * syn_words) return;
+    const int f = (int)(t / syn_words), w = (int)(t - (long long)f * syn_words);
+    const uint32_t *b = bits + (size_t)f * cw_words;
+    uint32_t out = 0;
+    for (int k = 0; k < 32; ++k) {
+        const int m = 32 * w + k;
+        if (m >= M) break;
+        unsigned s = 0;
+        for (int e = row_ptr[m]; e < row_ptr[m + 1]; ++e) s ^= get_bit(b, col_idx[e]);
+        out |= (s & 1u) << (31 - k);
+    }
+    syn[t] = out;
+}
+
+__global__ void gather_bits_kernel(const uint32_t *__restrict__ allbits, uint32_t *__restrict__ out, int F, int cw_words,
+                                   int out_words, int K, const int32_t *__restrict__ info_pos)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)F * out_words) return;
+    const int f = (int)(t / out_words), w = (int)(t - (long long)f * out_words);
+    const uint32_t *b = allbits + (size_t)f * cw_words;
+    uint32_t v = 0;
+    for (int k = 0; k < 32; ++k) {
+        const int i = 32 * w + k;
+        if (i >= K) break;
+        v |= get_bit(b, info_pos[i]) << (31 - k);
+    }
+    out[t] = v;
+}
+
+// Modem_OOK_BSC::demodulate + confirmed-parity / puncture override (BOOT/src/main.cpp:348-363):
+// received 0 -> +mag, received 1 -> -mag.  One thread per 4 consecutive bits (one 32-bit store
+// for int8 output).
+template <typename T>
+__global__ void make_llr_kernel(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ known,
+                                const uint32_t *__restrict__ punct, T noisy, T known_mag, int F, int N, int cw_words,
+                                T *__restrict__ out)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int groups = (N + 3) / 4;
+    if (t >= (long long)F * groups) return;
+    const int f = (int)(t / groups), g = (int)(t - (long long)f * groups);
+    const uint32_t *b = bits + (size_t)f * cw_words;
+    T *o = out + (size_t)f * N;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = 4 * g + k;
+        if (i >= N) break;
+        T mag = noisy;
+        if (known && get_bit(known, i)) mag = known_mag;
+        if (punct && get_bit(punct, i)) mag = (T)0;
+        o[i] = get_bit(b, i) ? (T)(-mag) : mag;
+    }
+}
+
+// 5G-NR double-diagonal encoder (ML/nrldpc_encode.m:12-40), one CTA per frame, bits unpacked in
+// shared memory as bytes: cword = [msg | p1 | p2 p3 p4 | extension parities].
+__global__ void encode_nr_kernel(const uint32_t *__restrict__ msg, uint32_t *__restrict__ cword, int F, int Z, int brows,
+                                 int bcols, const int32_t *__restrict__ base, int msg_words, int cw_words)
+{
+    extern __shared__ unsigned char cw[];   // bcols*Z bytes + Z bytes temp
+    const int kb = bcols - brows, N = bcols * Z, K = kb * Z;
+    unsigned char *temp = cw + N;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int f = blockIdx.x; f < F; f += gridDim.x) {
+        const uint32_t *mf = msg + (size_t)f * msg_words;
+        for (int i = tid; i < N; i += nt) cw[i] = i < K ? (unsigned char)get_bit(mf, i) : 0;
+        __syncthreads();
+        // :18-23 temp = sum over rows 0..3 and message columns of mul_sh(msg_j, B(i,j))
+        for (int l = tid; l < Z; l += nt) {
+            unsigned s = 0;
+            for (int r = 0; r < 4; ++r)
+                for (int j = 0; j < kb; ++j) {
+                    const int sh = base[r * bcols + j];
+                    if (sh >= 0) s ^= cw[j * Z + (l + sh) % Z];
+                }
+            temp[l] = (unsigned char)(s & 1u);
+        }
+        __syncthreads();
+        // :24-29 p1 = mul_sh(temp, z - p1_sh)
+        const int p1_sh = base[1 * bcols + kb] == -1 ? base[2 * bcols + kb] : base[1 * bcols + kb];
+        for (int l = tid; l < Z; l += nt) cw[K + l] = temp[(l + Z - p1_sh) % Z];
+        __syncthreads();
+        // :30-37 p2..p4 (each needs the previous one)
+        for (int r = 0; r < 3; ++r) {
+            for (int l = tid; l < Z; l += nt) {
+                unsigned s = 0;
+                for (int j = 0; j < kb + r + 1; ++j) {
+                    const int sh = base[r * bcols + j];
+                    if (sh >= 0) s ^= cw[j * Z + (l + sh) % Z];
+                }
+                cw[(kb + r + 1) * Z + l] = (unsigned char)(s & 1u);
+            }
+            __syncthreads();
+        }
+        // :38-45 extension parities, independent of each other
+        for (int t = tid; t < (brows - 4) * Z; t += nt) {
+            const int r = 4 + t / Z, l = t % Z;
+            unsigned s = 0;
+            for (int j = 0; j < kb + 4; ++j) {
+                const int sh = base[r * bcols + j];
+                if (sh >= 0) s ^= cw[j * Z + (l + sh) % Z];
+            }
+            cw[(kb + r) * Z + l] = (unsigned char)(s & 1u);
+        }
+        __syncthreads();
+        uint32_t *of = cword + (size_t)f * cw_words;
+        for (int w = tid; w < cw_words; w += nt) {
+            uint32_t v = 0;
+            for (int b = 0; b < 32; ++b) {
+                const int i = 32 * w + b;
+                if (i < N) v |= (uint32_t)cw[i] << (31 - b);
+            }
+            of[w] = v;
+        }
+        __syncthreads();
+    }
+}
+
+inline int grid_for(long long items, int block) { return (int)((items + block - 1) / block); }
+
+}  // namespace
+
+int launch_syndrome_csr(const uint32_t *bits, uint32_t *syn, int F, int N, int M, int cw_words, int syn_words,
+                        const int32_t *row_ptr, const int32_t *col_idx, cudaStream_t st)
+{
+    (void)N;
+    if (F <= 0) return QLDPC_OK;
+    syndrome_csr_kernel<<<grid_for((long long)F * syn_words, 128), 128, 0, st>>>(bits, syn, F, M, cw_words, syn_words,
+                                                                                  row_ptr, col_idx);
+    QLDPC_CUDA(cudaGetLastError());
+    return QLDPC_OK;
+}
+
+int launch_gather_bits(const uint32_t *allbits, uint32_t *out, int F, int cw_words, int out_words, int K,
+                       const int32_t *info_pos, cudaStream_t st)
+{
+    if (F <= 0) return QLDPC_OK;
+    gather_bits_kernel<<<grid_for((long long)F * out_words, 128), 128, 0, st>>>(allbits, out, F, cw_words, out_words, K,
+                                                                                info_pos);
+    QLDPC_CUDA(cudaGetLastError());
+    return QLDPC_OK;
+}
+
+int launch_make_llr(const uint32_t *bits, const uint32_t *known, const uint32_t *punct, float noisy, float known_mag,
+                    int F, int N, int cw_words, int dtype, void *llr_out, cudaStream_t st)
+{
+    if (F <= 0) return QLDPC_OK;
+    const int grid = grid_for((long long)F * ((N + 3) / 4), 256);
+    switch (dtype) {
+    case QLDPC_DTYPE_F32:
+        make_llr_kernel<float><<<grid, 256, 0, st>>>(bits, known, punct, noisy, known_mag, F, N, cw_words, (float *)llr_out);
+        break;
+    case QLDPC_DTYPE_I16:
+        make_llr_kernel<int16_t><<<grid, 256, 0, st>>>(bits, known, punct, (int16_t)lrintf(noisy), (int16_t)lrintf(known_mag),
+                                                       F, N, cw_words, (int16_t *)llr_out);
+        break;
+    case QLDPC_DTYPE_I8:
+        make_llr_kernel<int8_t><<<grid, 256, 0, st>>>(bits, known, punct, (int8_t)lrintf(noisy), (int8_t)lrintf(known_mag), F,
+                                                      N, cw_words, (int8_t *)llr_out);
+        break;
+    default: return QLDPC_ERR_UNSUPPORTED;
+    }
+    QLDPC_CUDA(cudaGetLastError());
+    return QLDPC_OK;
+}
+
+int launch_encode_nr(const uint32_t *msg, uint32_t *cword, int F, int Z, int brows, int bcols, const int32_t *base,
+                     int msg_words, int cw_words, cudaStream_t st)
+{
+    if (F <= 0) return QLDPC_OK;
+    const int smem = bcols * Z + Z;
+    QLDPC_CUDA(cudaFuncSetAttribute(encode_nr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int block = ((Z + 31) / 32) * 32;
+    if (block > 1024) block = 1024;
+    if (block < 128) block = 128;
+    const int grid = F < 148 * 8 ? F : 148 * 8;
+    encode_nr_kernel<<<grid, block, smem, st>>>(msg, cword, F, Z, brows, bcols, base, msg_words, cw_words);
+    QLDPC_CUDA(cudaGetLastError());
+    return QLDPC_OK;
+}
+
+}  // namespace qldpc

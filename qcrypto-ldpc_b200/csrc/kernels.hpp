@@ -1,0 +1,90 @@
+// Kernel parameter blocks and launcher prototypes (host <-> device contract inside the library).
+#pragma once
+
+#include "qldpc_internal.hpp"
+
+namespace qldpc {
+
+// ---- layered int8, QC, Z % 4 == 0 ("zpack4" family) ------------------------------------------
+struct LayeredI8Params {
+    const int8_t *llr;        // F * N
+    const uint32_t *syn;      // F * syn_words (MSB-first) or null
+    uint32_t *out;            // F * out_words (MSB-first)
+    uint8_t *ok;              // F or null
+    uint16_t *iters;          // F or null
+    DevStats *stats;
+    const QcEdge *edges;      // nnz
+    const QcEdgeAux *aux;     // nnz
+    const QcLayer *layers;    // brows
+    int F;
+    int Z, W, ZW32;           // lanes, belief words per column (Z/4), 32-bit words per Z-bit vector
+    int brows, bcols, nnz, N;
+    int out_cols;             // block columns written to `out`
+    int out_words, syn_words; // per frame
+    int max_iter, early_stop;
+    int rule, offset, norm_eighths, msg_max;
+    int slots, tpg;           // frames in flight per CTA, threads per frame group
+    int tab_bytes;            // shared tables at the start of dynamic smem
+    int slot_bytes;           // bytes per frame slot
+    int off_R, off_hd, off_syn;  // byte offsets inside a slot (beliefs start at 0)
+};
+int launch_layered_i8(const LayeredI8Params &p, int grid, int smem_bytes, cudaStream_t st);
+int layered_i8_max_threads();
+
+// ---- generic layered (QC, any Z; f32 / i16 / i8) ---------------------------------------------
+struct LayeredGenParams {
+    const void *llr;
+    const uint32_t *syn;
+    uint32_t *allbits;        // F * cw_words, MSB-first, all N hard decisions
+    uint8_t *ok;
+    uint16_t *iters;
+    void *posterior;          // F * N (float or int32) or null
+    DevStats *stats;
+    const QcEdgeAux *aux;
+    const QcLayer *layers;
+    void *msg;                // F_resident * nnz * Z messages (global scratch)
+    void *app;                // F_resident * N beliefs (global scratch)
+    int F;
+    int Z, brows, bcols, nnz, N, M;
+    int cw_words, syn_words;
+    int max_iter, early_stop, syndrome_depth;
+    int rule, dtype;
+    float norm, offset;
+    int offset_int, norm_eighths, msg_max, app_max;
+};
+int launch_layered_generic(const LayeredGenParams &p, int grid, cudaStream_t st);
+
+// ---- flooding (any H; f32 / i16 / i8) -----------------------------------------------------------
+struct FloodParams {
+    const void *llr;
+    const uint32_t *syn;
+    uint32_t *allbits;
+    uint8_t *ok;
+    uint16_t *iters;
+    void *posterior;
+    DevStats *stats;
+    const int32_t *row_ptr, *col_idx, *var_ptr, *var_edge;
+    void *c2v;                // grid * E messages (global scratch) when they do not fit in smem
+    void *post;               // grid * N
+    int F, N, M, E;
+    int cw_words, syn_words;
+    int max_iter, early_stop, syndrome_depth;
+    int rule, dtype;
+    float norm, offset;
+    int offset_int, norm_eighths, vmax;
+    int use_smem;             // messages + posteriors in shared memory
+};
+int launch_flooding(const FloodParams &p, int grid, int block, int smem_bytes, cudaStream_t st);
+
+// ---- bit-level helpers ---------------------------------------------------------------------------
+// syndrome of packed frames; QC codes use word-wise rotate+XOR, others a CSR gather
+int launch_syndrome_csr(const uint32_t *bits, uint32_t *syn, int F, int N, int M, int cw_words, int syn_words,
+                        const int32_t *row_ptr, const int32_t *col_idx, cudaStream_t st);
+int launch_gather_bits(const uint32_t *allbits, uint32_t *out, int F, int cw_words, int out_words, int K,
+                       const int32_t *info_pos, cudaStream_t st);
+int launch_make_llr(const uint32_t *bits, const uint32_t *known, const uint32_t *punct, float noisy, float known_mag,
+                    int F, int N, int cw_words, int dtype, void *llr_out, cudaStream_t st);
+int launch_encode_nr(const uint32_t *msg, uint32_t *cword, int F, int Z, int brows, int bcols, const int32_t *base,
+                     int msg_words, int cw_words, cudaStream_t st);
+
+}  // namespace qldpc

@@ -1,0 +1,126 @@
+// Internal host-side types of libqldpc_b200 (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/qldpc.h"
+
+namespace qldpc {
+
+// ---- parity-check matrix on the host ------------------------------------------------------
+struct HostCode {
+    int n = 0, m = 0, k = 0, edges = 0;
+    // CSR by check, variables ascending inside a check (edge id = position in col_idx)
+    std::vector<int32_t> row_ptr, col_idx;
+    // CSC by variable: var_ptr[n+1], var_edge[e] = CSR edge id, checks ascending inside a variable
+    std::vector<int32_t> var_ptr, var_edge;
+    // quasi-cyclic description (z == 0 for alist / CSR codes)
+    int z = 0, base_rows = 0, base_cols = 0;
+    std::vector<int32_t> base;  // base_rows*base_cols, -1 = zero block, else shift in [0,z)
+    std::vector<int32_t> info_pos;
+    int max_chk_degree = 0, max_var_degree = 0;
+
+    void finalize_from_csr();                   // sorts rows, builds CSC + degree stats, default info_pos
+    bool has_nr_core() const;                   // NR double-diagonal parity structure (for the encoder)
+};
+
+int parse_alist(const std::string &path, HostCode &out);
+int parse_qc(const std::string &path, HostCode &out);
+int build_qc(const int32_t *base, int rows, int cols, int z, HostCode &out);
+
+// ---- device-side tables ---------------------------------------------------------------------
+// One entry per non-zero block of the base matrix, row-major, columns ascending: the layer
+// schedule of ML/BPSK_nrldpc_sim_FP.m:45-47.
+struct QcEdge {          // 16 bytes, read as one int4 broadcast
+    int32_t off0;        // byte offset of the belief word for a lane that does not wrap
+    int32_t off1;        // ... for a lane that wraps past the end of the column
+    int32_t thresh;      // lane index (in words) from which the wrap happens
+    uint16_t selA0;      // PRMT selector (bytes -> half2 pair A) without wrap
+    uint16_t selA1;      // ... with wrap
+};
+struct QcEdgeAux {       // 8 bytes
+    uint16_t selW0, selW1;   // PRMT selectors packing two half2 pairs back into a belief word
+    int16_t col;             // block column
+    int16_t shift;           // shift in [0,z)
+};
+struct QcLayer {
+    int32_t edge_begin;
+    int32_t degree;
+};
+
+struct CudaCheck {
+    static thread_local std::string last;
+    static int fail(cudaError_t e, const char *what);
+};
+#define QLDPC_CUDA(expr)                                                         \
+    do {                                                                         \
+        cudaError_t _e = (expr);                                                 \
+        if (_e != cudaSuccess) return ::qldpc::CudaCheck::fail(_e, #expr);       \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    int ensure(size_t count) {
+        if (count <= n) return QLDPC_OK;
+        release();
+        if (cudaMalloc(&p, count * sizeof(T)) != cudaSuccess) { p = nullptr; return QLDPC_ERR_NOMEM; }
+        n = count;
+        return QLDPC_OK;
+    }
+    int upload(const std::vector<T> &v) {
+        if (int r = ensure(v.size() ? v.size() : 1)) return r;
+        if (!v.empty() && cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess)
+            return QLDPC_ERR_CUDA;
+        return QLDPC_OK;
+    }
+};
+
+// device statistics block, layout shared with the kernels
+struct DevStats {
+    unsigned long long frames, failures, iter_sum;
+    unsigned long long hist[QLDPC_ITER_HIST_BINS];
+};
+
+}  // namespace qldpc
+
+// ---- opaque handles of the C ABI -------------------------------------------------------------
+struct qldpc_code {
+    qldpc::HostCode h;
+};
+
+struct qldpc_decoder {
+    qldpc::HostCode code;
+    qldpc_decoder_config cfg{};
+    int kernel_family = 0;            // see KF_* in api.cpp
+    const char *kernel_name = "none";
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    int norm_eighths = 8;             // integer NMS factor k/8
+    int offset_int = 0;
+    int out_words = 0, syn_words = 0, cw_words = 0, out_bits = 0;
+    bool info_is_prefix = true;       // info bits are [0,k): kernels write them directly
+    uint64_t kernel_launches = 0;
+
+    // tables
+    qldpc::DevBuf<qldpc::QcEdge> d_qc_edges;
+    qldpc::DevBuf<qldpc::QcEdgeAux> d_qc_aux;
+    qldpc::DevBuf<qldpc::QcLayer> d_qc_layers;
+    qldpc::DevBuf<int32_t> d_row_ptr, d_col_idx, d_var_ptr, d_var_edge, d_info_pos;
+    qldpc::DevBuf<qldpc::DevStats> d_stats;
+    // scratch (grown on demand)
+    qldpc::DevBuf<uint8_t> d_scratch;       // messages / beliefs that do not fit on chip
+    qldpc::DevBuf<uint32_t> d_allbits;      // all-n hard decisions when info bits must be gathered
+    // staging for the host-pointer entry points
+    qldpc::DevBuf<uint8_t> d_in, d_out;
+    qldpc::DevBuf<uint32_t> d_syn;
+    // layered int8 launch geometry
+    int li8_slots = 0, li8_tpg = 0, li8_smem = 0, li8_grid = 0, li8_dcb = 0;
+};

@@ -1,0 +1,138 @@
+"""Parity of the CUDA layered int8 path (through the C ABI) against the CPU oracle.
+Bar: bit-exact decoded bits, syndrome-ok flag and iteration count."""
+import numpy as np
+import pytest
+
+from conftest import make_frames
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_case(q, O, data_dir, name, F, qber, mag, mode, rule, n_ite, early, offset=2, k8=6, out_all=True, seed=1,
+              expect_kernel="layered_i8_zpack4", random_llr=False):
+    path = "%s/%s" % (data_dir, name)
+    oc = O.Code.from_qc(path)
+    if random_llr:   # stress: arbitrary int8 LLRs incl. -128 / 127 saturation, random syndrome
+        rng = np.random.default_rng(seed)
+        llr = rng.integers(-128, 128, size=(F, oc.N)).astype(np.int32)
+        syn = rng.integers(0, 2, size=(F, oc.M)).astype(np.uint8) if mode == "syndrome" else None
+    else:
+        llr, syn, _ = make_frames(O, oc, F, qber, mag, 31, mode, seed)
+    code = q.Code.from_qc_file(path)
+    dec = q.Decoder(code, schedule=q.SCHED_LAYERED, rule=rule, dtype=q.DTYPE_I8, max_iter=n_ite, early_stop=early,
+                    norm_factor=k8 / 8.0, offset=float(offset), out_mode=q.OUT_ALL if out_all else q.OUT_INFO)
+    assert dec.kernel_name == expect_kernel
+    syn_packed = None if syn is None else q.pack_bits(syn)
+    out, ok, iters, _ = dec.decode(llr.astype(np.int8), syn_packed)
+    nbits = oc.N if out_all else oc.K
+    got = q.unpack_bits(out, nbits)
+    orule = O.RULE_NMS if rule == q.RULE_NMS else O.RULE_OMS
+    hard, oit, ook, _ = oc.batch_layered_fixed_i8(llr.astype(np.int8), syn, rule=orule, n_ite=n_ite, early_stop=early,
+                                                  offset=offset, norm_eighths=k8)
+    bad_frames = np.nonzero((got != hard[:, :nbits]).any(axis=1))[0]
+    assert bad_frames.size == 0, "bit mismatch in frames %s (first frame: %d differing bits, cols %s)" % (
+        bad_frames[:8], (got[bad_frames[0]] != hard[bad_frames[0], :nbits]).sum(),
+        np.unique(np.nonzero(got[bad_frames[0]] != hard[bad_frames[0], :nbits])[0] // oc.Z)[:16])
+    assert (iters == oit).all(), "iteration mismatch: gpu %s oracle %s" % (iters[:16], oit[:16])
+    assert (ok == ook).all()
+    st = dec.stats()
+    assert st["frames"] == F and st["iter_sum"] == int(oit.sum()) and st["failures"] == int((~ook).sum())
+    assert st["kernel_launches"] >= 1
+    dec.close()
+    return iters, ok
+
+
+@pytest.mark.parametrize("mode", ["parity", "syndrome"])
+@pytest.mark.parametrize("rule,k8,offset", [("nms", 6, 0), ("oms", 8, 2), ("nms", 8, 0), ("nms", 7, 0)])
+def test_bg1_z384_qber3(q, O, data_dir, mode, rule, k8, offset):
+    r = q.RULE_NMS if rule == "nms" else q.RULE_OMS
+    iters, ok = _run_case(q, O, data_dir, "NR_1_1_384.qc", 48, 0.03, 14, mode, r, 10, True, offset=offset, k8=k8)
+    assert ok.all()
+
+
+def test_bg1_z384_fixed_iterations_matlab_constants(q, O, data_dir):
+    # ML/BPSK_nrldpc_sim_FP.m constants: offset 2, no early stop; 20 iterations cut to 6 for test time
+    _run_case(q, O, data_dir, "NR_1_1_384.qc", 24, 0.06, 11, "syndrome", q.RULE_OMS, 6, False, offset=2)
+
+
+def test_bg1_z384_info_only_output(q, O, data_dir):
+    _run_case(q, O, data_dir, "NR_1_1_384.qc", 16, 0.03, 14, "parity", q.RULE_NMS, 10, True, out_all=False)
+
+
+def test_bg1_z384_failing_frames_high_qber(q, O, data_dir):
+    # far above threshold for pure syndrome mode: decoder must fail the same way the oracle does
+    iters, ok = _run_case(q, O, data_dir, "NR_1_1_384.qc", 12, 0.20, 5, "syndrome", q.RULE_NMS, 5, True)
+    assert not ok.all()
+
+
+@pytest.mark.parametrize("mode", ["parity", "syndrome"])
+def test_bg1_z384_random_saturating_llrs(q, O, data_dir, mode):
+    # arbitrary int8 input incl. -128/127: exercises every clip in the datapath
+    _run_case(q, O, data_dir, "NR_1_1_384.qc", 12, 0, 0, mode, q.RULE_OMS, 4, True, offset=1, random_llr=True)
+    _run_case(q, O, data_dir, "NR_1_1_384.qc", 12, 0, 0, mode, q.RULE_NMS, 4, False, k8=5, random_llr=True, seed=7)
+
+
+@pytest.mark.parametrize("name,mag", [("NR_1_1_192.qc", 14), ("NR_2_3_112.qc", 14), ("NR_1_1_24.qc", 14),
+                                      ("NR_2_6_52.qc", 14), ("NR_1_7_240.qc", 14), ("NR_1_0_256.qc", 14)])
+def test_other_lifting_sizes(q, O, data_dir, name, mag):
+    # Z = 192, 112 (W not a multiple of 32), 24 and 52 (Z not a multiple of 32), 240, 256
+    _run_case(q, O, data_dir, name, 20, 0.03, mag, "parity", q.RULE_NMS, 10, True)
+    _run_case(q, O, data_dir, name, 20, 0.04, mag, "syndrome", q.RULE_OMS, 10, True, offset=1, seed=3)
+
+
+def test_wifi_n1944(q, O, data_dir):
+    # rate-1/2 N=1944 (Z=81 is not a multiple of 4 -> generic kernel)
+    path = "%s/wifi_n1944_r12.qc" % data_dir
+    oc = O.Code.from_qc(path)
+    rng = np.random.default_rng(5)
+    F = 16
+    x = rng.integers(0, 2, (F, oc.N)).astype(np.uint8)
+    e = (rng.random((F, oc.N)) < 0.04).astype(np.uint8)
+    syn = np.stack([oc.syndrome(x[f]) for f in range(F)])
+    llr = np.where(x ^ e, -12, 12).astype(np.int8)
+    code = q.Code.from_qc_file(path)
+    dec = q.Decoder(code, schedule=q.SCHED_LAYERED, rule=q.RULE_NMS, dtype=q.DTYPE_I8, max_iter=20, early_stop=True,
+                    norm_factor=0.75, out_mode=q.OUT_ALL)
+    assert dec.kernel_name == "layered_generic"
+    out, ok, iters, post = dec.decode(llr, q.pack_bits(syn), want_posterior=True)
+    hard, oit, ook, _ = oc.batch_layered_fixed_i8(llr, syn, rule=O.RULE_NMS, n_ite=20, early_stop=True, norm_eighths=6)
+    assert (q.unpack_bits(out, oc.N) == hard).all() and (iters == oit).all() and (ok == ook).all()
+    for f in range(3):
+        _, app, _, _ = oc.decode_layered_fixed(llr[f].astype(np.int32), syn[f], rule=O.RULE_NMS, n_ite=20, early_stop=True,
+                                               norm_eighths=6)
+        assert (post[f] == app).all()
+
+
+def test_full_batch_roundtrip_property(q, O, data_dir):
+    """BASELINE config-2 scale property test: encode -> BSC -> decode returns Alice's bits for every frame
+    (size-independent; the oracle is only sampled)."""
+    path = "%s/NR_1_1_384.qc" % data_dir
+    oc = O.Code.from_qc(path)
+    code = q.Code.from_qc_file(path)
+    dec = q.Decoder(code, schedule=q.SCHED_LAYERED, rule=q.RULE_NMS, dtype=q.DTYPE_I8, max_iter=10, early_stop=True,
+                    norm_factor=0.75, out_mode=q.OUT_INFO)
+    F = 4096
+    rng = np.random.default_rng(11)
+    msg = rng.integers(0, 2, (F, oc.K)).astype(np.uint8)
+    cw = q.unpack_bits(dec.encode_nr(q.pack_bits(msg)), oc.N)
+    assert (cw[:, :oc.K] == msg).all()
+    for f in (0, 1, F - 1):   # GPU encoder against the oracle's restatement of nrldpc_encode.m
+        assert (cw[f] == oc.nr_encode(msg[f])).all()
+    syn = dec.syndrome(q.pack_bits(cw))
+    assert not syn.any()
+    noisy = cw.copy()
+    noisy[:, :oc.K] ^= (rng.random((F, oc.K)) < 0.03).astype(np.uint8)
+    known = np.zeros(oc.N, np.uint8)
+    known[oc.K:] = 1
+    llr = dec.make_llr(q.pack_bits(noisy), 14.0, 31.0, known_mask=q.pack_bits(known))
+    assert llr.dtype == np.int8 and set(np.unique(llr)) <= {-31, -14, 14, 31}
+    out, ok, iters, _ = dec.decode(llr)
+    assert ok.all()
+    assert (q.unpack_bits(out, oc.K) == msg).all()
+    st = dec.stats()
+    assert st["frames"] == F and st["failures"] == 0
+    assert sum(st["iter_hist"]) == F and st["iter_sum"] == int(iters.sum())
+    # sampled oracle agreement on iteration counts
+    sel = rng.choice(F, 16, replace=False)
+    hard, oit, ook, _ = oc.batch_layered_fixed_i8(llr[sel], None, rule=O.RULE_NMS, n_ite=10, early_stop=True, norm_eighths=6)
+    assert (oit == iters[sel]).all() and ook.all()

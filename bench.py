@@ -1,0 +1,354 @@
+#!/usr/bin/env python3
+"""Headline benchmark: reconciled information Mbit/s of the LDPC decode hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): 5G-NR BG1 Z=384 (N=26112, K=8448), int8 layered normalised
+min-sum (factor 6/8), at most 10 iterations with early termination (the reference decoders run with
+enable_syndrome=true, BOOT/src/main.cpp:101), BSC QBER 3 %, 65536-frame batch per GPU, the reference's
+send-parity formulation (info LLR +-14, parity LLR +-31, zero syndrome).  A "step" is one pass of the
+decoder over the batch.  Frames are independent: with N GPUs every rank decodes its own batch (weak
+scaling), no collective on the decode path; only the FER / iteration statistics are reduced.
+
+`value`  = device-resident throughput (CUDA events around K launches of the decode kernel, max over ranks)
+`e2e`    = the same batch through the host-buffer C-ABI call qldpc_decode(): pinned host LLRs in,
+           packed bits / ok / iteration counts out, copies inside the timed region.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CODE_FILE = "NR_1_1_384.qc"
+QBER = 0.03
+LLR_NOISY, LLR_KNOWN = 14.0, 31.0      # ln((1-q)/q)=3.476 at scale 2^2 -> 14; known parity saturates the 6-bit range
+MAX_ITER = 10
+NORM = 0.75
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=65536, help="frames per GPU per step")
+    ap.add_argument("--fixed-iters", action="store_true", help="no early termination (10 full iterations)")
+    ap.add_argument("--rule", default="nms", choices=["nms", "oms"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ helpers
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            p = [x.strip() for x in l.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1])); pw.append(float(p[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_run(frames_llr, seconds, steps=1, warmup=0, threads=0):
+    """times the CPU restatement (oracle 'port') on a bounded sample of the workload, all host threads"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    oc = O.Code.from_qc(os.path.join(ROOT, "qcrypto-ldpc_b200", "data", CODE_FILE))
+    rule = O.RULE_NMS
+    # calibrate on a few frames, then size the sample for ~`seconds`
+    t0 = time.perf_counter()
+    oc.batch_layered_fixed_i8(frames_llr[:16], None, rule=rule, n_ite=MAX_ITER, early_stop=True, norm_eighths=6, n_threads=threads)
+    dt = max(time.perf_counter() - t0, 1e-4)
+    n = int(max(16, min(len(frames_llr), 16 * seconds / dt)))
+    sample = frames_llr[:n]
+    for _ in range(warmup):
+        oc.batch_layered_fixed_i8(sample[: max(16, n // 8)], None, rule=rule, n_ite=MAX_ITER, early_stop=True, norm_eighths=6, n_threads=threads)
+    t0 = time.perf_counter()
+    nt = 1
+    for _ in range(steps):
+        hard, iters, ok, nt = oc.batch_layered_fixed_i8(sample, None, rule=rule, n_ite=MAX_ITER, early_stop=True,
+                                                        norm_eighths=6, n_threads=threads)
+    dt = time.perf_counter() - t0
+    mbps = steps * n * oc.K / dt / 1e6
+    return {"value": mbps, "unit": "Mbit/s", "cores": int(nt), "kind": "port",
+            "sample": "%d frames x %d step(s) of the same workload (BG1 Z=384 int8 layered NMS 6/8, early stop, QBER 3%%), "
+                      "oracle/qldpc_oracle.c over %d pthreads" % (n, steps, nt),
+            "ms_per_step": dt / steps * 1e3, "frames": n, "ok_frac": float(ok.mean()), "mean_iters": float(iters.mean())}
+
+
+def synth_frames_cpu(n, seed=1234):
+    """small CPU-side sample of the synthetic workload for the reference arm (numpy + oracle encoder)"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    oc = O.Code.from_qc(os.path.join(ROOT, "qcrypto-ldpc_b200", "data", CODE_FILE))
+    rng = np.random.default_rng(seed)
+    llr = np.empty((n, oc.N), dtype=np.int8)
+    for f in range(n):
+        cw = oc.nr_encode(rng.integers(0, 2, oc.K).astype(np.uint8))
+        e = (rng.random(oc.K) < QBER).astype(np.uint8)
+        llr[f, :oc.K] = np.where(cw[:oc.K] ^ e, -LLR_NOISY, LLR_NOISY)
+        llr[f, oc.K:] = np.where(cw[oc.K:], -LLR_KNOWN, LLR_KNOWN)
+    return llr, oc
+
+
+def workload_config(args, world):
+    return {"workload": "5G-NR BG1 Z=384 (N=26112,K=8448) int8 layered normalised min-sum 6/8, max %d iters, %s, BSC QBER 3%%, "
+                        "send-parity formulation (info LLR +-14, parity +-31), %d frames per GPU per step" %
+                        (MAX_ITER, "no early stop" if args.fixed_iters else "early termination on zero syndrome", args.frames),
+            "code": CODE_FILE, "frames_per_gpu": args.frames, "global_frames": args.frames * world,
+            "info_bits_per_frame": 8448, "codeword_bits": 26112, "qber": QBER, "max_iter": MAX_ITER,
+            "early_stop": not args.fixed_iters, "rule": args.rule, "parallelism": "frame-sharded x%d, no collective" % world,
+            "l2_policy": "inputs (1.71 GB of int8 LLRs per step) are larger than the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------- reference arm
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    llr, oc = synth_frames_cpu(2048 if args.cpu_seconds > 5 else 256)
+    r = cpu_reference_run(llr, args.cpu_seconds, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": "reconciled info Mbit/s", "value": r["value"], "unit": "Mbit/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "i8", "data": "synthetic",
+            "config": workload_config(args, world),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "the reference's own LDPC arithmetic (AFF3CT v2.3.5, MATLAB) cannot be built here; this arm times the "
+                    "CPU restatement of it (oracle/, kind=port) on the host cores; each step is a bounded sample"}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- ours
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    q = importlib.import_module("qcrypto-ldpc_b200")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    code = q.Code.from_qc_file(q.data_path(CODE_FILE))
+    rule = q.RULE_NMS if args.rule == "nms" else q.RULE_OMS
+    dec = q.Decoder(code, schedule=q.SCHED_LAYERED, rule=rule, dtype=q.DTYPE_I8, max_iter=MAX_ITER,
+                    early_stop=not args.fixed_iters, norm_factor=NORM, offset=2.0, out_mode=q.OUT_INFO, device=local_rank)
+    assert dec.kernel_name == "layered_i8_zpack4"
+    F, N, K = args.frames, code.n, code.k
+    st = torch.cuda.current_stream().cuda_stream
+
+    # ---- synthetic sifted-key frames, generated on the device with the library's own encoder / LLR kernels
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    kw = K // 32
+    msg = torch.randint(-2**31, 2**31 - 1, (F, kw), dtype=torch.int32, device=dev, generator=g)
+    cw = torch.empty((F, dec.cw_words), dtype=torch.int32, device=dev)
+    dec.encode_nr_device(msg.data_ptr(), F, cw.data_ptr(), st)
+    # BSC on the information part: flip each of the K bits with probability QBER
+    flips = (torch.rand((F, K), device=dev, generator=g) < QBER).view(F, kw, 32)
+    weights = (2 ** torch.arange(31, -1, -1, device=dev, dtype=torch.int64))
+    fw = (flips.to(torch.int64) * weights).sum(dim=2)
+    fw = torch.where(fw >= 2**31, fw - 2**32, fw).to(torch.int32)
+    noisy = cw.clone()
+    noisy[:, :kw] ^= fw
+    del flips, weights, fw
+    known = torch.zeros(dec.cw_words, dtype=torch.int32, device=dev)
+    known[kw:] = -1
+    llr = torch.empty((F, N), dtype=torch.int8, device=dev)
+    dec.make_llr_device(noisy.data_ptr(), known.data_ptr(), 0, LLR_NOISY, LLR_KNOWN, F, llr.data_ptr(), st)
+    out = torch.empty((F, dec.out_words), dtype=torch.int32, device=dev)
+    ok = torch.empty(F, dtype=torch.uint8, device=dev)
+    iters = torch.empty(F, dtype=torch.int16, device=dev)
+    torch.cuda.synchronize()
+
+    def step():
+        dec.decode_device(llr.data_ptr(), 0, F, out.data_ptr(), ok.data_ptr(), iters.data_ptr(), 0, st)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    # correctness of what is being timed: every frame reconciled to Alice's bits
+    assert bool((out[:, :kw] == msg).all()) and bool(ok.all()), "decoded bits differ from Alice's key"
+    dec.reset_stats()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    torch.cuda.synchronize()
+    ev[0].record()
+    for s in range(args.steps):
+        step()
+        ev[s + 1].record()
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[s].elapsed_time(ev[s + 1]) for s in range(args.steps)]
+    stats = dec.stats()
+    launches = stats["kernel_launches"]
+
+    # ---- end to end through the host-buffer C ABI (pinned host buffers, copies inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        h_llr = torch.empty((F, N), dtype=torch.int8).pin_memory()
+        h_llr.copy_(llr)
+        h_out = torch.empty((F, dec.out_words), dtype=torch.int32).pin_memory()
+        h_ok = torch.empty(F, dtype=torch.uint8).pin_memory()
+        h_it = torch.empty(F, dtype=torch.int16).pin_memory()
+        L = q.lib()
+
+        def e2e_step():
+            rc = L.qldpc_decode(dec.h, h_llr.data_ptr(), None, F, h_out.data_ptr(), h_ok.data_ptr(), h_it.data_ptr(), None)
+            assert rc == 0, rc
+
+        for _ in range(min(args.warmup, 2)):
+            e2e_step()
+        e2e_steps = max(2, min(args.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        e2e_s = time.perf_counter() - t0          # qldpc_decode synchronises before returning
+        barrier()
+        assert bool((h_out[:, :kw].to(dev) == msg).all()) and bool(h_ok.all())
+        e2e = {"s": e2e_s, "steps": e2e_steps, "h2d": F * N, "d2h": F * (dec.out_words * 4 + 1 + 2)}
+        del h_llr
+
+    # ---- reductions over ranks: time = max, statistics = sum (host side)
+    vec = torch.tensor([total_ms, e2e["s"] / e2e["steps"] * 1e3 if e2e else 0.0], dtype=torch.float64)
+    cnt = torch.tensor([stats["frames"], stats["failures"], stats["iter_sum"], launches] + stats["iter_hist"][:16], dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(vec, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    if rank != 0:
+        return
+    total_ms, e2e_ms = float(vec[0]), float(vec[1])
+    frames_total = F * world * args.steps
+    value = frames_total * K / (total_ms * 1e-3) / 1e6
+    mean_iters = float(cnt[2]) / max(1, int(cnt[0]))
+    fer = float(cnt[1]) / max(1, int(cnt[0]))
+
+    peak, peak_src = measured_peak_hbm()
+    bytes_per_frame = N + dec.out_words * 4 + 1 + 2          # int8 LLRs in; packed info bits, ok, iters out
+    launch_ms = float(np.mean(per_launch_ms))
+    achieved = bytes_per_frame * F / (launch_ms * 1e-3) / 1e9
+    smem_bytes_per_frame = mean_iters * code.edges * 4        # read L, read R, write L, write R per edge per iteration
+    roofline = {"bound": "hbm", "kernel": "layered_i8_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                "bytes_per_frame": bytes_per_frame, "launch_ms": launch_ms,
+                "note": "working set is on chip: the kernel is issue / shared-memory bound, not HBM bound (DESIGN.md)",
+                "onchip": {"smem_algorithmic_bytes_per_frame": smem_bytes_per_frame,
+                           "smem_GBps": smem_bytes_per_frame * F / (launch_ms * 1e-3) / 1e9,
+                           "edge_updates_per_s": mean_iters * code.edges * F / (launch_ms * 1e-3)}}
+
+    cpu = None
+    if not args.no_cpu:
+        n_cpu = 1024
+        cpu = cpu_reference_run(llr[:n_cpu].cpu().numpy(), args.cpu_seconds)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    line = {"metric": "reconciled info Mbit/s", "value": value, "unit": "Mbit/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "i8", "data": "synthetic", "config": workload_config(args, world),
+            "fer": fer, "mean_iters": mean_iters, "iter_hist": [int(x) for x in cnt[4:16]],
+            "codeword_basis_mbps": value * N / K,
+            "clocks": clocks, "gpu_launches": int(cnt[3]), "roofline": roofline, "cpu_baseline": cpu}
+    if e2e:
+        line["e2e"] = {"value": F * world * K / (e2e_ms * 1e-3) / 1e6, "unit": "Mbit/s", "h2d_bytes_per_step": e2e["h2d"] * world,
+                       "d2h_bytes_per_step": e2e["d2h"] * world, "ms_per_step": e2e_ms, "steps": e2e["steps"],
+                       "api": "qldpc_decode (host pointers, pinned int8 LLRs, 2-stream chunked pipeline)"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

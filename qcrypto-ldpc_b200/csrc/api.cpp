@@ -36,62 +36,114 @@ uint16_t unpack_selector(int rho)   // bytes rho, rho+1 -> low bytes of the two 
     return (uint16_t)((rho & 3) | (4 << 4) | (((rho + 1) & 3) << 8) | (4 << 12));
 }
 
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// generic QC tables (generic layered kernel, syndrome phase of the int8 kernel)
 int build_qc_tables(qldpc_decoder *d)
 {
     const HostCode &c = d->code;
-    std::vector<QcEdge> edges;
     std::vector<QcEdgeAux> aux;
     std::vector<QcLayer> layers;
-    const int W = c.z / 4;
+    const int ZW32 = (c.z + 31) / 32;
     for (int r = 0; r < c.base_rows; ++r) {
-        QcLayer ly{(int32_t)edges.size(), 0};
+        QcLayer ly{(int32_t)aux.size(), 0};
         for (int col = 0; col < c.base_cols; ++col) {
             const int s = c.base[r * c.base_cols + col];
             if (s < 0) continue;
-            QcEdge e{};
-            QcEdgeAux a{};
-            a.col = (int16_t)col;
-            a.shift = (int16_t)s;
-            if (W > 0 && c.z % 4 == 0) {
-                const int q = s / W, rr = s % W;
-                e.off0 = (col * W + rr) * 4;
-                e.off1 = (col * W + rr - W) * 4;
-                e.thresh = W - rr;
-                e.selA0 = unpack_selector(q);
-                e.selA1 = unpack_selector(q + 1);
-                a.selW0 = pack_selector(q);
-                a.selW1 = pack_selector(q + 1);
-            }
-            edges.push_back(e);
-            aux.push_back(a);
+            aux.push_back(QcEdgeAux{col * ZW32, (int16_t)col, (int16_t)s});
             ++ly.degree;
         }
         layers.push_back(ly);
     }
-    if (int r = d->d_qc_edges.upload(edges)) return r;
     if (int r = d->d_qc_aux.upload(aux)) return r;
     if (int r = d->d_qc_layers.upload(layers)) return r;
     return QLDPC_OK;
 }
 
-int round_up(int x, int m) { return (x + m - 1) / m * m; }
-
-// shared-memory geometry of the layered int8 kernel; returns false when one frame does not fit
-bool plan_layered_i8(qldpc_decoder *d, LayeredI8Params &p)
+// Tables and shared-memory geometry of the layered int8 kernel; false when the code does not fit
+// the kernel's assumptions (the caller then uses the generic kernel).
+bool plan_layered_i8(qldpc_decoder *d, LayeredI8Params &p, bool upload)
 {
     const HostCode &c = d->code;
-    if (c.z <= 0 || c.z % 4 != 0 || c.max_chk_degree > 20) return false;
+    if (c.z <= 0 || c.z % 4 != 0 || c.max_chk_degree > 20 || d->cfg.max_iter < 1) return false;
     const int W = c.z / 4, ZW32 = (c.z + 31) / 32;
     const int nnz = c.edges / c.z;
     const int tpg = round_up(W, 32);
     if (tpg > layered_i8_max_threads()) return false;
+    const int R = c.base_rows, C = c.base_cols;
+    auto B = [&](int r, int col) { return c.base[r * C + col]; };
+    const bool fast_bits = (W % 32 == 0) && (c.z % 32 == 0);
+
+    // column weights; extension columns = weight 1, shift 0, and the LAST edge of their row
+    std::vector<int> colw(C, 0), deg(R, 0), last_col(R, -1);
+    for (int r = 0; r < R; ++r)
+        for (int col = 0; col < C; ++col)
+            if (B(r, col) >= 0) { colw[col]++; deg[r]++; last_col[r] = col; }
+    std::vector<int> has_ext(R, 0);
+    std::vector<char> is_ext_col(C, 0);
+    if (fast_bits)
+        for (int r = 0; r < R; ++r)
+            if (deg[r] >= 2 && colw[last_col[r]] == 1 && B(r, last_col[r]) == 0) { has_ext[r] = 1; is_ext_col[last_col[r]] = 1; }
+
+    // register rows: the kRegRows heaviest rows, if they all have 19 or 20 edges and no extension edge
+    std::vector<int> reg_idx(R, -1);
+    int regdc = 0;
+    if (R >= layered_i8_reg_rows()) {
+        std::vector<int> order(R);
+        for (int r = 0; r < R; ++r) order[r] = r;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return deg[a] > deg[b]; });
+        bool ok = true;
+        for (int k = 0; k < layered_i8_reg_rows(); ++k) ok = ok && !has_ext[order[k]] && (deg[order[k]] == 19 || deg[order[k]] == 20);
+        for (int k = layered_i8_reg_rows(); k < R; ++k) ok = ok && (deg[order[k]] - has_ext[order[k]] <= 10);
+        if (ok) {
+            regdc = 20;
+            for (int k = 0; k < layered_i8_reg_rows(); ++k) reg_idx[order[k]] = k;
+        }
+    }
+
+    std::vector<Li8Edge> edges;
+    std::vector<Li8Layer> layers;
+    int n_store = 0;
+    for (int r = 0; r < R; ++r) {
+        Li8Layer ly{};
+        ly.edge_begin = (int32_t)edges.size();
+        ly.degree = (int16_t)deg[r];
+        ly.has_ext = (int16_t)has_ext[r];
+        ly.n_core = (int16_t)(deg[r] - has_ext[r]);
+        ly.reg_idx = (int16_t)reg_idx[r];
+        ly.r_off = reg_idx[r] >= 0 ? -1 : n_store;
+        if (reg_idx[r] < 0) n_store += ly.n_core;
+        for (int col = 0; col < C; ++col) {
+            const int s = B(r, col);
+            if (s < 0) continue;
+            const int q = s / W, rr = s % W;
+            Li8Edge e{};
+            e.off0 = (col * W + rr) * 4;
+            e.off1 = (col * W + rr - W) * 4;
+            e.thresh = W - rr;
+            e.hdw = col * ZW32;
+            e.selA0 = unpack_selector(q);
+            e.selA1 = unpack_selector(q + 1);
+            e.selW0 = pack_selector(q);
+            e.selW1 = pack_selector(q + 1);
+            edges.push_back(e);
+        }
+        layers.push_back(ly);
+    }
+    std::vector<uint16_t> pack_cols;
+    for (int col = 0; col < C; ++col)
+        if (!is_ext_col[col]) pack_cols.push_back((uint16_t)col);
+
     p.Z = c.z; p.W = W; p.ZW32 = ZW32;
-    p.brows = c.base_rows; p.bcols = c.base_cols; p.nnz = nnz; p.N = c.n;
-    p.tab_bytes = round_up(nnz * (16 + 16 + (int)sizeof(QcEdgeAux)) + c.base_rows * (int)sizeof(QcLayer), 16);
-    const int L_bytes = c.base_cols * W * 4;
-    const int R_bytes = nnz * W * 4;
-    const int hd_bytes = round_up(c.base_cols * ZW32 * 4, 16);
-    const int syn_bytes = round_up(c.base_rows * ZW32 * 4, 16);
+    p.brows = R; p.bcols = C; p.nnz = nnz; p.N = c.n;
+    p.n_store = n_store;
+    p.n_pack = (int)pack_cols.size();
+    p.regdc = regdc;
+    p.tab_bytes = round_up(nnz * (int)(sizeof(Li8Edge) + sizeof(QcEdgeAux)) + R * (int)sizeof(Li8Layer) + C * 2, 16);
+    const int L_bytes = C * W * 4;
+    const int R_bytes = n_store * W * 4;
+    const int hd_bytes = round_up(C * ZW32 * 4, 16);
+    const int syn_bytes = round_up(R * ZW32 * 4, 16);
     p.off_R = round_up(L_bytes, 16);
     p.off_hd = p.off_R + round_up(R_bytes, 16);
     p.off_syn = p.off_hd + hd_bytes;
@@ -106,6 +158,12 @@ bool plan_layered_i8(qldpc_decoder *d, LayeredI8Params &p)
     d->li8_slots = slots;
     d->li8_tpg = tpg;
     d->li8_smem = p.tab_bytes + slots * p.slot_bytes;
+    d->li8_regdc = regdc;
+    d->li8_n_store = n_store;
+    d->li8_n_pack = p.n_pack;
+    if (upload) {
+        if (d->d_li8_edges.upload(edges) || d->d_li8_layers.upload(layers) || d->d_li8_pack_cols.upload(pack_cols)) return false;
+    }
     return true;
 }
 
@@ -304,7 +362,7 @@ extern "C" int qldpc_decoder_create(const qldpc_code *code, const qldpc_decoder_
     if (cfg->schedule == QLDPC_SCHED_LAYERED) {
         LayeredI8Params p{};
         const bool fast = cfg->dtype == QLDPC_DTYPE_I8 && d->cfg.app_max == 127 && d->cfg.msg_max <= 63 &&
-                          plan_layered_i8(d, p);
+                          plan_layered_i8(d, p, true);
         if (fast) {
             d->kernel_family = KF_LAYERED_I8;
             d->kernel_name = "layered_i8_zpack4";
@@ -382,7 +440,7 @@ extern "C" int qldpc_decode_device(qldpc_decoder *dec, const void *d_llr, const 
 
     if (family == KF_LAYERED_I8) {
         LayeredI8Params p{};
-        if (!plan_layered_i8(d, p)) return QLDPC_ERR_UNSUPPORTED;
+        if (!plan_layered_i8(d, p, false)) return QLDPC_ERR_UNSUPPORTED;
         const bool direct = cfg.out_mode == QLDPC_OUT_ALL || d->info_is_prefix;
         if (!direct)
             if ((rc = d->d_allbits.ensure((size_t)n_frames * d->cw_words))) return rc;
@@ -390,7 +448,7 @@ extern "C" int qldpc_decode_device(qldpc_decoder *dec, const void *d_llr, const 
         p.syn = d_syndrome;
         p.out = direct ? d_out_bits : d->d_allbits.p;
         p.ok = d_ok; p.iters = d_iters; p.stats = d->d_stats.p;
-        p.edges = d->d_qc_edges.p; p.aux = d->d_qc_aux.p; p.layers = d->d_qc_layers.p;
+        p.edges = d->d_li8_edges.p; p.layers = d->d_li8_layers.p; p.aux = d->d_qc_aux.p; p.pack_cols = d->d_li8_pack_cols.p;
         p.F = n_frames;
         p.out_cols = (direct && cfg.out_mode == QLDPC_OUT_INFO) ? c.base_cols - c.base_rows : c.base_cols;
         p.out_words = (p.out_cols * c.z + 31) / 32;

@@ -13,12 +13,16 @@ struct LayeredI8Params {
     uint8_t *ok;              // F or null
     uint16_t *iters;          // F or null
     DevStats *stats;
-    const QcEdge *edges;      // nnz
+    const Li8Edge *edges;     // nnz
+    const Li8Layer *layers;   // brows
     const QcEdgeAux *aux;     // nnz
-    const QcLayer *layers;    // brows
+    const uint16_t *pack_cols;  // n_pack block columns whose hard decisions are packed from the beliefs
     int F;
     int Z, W, ZW32;           // lanes, belief words per column (Z/4), 32-bit words per Z-bit vector
     int brows, bcols, nnz, N;
+    int n_store;              // edges with a stored message (shared memory)
+    int n_pack;
+    int regdc;                // 0, or unrolled degree of the four register-resident rows
     int out_cols;             // block columns written to `out`
     int out_words, syn_words; // per frame
     int max_iter, early_stop;
@@ -30,6 +34,7 @@ struct LayeredI8Params {
 };
 int launch_layered_i8(const LayeredI8Params &p, int grid, int smem_bytes, cudaStream_t st);
 int layered_i8_max_threads();
+int layered_i8_reg_rows();
 
 // ---- generic layered (QC, any Z; f32 / i16 / i8) ---------------------------------------------
 struct LayeredGenParams {

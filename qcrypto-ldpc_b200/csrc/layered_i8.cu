@@ -18,6 +18,12 @@
 // intrinsics (__vsubss4 ...) are emulated with 5-10 instructions each on sm_100a.
 // Early termination: hard decisions are packed with warp ballots into Z-bit vectors and the
 // syndrome is evaluated word-wise with funnel shifts + XOR (a few % of an iteration).
+// Footprint diet so that TWO frames fit in one SM's 227 KB (BG1 Z=384: 105 KB per frame):
+//   - an edge into a weight-1, shift-0 column (the NR extension parities) stores no message and
+//     never rewrites the belief: belief - message is the channel LLR for ever, so the edge reads
+//     the channel byte, takes part in the min-sum, and only its a-posteriori SIGN is kept (ballot
+//     straight into the hard-decision vector);
+//   - the messages of the four heaviest rows (19 edges each in BG1) live in registers.
 #include <cuda_fp16.h>
 
 #include "kernels.hpp"
@@ -32,6 +38,7 @@ constexpr u32 kSignMask = 0x80008000u;
 constexpr u32 kInf2 = 0x03ff03ffu;     // 1023 ulp: larger than any message magnitude
 constexpr u32 kOne2 = 0x3c003c00u;     // 1.0h, 1.0h
 constexpr int kMaxBlock = 256;
+constexpr int kRegRows = 4;
 
 __device__ __forceinline__ __half2 h2(u32 x) { return *reinterpret_cast<__half2 *>(&x); }
 __device__ __forceinline__ u32 bits(__half2 h) { return *reinterpret_cast<u32 *>(&h); }
@@ -96,20 +103,26 @@ struct LayerCtx {
     u32 c128, c255;
     int norm_eighths;
     u32 negOff;           // -offset
+    u32 *hd;              // this slot's hard-decision vectors
+    int wis, lane, wq;    // warp in slot, lane, W/32
 };
 
 // One layer (block row) for the four check lanes of this thread.
 //   NK    rule: 0 = offset min-sum, 1..8 = normalised by NK/8, -1 = normalised, factor at run time
-//   DC    unrolled edge slots; EXACT: the row has exactly DC edges, else DC-1 or DC
+//   DC    unrolled slots of edges with a stored message; MODE 0: exactly DC, 1: DC-1 or DC
+//   EXT   one more edge follows into a weight-1 shift-0 column (no stored message, no belief update)
+//   REG   stored messages live in the register array Rr instead of shared memory
 //   Li    this thread's belief base address (slot beliefs + 4*i)
-//   Rrow  this thread's message word of the row's first edge; consecutive edges are W words apart
-//   etab  two int4 per edge: {off0, off1, thresh, -} {selA0, selA1, selW0, selW1}
-template <int NK, int DC, bool EXACT>
-__device__ __forceinline__ void process_layer(const LayerCtx &cx, char *Li, u32 *Rrow, int W, const int4 *etab, int dc,
-                                              int i, u32 synbits)
+//   Rrow  this thread's message word of the row's first stored edge; consecutive edges are W words apart
+//   etab  two int4 per edge: {off0, off1, thresh, hdw} {selA0, selA1, selW0, selW1}
+template <int NK, int DC, int MODE, bool EXT, bool REG, int RDC>
+__device__ __forceinline__ void process_layer(const LayerCtx &cx, char *Li, u32 *Rrow, u32 (&Rr)[RDC], int W,
+                                              const int4 *etab, int nc, int i, u32 synbits)
 {
-    u32 uA[DC], uB[DC], tA[DC], tB[DC], sw[DC];
-    char *ad[DC];
+    // register rows recompute the belief address / pack selector in the second pass (register budget)
+    constexpr int KEEP = REG ? 1 : DC;
+    u32 uA[DC], uB[DC], tA[DC], tB[DC], sw[KEEP];
+    char *ad[KEEP];
     // running sign product starts at the syndrome bit of each lane
     u32 m1A = kInf2 ^ (((synbits & 1u) << 15) | ((synbits & 2u) << 30));
     u32 m1B = kInf2 ^ (((synbits & 4u) << 13) | ((synbits & 8u) << 28));
@@ -117,16 +130,16 @@ __device__ __forceinline__ void process_layer(const LayerCtx &cx, char *Li, u32 
 
 #pragma unroll
     for (int j = 0; j < DC; ++j) {
-        if (EXACT || j < DC - 1 || j < dc) {
-            const int4 ed = etab[2 * j];       // off0, off1, thresh, -
+        if (MODE == 0 || j < DC - 1 || j < nc) {
+            const int4 ed = etab[2 * j];       // off0, off1, thresh, hdw
             const int4 sl = etab[2 * j + 1];   // selA0, selA1, selW0, selW1
             const bool wrap = i >= ed.z;
             char *a = Li + (wrap ? ed.y : ed.x);
             const u32 selA = wrap ? sl.y : sl.x;
-            sw[j] = wrap ? sl.w : sl.z;
-            ad[j] = a;
+            if constexpr (!REG) { sw[j] = wrap ? sl.w : sl.z; ad[j] = a; }
             const u32 X = *reinterpret_cast<const u32 *>(a);
-            const u32 Y = Rrow[j * W];
+            u32 Y;
+            if constexpr (REG) Y = Rr[j]; else Y = Rrow[j * W];
             const u32 xA = prmt(X, 0u, selA), xB = prmt(X, 0u, selA ^ 0x0202u);
             const u32 yA = prmt(Y, 0u, 0x4140u), yB = prmt(Y, 0u, 0x4342u);
             const u32 ua = hsub(xA, yA), ub = hsub(xB, yB);          // L - R_old  (:51)
@@ -138,6 +151,22 @@ __device__ __forceinline__ void process_layer(const LayerCtx &cx, char *Li, u32 
             m1A = min_xorsign_abs(m1A, ta);                           // first minimum and sign product (:60,:63)
             m1B = min_xorsign_abs(m1B, tb);
         }
+    }
+    u32 ueA = 0, ueB = 0, teA = 0, teB = 0;
+    int ehdw = 0;
+    if constexpr (EXT) {   // the extension edge: belief - message == channel LLR (see file header)
+        const int4 ed = etab[2 * nc];
+        const int4 sl = etab[2 * nc + 1];
+        const u32 X = *reinterpret_cast<const u32 *>(Li + ed.x);     // shift 0: never wraps
+        ehdw = ed.w;
+        ueA = hsub(prmt(X, 0u, sl.x), cx.c128);
+        ueB = hsub(prmt(X, 0u, sl.x ^ 0x0202u), cx.c128);
+        teA = hmin(hmax(ueA, cx.cLo), cx.cHi);
+        teB = hmin(hmax(ueB, cx.cLo), cx.cHi);
+        m2A = hmax(habs(m1A), hmin(habs(teA), m2A));
+        m2B = hmax(habs(m1B), hmin(habs(teB), m2B));
+        m1A = min_xorsign_abs(m1A, teA);
+        m1B = min_xorsign_abs(m1B, teB);
     }
     const u32 parA = m1A & kSignMask, parB = m1B & kSignMask;
     const u32 min1A = habs(m1A), min1B = habs(m1B);
@@ -155,7 +184,7 @@ __device__ __forceinline__ void process_layer(const LayerCtx &cx, char *Li, u32 
 
 #pragma unroll
     for (int j = 0; j < DC; ++j) {
-        if (EXACT || j < DC - 1 || j < dc) {
+        if (MODE == 0 || j < DC - 1 || j < nc) {
             const u32 eA = heq_mask(habs(tA[j]), min1A), eB = heq_mask(habs(tB[j]), min1B);
             // |t| == min1 ? c1 : c2, then the edge's own sign (:73-75)
             const u32 rA = ((eA & c1A) | (~eA & c2A)) ^ (tA[j] & kSignMask);
@@ -163,33 +192,65 @@ __device__ __forceinline__ void process_layer(const LayerCtx &cx, char *Li, u32 
             const u32 bA = hadd(rA, cx.c128), bB = hadd(rB, cx.c128); // biased new message
             const u32 lA = hmin(hadd_relu(uA[j], bA), cx.c255);       // clip(L - R_old + R_new) biased (:88-91)
             const u32 lB = hmin(hadd_relu(uB[j], bB), cx.c255);
-            Rrow[j * W] = prmt(bA, bB, 0x6420u);
-            *reinterpret_cast<u32 *>(ad[j]) = prmt(lA, lB, sw[j]);
+            const u32 Ynew = prmt(bA, bB, 0x6420u);
+            if constexpr (REG) {
+                Rr[j] = Ynew;
+                const int4 ed = etab[2 * j];
+                const int4 sl = etab[2 * j + 1];
+                const bool wrap = i >= ed.z;
+                *reinterpret_cast<u32 *>(Li + (wrap ? ed.y : ed.x)) = prmt(lA, lB, wrap ? sl.w : sl.z);
+            } else {
+                Rrow[j * W] = Ynew;
+                *reinterpret_cast<u32 *>(ad[j]) = prmt(lA, lB, sw[j]);
+            }
+        }
+    }
+    if constexpr (EXT) {   // only the sign of channel + new message is observable: ballot it into the hd vector
+        const u32 eA = heq_mask(habs(teA), min1A), eB = heq_mask(habs(teB), min1B);
+        const u32 rA = ((eA & c1A) | (~eA & c2A)) ^ (teA & kSignMask);
+        const u32 rB = ((eB & c1B) | (~eB & c2B)) ^ (teB & kSignMask);
+        const u32 aA = hadd(ueA, rA), aB = hadd(ueB, rB);
+        const u32 b0 = __ballot_sync(0xffffffffu, (int)(aA << 16) < 0);   // lane i
+        const u32 b1 = __ballot_sync(0xffffffffu, (int)aA < 0);           // lane i + W
+        const u32 b2 = __ballot_sync(0xffffffffu, (int)(aB << 16) < 0);   // lane i + 2W
+        const u32 b3 = __ballot_sync(0xffffffffu, (int)aB < 0);           // lane i + 3W
+        if (cx.lane < 4) {
+            const u32 v = cx.lane == 0 ? b0 : (cx.lane == 1 ? b1 : (cx.lane == 2 ? b2 : b3));
+            cx.hd[ehdw + cx.wis + cx.wq * cx.lane] = v;
         }
     }
 }
 
-template <int NK>
-__device__ __forceinline__ void dispatch_layer(const LayerCtx &cx, char *Li, u32 *Rrow, int W, const int4 *et, int dc,
+// BIG: rows with more than 10 stored edges exist (never together with register rows: the host
+// only enables those when every other row has at most 10 stored edges)
+template <int NK, bool EXT, bool BIG>
+__device__ __forceinline__ void dispatch_layer(const LayerCtx &cx, char *Li, u32 *Rrow, int W, const int4 *et, int nc,
                                                int i, u32 synbits)
 {
-    switch (dc) {
-    case 1: process_layer<NK, 1, true>(cx, Li, Rrow, W, et, dc, i, synbits); break;
-    case 2: process_layer<NK, 2, true>(cx, Li, Rrow, W, et, dc, i, synbits); break;
-    case 3: process_layer<NK, 3, true>(cx, Li, Rrow, W, et, dc, i, synbits); break;
-    case 4: process_layer<NK, 4, true>(cx, Li, Rrow, W, et, dc, i, synbits); break;
-    case 5: process_layer<NK, 5, true>(cx, Li, Rrow, W, et, dc, i, synbits); break;
-    case 6: process_layer<NK, 6, true>(cx, Li, Rrow, W, et, dc, i, synbits); break;
-    case 7: process_layer<NK, 7, true>(cx, Li, Rrow, W, et, dc, i, synbits); break;
-    case 8: process_layer<NK, 8, true>(cx, Li, Rrow, W, et, dc, i, synbits); break;
-    case 9: process_layer<NK, 9, true>(cx, Li, Rrow, W, et, dc, i, synbits); break;
-    case 10: process_layer<NK, 10, true>(cx, Li, Rrow, W, et, dc, i, synbits); break;
-    case 11: case 12: process_layer<NK, 12, false>(cx, Li, Rrow, W, et, dc, i, synbits); break;
-    case 13: case 14: process_layer<NK, 14, false>(cx, Li, Rrow, W, et, dc, i, synbits); break;
-    case 15: case 16: process_layer<NK, 16, false>(cx, Li, Rrow, W, et, dc, i, synbits); break;
-    case 17: case 18: process_layer<NK, 18, false>(cx, Li, Rrow, W, et, dc, i, synbits); break;
-    default: process_layer<NK, 20, false>(cx, Li, Rrow, W, et, dc, i, synbits); break;
+    u32 dummy[1];
+#define QL_CASE(DCV, MODEV) process_layer<NK, DCV, MODEV, EXT, false, 1>(cx, Li, Rrow, dummy, W, et, nc, i, synbits)
+    switch (nc) {
+    case 1: QL_CASE(1, 0); break;
+    case 2: QL_CASE(2, 0); break;
+    case 3: QL_CASE(3, 0); break;
+    case 4: QL_CASE(4, 0); break;
+    case 5: QL_CASE(5, 0); break;
+    case 6: QL_CASE(6, 0); break;
+    case 7: QL_CASE(7, 0); break;
+    case 8: QL_CASE(8, 0); break;
+    case 9: QL_CASE(9, 0); break;
+    case 10: QL_CASE(10, 0); break;
+    default:
+        if constexpr (BIG) {
+            if (nc <= 12) QL_CASE(12, 1);
+            else if (nc <= 14) QL_CASE(14, 1);
+            else if (nc <= 16) QL_CASE(16, 1);
+            else if (nc <= 18) QL_CASE(18, 1);
+            else QL_CASE(20, 1);
+        }
+        break;
     }
+#undef QL_CASE
 }
 
 // cnt (<=32) bits of a Z-bit little-endian vector starting at bit pos (pos + cnt <= Z)
@@ -210,7 +271,19 @@ __device__ __forceinline__ u32 rotated_bits(const u32 *vec, int Z, int nwords, i
     return x;
 }
 
-template <int NK>
+// 4x4 byte transpose: in[k] holds lanes 4j..4j+3 of quarter k; out[m] = belief word of lane 4j+m
+__device__ __forceinline__ void transpose4x4(const u32 (&in)[4], u32 (&out)[4])
+{
+    const u32 t0 = prmt(in[0], in[1], 0x5140u), t1 = prmt(in[2], in[3], 0x5140u);   // bytes 0,1 of the four quarters
+    const u32 t2 = prmt(in[0], in[1], 0x7362u), t3 = prmt(in[2], in[3], 0x7362u);   // bytes 2,3
+    out[0] = prmt(t0, t1, 0x5410u);
+    out[1] = prmt(t0, t1, 0x7632u);
+    out[2] = prmt(t2, t3, 0x5410u);
+    out[3] = prmt(t2, t3, 0x7632u);
+}
+
+// REGDC: 0, or the unrolled degree of the kRegRows rows whose messages live in registers
+template <int NK, int REGDC>
 __global__ void __launch_bounds__(kMaxBlock, 1) layered_i8_kernel(const LayeredI8Params p)
 {
     extern __shared__ __align__(16) char smem[];
@@ -219,20 +292,18 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layered_i8_kernel(const LayeredI
     const int lane = threadIdx.x & 31, wis = i >> 5;
     const int bar_id = 1 + g;
     const bool active = i < W;
-    const bool aligned = (W & 31) == 0;
+    const bool aligned = (W & 31) == 0;      // every ballot lands on whole words
+    const bool fast_bits = aligned && (Z & 31) == 0;
 
     // ---- shared tables (all slots)
     int4 *etab = reinterpret_cast<int4 *>(smem);   // two int4 per edge
     QcEdgeAux *atab = reinterpret_cast<QcEdgeAux *>(etab + 2 * p.nnz);
-    QcLayer *ltab = reinterpret_cast<QcLayer *>(atab + p.nnz);
-    for (int e = threadIdx.x; e < p.nnz; e += blockDim.x) {
-        const QcEdge ed = p.edges[e];
-        const QcEdgeAux ax = p.aux[e];
-        etab[2 * e] = make_int4(ed.off0, ed.off1, ed.thresh, 0);
-        etab[2 * e + 1] = make_int4(ed.selA0, ed.selA1, ax.selW0, ax.selW1);
-        atab[e] = ax;
-    }
+    Li8Layer *ltab = reinterpret_cast<Li8Layer *>(atab + p.nnz);
+    uint16_t *pcols = reinterpret_cast<uint16_t *>(ltab + p.brows);
+    for (int e = threadIdx.x; e < 2 * p.nnz; e += blockDim.x) etab[e] = reinterpret_cast<const int4 *>(p.edges)[e];
+    for (int e = threadIdx.x; e < p.nnz; e += blockDim.x) atab[e] = p.aux[e];
     for (int r = threadIdx.x; r < p.brows; r += blockDim.x) ltab[r] = p.layers[r];
+    for (int c = threadIdx.x; c < p.n_pack; c += blockDim.x) pcols[c] = p.pack_cols[c];
     __syncthreads();
 
     char *slot = smem + p.tab_bytes + (size_t)g * p.slot_bytes;
@@ -249,17 +320,40 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layered_i8_kernel(const LayeredI
     cx.c255 = dup16(255u);
     cx.norm_eighths = p.norm_eighths;
     cx.negOff = dup16(0x8000u | (u32)p.offset);
+    cx.hd = hd;
+    cx.wis = wis;
+    cx.lane = lane;
+    cx.wq = W >> 5;
+
+    constexpr int RDC = REGDC > 0 ? REGDC : 1;
+    u32 Rreg0[RDC], Rreg1[RDC], Rreg2[RDC], Rreg3[RDC];
 
     for (int f = blockIdx.x * p.slots + g; f < p.F; f += gridDim.x * p.slots) {
         // ---- load: int8 LLRs -> interleaved biased belief words; messages = 0
         const int8_t *src = p.llr + (size_t)f * p.N;
-        if (active) {
+        if ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+            // 4 aligned 32-bit loads (one per quarter of the column) -> 4x4 byte transpose -> one 128-bit store
+            const int wq4 = W >> 2;
+            for (int it = i; it < p.bcols * wq4; it += tpg) {
+                const int c = it / wq4, j = it - c * wq4;
+                const u32 *q = reinterpret_cast<const u32 *>(src + c * Z) + j;
+                u32 in[4], out[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) in[k] = __ldg(q + k * wq4) ^ 0x80808080u;
+                transpose4x4(in, out);
+                *reinterpret_cast<uint4 *>(Lw + c * W + 4 * j) = make_uint4(out[0], out[1], out[2], out[3]);
+            }
+        } else if (active) {
             for (int c = 0; c < p.bcols; ++c) {
                 const uint8_t *q = reinterpret_cast<const uint8_t *>(src) + c * Z + i;
                 const u32 b0 = __ldg(q), b1 = __ldg(q + W), b2 = __ldg(q + 2 * W), b3 = __ldg(q + 3 * W);
                 Lw[c * W + i] = (b0 | (b1 << 8) | (b2 << 16) | (b3 << 24)) ^ 0x80808080u;
             }
-            for (int e = 0; e < p.nnz; ++e) Rw[e * W + i] = 0x80808080u;
+        }
+        for (int idx = i; idx < p.n_store * W; idx += tpg) Rw[idx] = 0x80808080u;
+        if constexpr (REGDC > 0) {
+#pragma unroll
+            for (int j = 0; j < RDC; ++j) Rreg0[j] = Rreg1[j] = Rreg2[j] = Rreg3[j] = 0x80808080u;
         }
         if (p.syn) {   // syndrome rows, Z-bit little-endian vectors (row r, lane l -> bit l)
             const u32 *sf = p.syn + (size_t)f * p.syn_words;
@@ -284,10 +378,9 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layered_i8_kernel(const LayeredI
         int it = 0;
         bool conv = false;
         for (;;) {
-            const bool run_layers = it < p.max_iter;
-            if (run_layers) {
+            if (it < p.max_iter) {
                 for (int r = 0; r < p.brows; ++r) {
-                    const QcLayer ly = ltab[r];
+                    const Li8Layer ly = ltab[r];
                     if (active) {
                         u32 synbits = 0;
                         if (p.syn) {
@@ -297,8 +390,22 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layered_i8_kernel(const LayeredI
                                 synbits |= ((synl[r * ZW32 + (l >> 5)] >> (l & 31)) & 1u) << k;
                             }
                         }
-                        u32 *Rrow = Rw + ly.edge_begin * W + i;
-                        dispatch_layer<NK>(cx, slot + 4 * i, Rrow, W, etab + 2 * ly.edge_begin, ly.degree, i, synbits);
+                        char *Li = slot + 4 * i;
+                        const int4 *et = etab + 2 * ly.edge_begin;
+                        if (REGDC > 0 && ly.reg_idx >= 0) {
+                            if constexpr (REGDC > 0) {
+                                switch (ly.reg_idx) {
+                                case 0: process_layer<NK, RDC, 1, false, true, RDC>(cx, Li, nullptr, Rreg0, W, et, ly.n_core, i, synbits); break;
+                                case 1: process_layer<NK, RDC, 1, false, true, RDC>(cx, Li, nullptr, Rreg1, W, et, ly.n_core, i, synbits); break;
+                                case 2: process_layer<NK, RDC, 1, false, true, RDC>(cx, Li, nullptr, Rreg2, W, et, ly.n_core, i, synbits); break;
+                                default: process_layer<NK, RDC, 1, false, true, RDC>(cx, Li, nullptr, Rreg3, W, et, ly.n_core, i, synbits); break;
+                                }
+                            }
+                        } else {
+                            u32 *Rrow = Rw + ly.r_off * W + i;
+                            if (ly.has_ext) dispatch_layer<NK, true, REGDC == 0>(cx, Li, Rrow, W, et, ly.n_core, i, synbits);
+                            else dispatch_layer<NK, false, REGDC == 0>(cx, Li, Rrow, W, et, ly.n_core, i, synbits);
+                        }
                     }
                     bar_sync(bar_id, tpg);
                 }
@@ -307,42 +414,75 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layered_i8_kernel(const LayeredI
             // the syndrome / hard-decision phase runs after every iteration when early stop is on,
             // otherwise once after the last iteration
             if (p.early_stop || it >= p.max_iter) {
-                if (!aligned) {
-                    for (int idx = i; idx < p.bcols * ZW32; idx += tpg) hd[idx] = 0u;
+                u32 bad = 0;
+                if (fast_bits) {
+                    // hard decisions of the columns that are not extension columns (those were balloted in the layers)
+                    for (int c = 0; c < p.n_pack; ++c) {
+                        const int col = pcols[c];
+                        const u32 X = Lw[col * W + i];                 // biased: bit 7 clear <=> L < 0
+                        const u32 b0 = __ballot_sync(0xffffffffu, (X & 0x80u) == 0u);
+                        const u32 b1 = __ballot_sync(0xffffffffu, (X & 0x8000u) == 0u);
+                        const u32 b2 = __ballot_sync(0xffffffffu, (X & 0x800000u) == 0u);
+                        const u32 b3 = __ballot_sync(0xffffffffu, (int)X >= 0);
+                        if (lane < 4) {
+                            const u32 v = lane == 0 ? b0 : (lane == 1 ? b1 : (lane == 2 ? b2 : b3));
+                            hd[col * ZW32 + wis + cx.wq * lane] = v;
+                        }
+                    }
                     bar_sync(bar_id, tpg);
-                }
-                for (int c = 0; c < p.bcols; ++c) {
-                    const u32 X = active ? Lw[c * W + i] : 0x80808080u;   // biased: bit 7 clear <=> L < 0
+                    // syndrome words: thread -> (row r0 + i / ZW32, word i % ZW32)
+                    const int rsub = i / ZW32, w = i - rsub * ZW32, rstep = tpg / ZW32;
+                    if (rsub < rstep) {
+                        for (int r = rsub; r < p.brows; r += rstep) {
+                            const Li8Layer ly = ltab[r];
+                            u32 acc = p.syn ? synl[r * ZW32 + w] : 0u;
+                            for (int e = ly.edge_begin; e < ly.edge_begin + ly.degree; ++e) {
+                                const QcEdgeAux ax = atab[e];
+                                int w0 = w + (ax.shift >> 5);
+                                if (w0 >= ZW32) w0 -= ZW32;
+                                const int w1 = (w0 + 1 == ZW32) ? 0 : w0 + 1;
+                                acc ^= __funnelshift_r(hd[ax.hdw + w0], hd[ax.hdw + w1], ax.shift & 31);
+                            }
+                            bad |= acc;
+                        }
+                    }
+                } else {
+                    if (!aligned) {
+                        for (int idx = i; idx < p.bcols * ZW32; idx += tpg) hd[idx] = 0u;
+                        bar_sync(bar_id, tpg);
+                    }
+                    for (int c = 0; c < p.bcols; ++c) {
+                        const u32 X = active ? Lw[c * W + i] : 0x80808080u;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const u32 b = __ballot_sync(0xffffffffu, ((X >> (8 * k + 7)) & 1u) == 0u);
-                        if (lane == 0) {
-                            const int o = 32 * wis + W * k;
-                            if (o < Z) {
-                                if (aligned) {
-                                    hd[c * ZW32 + (o >> 5)] = b;
-                                } else {
-                                    atomicOr(&hd[c * ZW32 + (o >> 5)], b << (o & 31));
-                                    if ((o & 31) && (o >> 5) + 1 < ZW32) atomicOr(&hd[c * ZW32 + (o >> 5) + 1], b >> (32 - (o & 31)));
+                        for (int k = 0; k < 4; ++k) {
+                            const u32 b = __ballot_sync(0xffffffffu, ((X >> (8 * k + 7)) & 1u) == 0u);
+                            if (lane == 0) {
+                                const int o = 32 * wis + W * k;
+                                if (o < Z) {
+                                    if (aligned) {
+                                        hd[c * ZW32 + (o >> 5)] = b;
+                                    } else {
+                                        atomicOr(&hd[c * ZW32 + (o >> 5)], b << (o & 31));
+                                        if ((o & 31) && (o >> 5) + 1 < ZW32) atomicOr(&hd[c * ZW32 + (o >> 5) + 1], b >> (32 - (o & 31)));
+                                    }
                                 }
                             }
                         }
                     }
-                }
-                bar_sync(bar_id, tpg);
-                u32 bad = 0;
-                for (int idx = i; idx < p.brows * ZW32; idx += tpg) {
-                    const int r = idx / ZW32, w = idx - r * ZW32;
-                    const int nb = min(32, Z - 32 * w);
-                    u32 acc = p.syn ? synl[idx] : 0u;
-                    const QcLayer ly = ltab[r];
-                    for (int e = ly.edge_begin; e < ly.edge_begin + ly.degree; ++e) {
-                        const QcEdgeAux ax = atab[e];
-                        int start = 32 * w + ax.shift;
-                        if (start >= Z) start -= Z;
-                        acc ^= rotated_bits(hd + ax.col * ZW32, Z, ZW32, start, nb);
+                    bar_sync(bar_id, tpg);
+                    for (int idx = i; idx < p.brows * ZW32; idx += tpg) {
+                        const int r = idx / ZW32, w = idx - r * ZW32;
+                        const int nb = min(32, Z - 32 * w);
+                        u32 acc = p.syn ? synl[idx] : 0u;
+                        const Li8Layer ly = ltab[r];
+                        for (int e = ly.edge_begin; e < ly.edge_begin + ly.degree; ++e) {
+                            const QcEdgeAux ax = atab[e];
+                            int start = 32 * w + ax.shift;
+                            if (start >= Z) start -= Z;
+                            acc ^= rotated_bits(hd + ax.hdw, Z, ZW32, start, nb);
+                        }
+                        bad |= nb >= 32 ? acc : (acc & ((1u << nb) - 1u));
                     }
-                    bad |= nb >= 32 ? acc : (acc & ((1u << nb) - 1u));
                 }
                 conv = !bar_red_or(bar_id, tpg, bad != 0u);
                 if (conv || it >= p.max_iter) break;
@@ -385,23 +525,33 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layered_i8_kernel(const LayeredI
 
 int layered_i8_max_threads() { return kMaxBlock; }
 
-template <int NK>
+template <int NK, int REGDC>
 static int launch_nk(const LayeredI8Params &p, int grid, int smem_bytes, cudaStream_t st)
 {
-    QLDPC_CUDA(cudaFuncSetAttribute(layered_i8_kernel<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    layered_i8_kernel<NK><<<grid, p.slots * p.tpg, smem_bytes, st>>>(p);
+    QLDPC_CUDA(cudaFuncSetAttribute(layered_i8_kernel<NK, REGDC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    layered_i8_kernel<NK, REGDC><<<grid, p.slots * p.tpg, smem_bytes, st>>>(p);
     QLDPC_CUDA(cudaGetLastError());
     return QLDPC_OK;
 }
 
-int launch_layered_i8(const LayeredI8Params &p, int grid, int smem_bytes, cudaStream_t st)
+template <int REGDC>
+static int launch_reg(const LayeredI8Params &p, int grid, int smem_bytes, cudaStream_t st)
 {
-    if (p.rule == QLDPC_RULE_OMS) return launch_nk<0>(p, grid, smem_bytes, st);
+    if (p.rule == QLDPC_RULE_OMS) return launch_nk<0, REGDC>(p, grid, smem_bytes, st);
     switch (p.norm_eighths) {
-    case 8: return launch_nk<8>(p, grid, smem_bytes, st);
-    case 6: return launch_nk<6>(p, grid, smem_bytes, st);
-    default: return launch_nk<-1>(p, grid, smem_bytes, st);
+    case 8: return launch_nk<8, REGDC>(p, grid, smem_bytes, st);
+    case 6: return launch_nk<6, REGDC>(p, grid, smem_bytes, st);
+    default: return launch_nk<-1, REGDC>(p, grid, smem_bytes, st);
     }
 }
+
+int launch_layered_i8(const LayeredI8Params &p, int grid, int smem_bytes, cudaStream_t st)
+{
+    if (p.regdc == 20) return launch_reg<20>(p, grid, smem_bytes, st);
+    if (p.regdc == 0) return launch_reg<0>(p, grid, smem_bytes, st);
+    return QLDPC_ERR_UNSUPPORTED;
+}
+
+int layered_i8_reg_rows() { return kRegRows; }
 
 }  // namespace qldpc

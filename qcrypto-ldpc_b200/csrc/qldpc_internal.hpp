@@ -35,17 +35,30 @@ int build_qc(const int32_t *base, int rows, int cols, int z, HostCode &out);
 // ---- device-side tables ---------------------------------------------------------------------
 // One entry per non-zero block of the base matrix, row-major, columns ascending: the layer
 // schedule of ML/BPSK_nrldpc_sim_FP.m:45-47.
-struct QcEdge {          // 16 bytes, read as one int4 broadcast
+// layered int8 kernel tables ------------------------------------------------------------------
+struct Li8Edge {         // 32 bytes, read as two int4 broadcasts
     int32_t off0;        // byte offset of the belief word for a lane that does not wrap
     int32_t off1;        // ... for a lane that wraps past the end of the column
     int32_t thresh;      // lane index (in words) from which the wrap happens
-    uint16_t selA0;      // PRMT selector (bytes -> half2 pair A) without wrap
-    uint16_t selA1;      // ... with wrap
+    int32_t hdw;         // word offset of the column's hard-decision bit vector (col * ZW32)
+    int32_t selA0;       // PRMT selector (bytes -> half2 pair A) without wrap
+    int32_t selA1;       // ... with wrap
+    int32_t selW0;       // PRMT selector packing two half2 pairs back into a belief word, no wrap
+    int32_t selW1;       // ... with wrap
 };
+struct Li8Layer {        // 16 bytes
+    int32_t edge_begin;  // first edge of the block row (edges are row-major, columns ascending)
+    int16_t degree;      // all edges of the row
+    int16_t n_core;      // edges whose messages are stored (degree - has_ext)
+    int32_t r_off;       // index of the row's first stored message (units of W words), -1 for register rows
+    int16_t reg_idx;     // 0..3: messages live in registers, -1 otherwise
+    int16_t has_ext;     // last edge goes to a weight-1, shift-0 column: no stored message, no belief update
+};
+// generic QC tables (syndrome phase of the int8 kernel, generic layered kernel)
 struct QcEdgeAux {       // 8 bytes
-    uint16_t selW0, selW1;   // PRMT selectors packing two half2 pairs back into a belief word
-    int16_t col;             // block column
-    int16_t shift;           // shift in [0,z)
+    int32_t hdw;         // col * ZW32
+    int16_t col;         // block column
+    int16_t shift;       // shift in [0,z)
 };
 struct QcLayer {
     int32_t edge_begin;
@@ -110,7 +123,9 @@ struct qldpc_decoder {
     uint64_t kernel_launches = 0;
 
     // tables
-    qldpc::DevBuf<qldpc::QcEdge> d_qc_edges;
+    qldpc::DevBuf<qldpc::Li8Edge> d_li8_edges;
+    qldpc::DevBuf<qldpc::Li8Layer> d_li8_layers;
+    qldpc::DevBuf<uint16_t> d_li8_pack_cols;
     qldpc::DevBuf<qldpc::QcEdgeAux> d_qc_aux;
     qldpc::DevBuf<qldpc::QcLayer> d_qc_layers;
     qldpc::DevBuf<int32_t> d_row_ptr, d_col_idx, d_var_ptr, d_var_edge, d_info_pos;
@@ -122,5 +137,6 @@ struct qldpc_decoder {
     qldpc::DevBuf<uint8_t> d_in, d_out;
     qldpc::DevBuf<uint32_t> d_syn;
     // layered int8 launch geometry
-    int li8_slots = 0, li8_tpg = 0, li8_smem = 0, li8_grid = 0, li8_dcb = 0;
+    int li8_slots = 0, li8_tpg = 0, li8_smem = 0, li8_regdc = 0, li8_n_store = 0, li8_n_pack = 0;
+    bool li8_ext = false;
 };

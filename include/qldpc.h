@@ -24,6 +24,8 @@
  *   qldpc_syndrome[_device]      check_cword(B,z,c)                    ML/check_cword.m:9-19
  *   qldpc_make_llr[_device]      Modem_OOK_BSC::demodulate + parity/puncture override
  *                                                                      BOOT/src/main.cpp:348-363
+ *   qldpc_decode_bits[_device]   the two steps above fused for callers that hold key BITS: the ecd2
+ *                                handlers work on pb->mainBufPtr       errorcorrection/definitions/processblock.h:105
  *   qldpc_encode_nr[_device]     nrldpc_encode(B,z,msg)                ML/nrldpc_encode.m:12-40
  *   qldpc_get_stats              Monitor_BFER / FER bookkeeping        BOOT/src/main.cpp:366-388
  *   (decoder.reset(), BOOT/src/main.cpp:389, has no counterpart: every decode call starts
@@ -159,6 +161,19 @@ int qldpc_make_llr(qldpc_decoder *dec, const uint32_t *bits, const uint32_t *kno
 int qldpc_make_llr_device(qldpc_decoder *dec, const uint32_t *d_bits, const uint32_t *d_known_mask,
                           const uint32_t *d_punct_mask, float llr_noisy, float llr_known, int32_t n_frames,
                           void *d_llr_out, void *cuda_stream);
+
+/*
+ * Fused LLR synthesis + decode for callers that hold sifted-key bits (what an ecd2 LDPC handler has in
+ * pb->mainBufPtr, MSB-first words): only n/8 bytes per frame cross the bus instead of n LLR values.
+ * Arguments as in qldpc_make_llr followed by qldpc_decode; results are identical to calling the two.
+ */
+int qldpc_decode_bits(qldpc_decoder *dec, const uint32_t *bits, const uint32_t *known_mask, const uint32_t *punct_mask,
+                      float llr_noisy, float llr_known, const uint32_t *syndrome, int32_t n_frames,
+                      uint32_t *out_bits, uint8_t *ok, uint16_t *iters);
+int qldpc_decode_bits_device(qldpc_decoder *dec, const uint32_t *d_bits, const uint32_t *d_known_mask,
+                             const uint32_t *d_punct_mask, float llr_noisy, float llr_known,
+                             const uint32_t *d_syndrome, int32_t n_frames, uint32_t *d_out_bits, uint8_t *d_ok,
+                             uint16_t *d_iters, void *cuda_stream);
 
 /* 5G-NR systematic encoder (QC codes with the NR double-diagonal core only):
  * msg: n_frames * ceil(k/32) packed words; cword: n_frames * qldpc_codeword_words() */

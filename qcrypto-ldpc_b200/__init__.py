@@ -15,7 +15,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqldpc_b200.so")
+# QLDPC_LIB overrides the library path (kernel experiments build variant libraries side by side)
+LIB_PATH = os.environ.get("QLDPC_LIB") or os.path.join(_HERE, "libqldpc_b200.so")
 DATA_DIR = os.path.join(_HERE, "data")
 
 SCHED_FLOODING, SCHED_LAYERED = 0, 1
@@ -33,7 +34,7 @@ ABI_SYMBOLS = [
     "qldpc_decoder_config_default", "qldpc_decoder_create", "qldpc_decoder_free",
     "qldpc_out_words", "qldpc_syndrome_words", "qldpc_codeword_words",
     "qldpc_decode", "qldpc_decode_device", "qldpc_syndrome", "qldpc_syndrome_device",
-    "qldpc_make_llr", "qldpc_make_llr_device", "qldpc_encode_nr", "qldpc_encode_nr_device",
+    "qldpc_make_llr", "qldpc_make_llr_device", "qldpc_decode_bits", "qldpc_decode_bits_device", "qldpc_encode_nr", "qldpc_encode_nr_device",
     "qldpc_get_stats", "qldpc_reset_stats", "qldpc_decoder_kernel_name", "qldpc_strerror",
     "qldpc_last_cuda_error", "qldpc_version",
 ]
@@ -98,6 +99,8 @@ def lib():
         L.qldpc_syndrome_device.argtypes = [vp, vp, i32, vp, vp]
         L.qldpc_make_llr.argtypes = [vp, vp, vp, vp, C.c_float, C.c_float, i32, vp]
         L.qldpc_make_llr_device.argtypes = [vp, vp, vp, vp, C.c_float, C.c_float, i32, vp, vp]
+        L.qldpc_decode_bits.argtypes = [vp, vp, vp, vp, C.c_float, C.c_float, vp, i32, vp, vp, vp]
+        L.qldpc_decode_bits_device.argtypes = [vp, vp, vp, vp, C.c_float, C.c_float, vp, i32, vp, vp, vp, vp]
         L.qldpc_encode_nr.argtypes = [vp, vp, i32, vp]
         L.qldpc_encode_nr_device.argtypes = [vp, vp, i32, vp, vp]
         L.qldpc_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -242,6 +245,20 @@ class Decoder:
         _chk(lib().qldpc_make_llr(self.h, _np_ptr(bits), _np_ptr(km), _np_ptr(pm), llr_noisy, llr_known, F, _np_ptr(out)),
              "qldpc_make_llr")
         return out
+
+    def decode_bits(self, bits_packed, llr_noisy, llr_known=0.0, known_mask=None, punct_mask=None, syndrome=None):
+        """fused LLR synthesis + decode from packed sifted-key bits (the ecd2-facing call)"""
+        bits = np.ascontiguousarray(bits_packed, dtype=np.uint32)
+        F = bits.shape[0]
+        km = None if known_mask is None else np.ascontiguousarray(known_mask, dtype=np.uint32)
+        pm = None if punct_mask is None else np.ascontiguousarray(punct_mask, dtype=np.uint32)
+        syn = None if syndrome is None else np.ascontiguousarray(syndrome, dtype=np.uint32)
+        out = np.zeros((F, self.out_words), dtype=np.uint32)
+        ok = np.zeros(F, dtype=np.uint8)
+        iters = np.zeros(F, dtype=np.uint16)
+        _chk(lib().qldpc_decode_bits(self.h, _np_ptr(bits), _np_ptr(km), _np_ptr(pm), llr_noisy, llr_known, _np_ptr(syn), F,
+                                     _np_ptr(out), _np_ptr(ok), _np_ptr(iters)), "qldpc_decode_bits")
+        return out, ok.astype(bool), iters
 
     def encode_nr(self, msg_packed):
         msg = np.ascontiguousarray(msg_packed, dtype=np.uint32)

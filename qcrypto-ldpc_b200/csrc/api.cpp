@@ -170,7 +170,7 @@ bool plan_layered_i8(qldpc_decoder *d, LayeredI8Params &p, bool upload)
 struct Lane {   // per-stream staging of the host-pointer entry points
     cudaStream_t st = nullptr;
     DevBuf<uint8_t> in, post;
-    DevBuf<uint32_t> syn, out;
+    DevBuf<uint32_t> syn, out, bits;
     DevBuf<uint8_t> ok;
     DevBuf<uint16_t> iters;
 };
@@ -280,6 +280,7 @@ extern "C" void qldpc_decoder_config_default(qldpc_decoder_config *cfg)
 
 struct qldpc_decoder_full : qldpc_decoder {
     qldpc_decoder_lanes lanes;
+    DevBuf<uint8_t> d_llr_tmp;          // LLRs synthesised by qldpc_decode_bits_device
     DevBuf<int32_t> d_base;
     DevBuf<uint32_t> d_mask_known, d_mask_punct, d_tmp_bits;
     size_t scratch_msg_bytes = 0, scratch_app_bytes = 0;
@@ -636,6 +637,84 @@ extern "C" int qldpc_make_llr(qldpc_decoder *dec, const uint32_t *bits, const ui
     QLDPC_CUDA(cudaMemcpyAsync(llr_out, ln.in.p, (size_t)n_frames * d->code.n * esz, cudaMemcpyDeviceToHost, ln.st));
     QLDPC_CUDA(cudaStreamSynchronize(ln.st));
     return QLDPC_OK;
+}
+
+extern "C" int qldpc_decode_bits_device(qldpc_decoder *dec, const uint32_t *d_bits, const uint32_t *d_known_mask,
+                                        const uint32_t *d_punct_mask, float llr_noisy, float llr_known,
+                                        const uint32_t *d_syndrome, int32_t n_frames, uint32_t *d_out_bits, uint8_t *d_ok,
+                                        uint16_t *d_iters, void *cuda_stream)
+{
+    if (!dec || !d_bits || !d_out_bits || n_frames < 0) return QLDPC_ERR_ARG;
+    if (n_frames == 0) return QLDPC_OK;
+    qldpc_decoder_full *d = full(dec);
+    QLDPC_CUDA(cudaSetDevice(d->cfg.device));
+    int rc;
+    if ((rc = d->d_llr_tmp.ensure((size_t)n_frames * d->code.n * dtype_size(d->cfg.dtype)))) return rc;
+    if ((rc = qldpc_make_llr_device(dec, d_bits, d_known_mask, d_punct_mask, llr_noisy, llr_known, n_frames, d->d_llr_tmp.p,
+                                    cuda_stream))) return rc;
+    return qldpc_decode_device(dec, d->d_llr_tmp.p, d_syndrome, n_frames, d_out_bits, d_ok, d_iters, nullptr, cuda_stream);
+}
+
+// Host-pointer version: packed bits in, packed bits out, chunks ping-pong over two streams.
+extern "C" int qldpc_decode_bits(qldpc_decoder *dec, const uint32_t *bits, const uint32_t *known_mask,
+                                 const uint32_t *punct_mask, float llr_noisy, float llr_known, const uint32_t *syndrome,
+                                 int32_t n_frames, uint32_t *out_bits, uint8_t *ok, uint16_t *iters)
+{
+    if (!dec || !bits || !out_bits || n_frames < 0) return QLDPC_ERR_ARG;
+    if (n_frames == 0) return QLDPC_OK;
+    qldpc_decoder_full *d = full(dec);
+    const HostCode &c = d->code;
+    QLDPC_CUDA(cudaSetDevice(d->cfg.device));
+    const size_t esz = dtype_size(d->cfg.dtype);
+    const size_t frame_llr = (size_t)c.n * esz;
+    int chunk = (int)std::max<size_t>(1, (128u << 20) / frame_llr);
+    chunk = std::max(chunk, d->sm_count * std::max(1, d->li8_slots) * 4);
+    chunk = std::min(chunk, n_frames);
+    const bool shared_scratch = !(d->kernel_family == KF_LAYERED_I8 && (d->cfg.out_mode == QLDPC_OUT_ALL || d->info_is_prefix));
+    int rc = QLDPC_OK;
+    Lane &l0 = d->lanes.lane[0];
+    const uint32_t *dk = nullptr, *dp = nullptr;
+    if (known_mask) {
+        if ((rc = d->d_mask_known.ensure(d->cw_words))) return rc;
+        QLDPC_CUDA(cudaMemcpyAsync(d->d_mask_known.p, known_mask, (size_t)d->cw_words * 4, cudaMemcpyHostToDevice, l0.st));
+        dk = d->d_mask_known.p;
+    }
+    if (punct_mask) {
+        if ((rc = d->d_mask_punct.ensure(d->cw_words))) return rc;
+        QLDPC_CUDA(cudaMemcpyAsync(d->d_mask_punct.p, punct_mask, (size_t)d->cw_words * 4, cudaMemcpyHostToDevice, l0.st));
+        dp = d->d_mask_punct.p;
+    }
+    QLDPC_CUDA(cudaStreamSynchronize(l0.st));   // masks are read by both lanes
+    for (auto &ln : d->lanes.lane) {
+        if ((rc = ln.in.ensure((size_t)chunk * frame_llr))) return rc;
+        if ((rc = ln.bits.ensure((size_t)chunk * d->cw_words))) return rc;
+        if ((rc = ln.out.ensure((size_t)chunk * d->out_words))) return rc;
+        if ((rc = ln.ok.ensure(chunk))) return rc;
+        if ((rc = ln.iters.ensure(chunk))) return rc;
+        if (syndrome && (rc = ln.syn.ensure((size_t)chunk * d->syn_words))) return rc;
+    }
+    int idx = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += chunk, ++idx) {
+        Lane &ln = d->lanes.lane[shared_scratch ? 0 : (idx & 1)];
+        const int nf = std::min(chunk, n_frames - f0);
+        QLDPC_CUDA(cudaMemcpyAsync(ln.bits.p, bits + (size_t)f0 * d->cw_words, (size_t)nf * d->cw_words * 4,
+                                   cudaMemcpyHostToDevice, ln.st));
+        if (syndrome)
+            QLDPC_CUDA(cudaMemcpyAsync(ln.syn.p, syndrome + (size_t)f0 * d->syn_words, (size_t)nf * d->syn_words * 4,
+                                       cudaMemcpyHostToDevice, ln.st));
+        if ((rc = qldpc_make_llr_device(dec, ln.bits.p, dk, dp, llr_noisy, llr_known, nf, ln.in.p, ln.st))) break;
+        if ((rc = qldpc_decode_device(dec, ln.in.p, syndrome ? ln.syn.p : nullptr, nf, ln.out.p, ln.ok.p, ln.iters.p, nullptr,
+                                      ln.st))) break;
+        QLDPC_CUDA(cudaMemcpyAsync(out_bits + (size_t)f0 * d->out_words, ln.out.p, (size_t)nf * d->out_words * 4,
+                                   cudaMemcpyDeviceToHost, ln.st));
+        if (ok) QLDPC_CUDA(cudaMemcpyAsync(ok + f0, ln.ok.p, nf, cudaMemcpyDeviceToHost, ln.st));
+        if (iters) QLDPC_CUDA(cudaMemcpyAsync(iters + f0, ln.iters.p, (size_t)nf * 2, cudaMemcpyDeviceToHost, ln.st));
+    }
+    for (auto &ln : d->lanes.lane) {
+        cudaError_t e = cudaStreamSynchronize(ln.st);
+        if (e != cudaSuccess && rc == QLDPC_OK) rc = CudaCheck::fail(e, "cudaStreamSynchronize");
+    }
+    return rc;
 }
 
 extern "C" int qldpc_encode_nr_device(qldpc_decoder *dec, const uint32_t *d_msg, int32_t n_frames, uint32_t *d_cword,

@@ -28,6 +28,24 @@
 
 #include "kernels.hpp"
 
+// Experiment switches (measured on B200, BG1 Z=384, bench.py; see profiles/r1_experiments.md):
+//   LOADUNROLL  unrolled frame load + L2 prefetch of the slot's next frame      +1.2 %  (on)
+//   EXTEARLY    extension-edge ballots before the core second pass               +0.4 %  (off: noise)
+//   PAIRS       degree buckets of two instead of exact-degree code variants      -1.8 %  (off)
+//   REGDEDUPE   one code copy for the register rows (messages moved through a working array) -13 % (off)
+#ifndef QL_OPT_LOADUNROLL
+#define QL_OPT_LOADUNROLL 1
+#endif
+#ifndef QL_OPT_EXTEARLY
+#define QL_OPT_EXTEARLY 0
+#endif
+#ifndef QL_OPT_PAIRS
+#define QL_OPT_PAIRS 0
+#endif
+#ifndef QL_OPT_REGDEDUPE
+#define QL_OPT_REGDEDUPE 0
+#endif
+
 namespace qldpc {
 
 namespace {
@@ -121,7 +139,7 @@ __device__ __forceinline__ void process_layer(const LayerCtx &cx, char *Li, u32 
 {
     // register rows recompute the belief address / pack selector in the second pass (register budget)
     constexpr int KEEP = REG ? 1 : DC;
-    u32 uA[DC], uB[DC], tA[DC], tB[DC], sw[KEEP];
+    u32 uA[DC], uB[DC], tA[KEEP], tB[KEEP], sw[KEEP];
     char *ad[KEEP];
     // running sign product starts at the syndrome bit of each lane
     u32 m1A = kInf2 ^ (((synbits & 1u) << 15) | ((synbits & 2u) << 30));
@@ -145,7 +163,8 @@ __device__ __forceinline__ void process_layer(const LayerCtx &cx, char *Li, u32 
             const u32 ua = hsub(xA, yA), ub = hsub(xB, yB);          // L - R_old  (:51)
             const u32 ta = hmin(hmax(ua, cx.cLo), cx.cHi);            // clip to the message range (:54-55)
             const u32 tb = hmin(hmax(ub, cx.cLo), cx.cHi);
-            uA[j] = ua; uB[j] = ub; tA[j] = ta; tB[j] = tb;
+            uA[j] = ua; uB[j] = ub;
+            if constexpr (!REG) { tA[j] = ta; tB[j] = tb; }
             m2A = hmax(habs(m1A), hmin(habs(ta), m2A));               // second minimum (:61)
             m2B = hmax(habs(m1B), hmin(habs(tb), m2B));
             m1A = min_xorsign_abs(m1A, ta);                           // first minimum and sign product (:60,:63)
@@ -182,13 +201,36 @@ __device__ __forceinline__ void process_layer(const LayerCtx &cx, char *Li, u32 
     }
     c1A ^= parA; c2A ^= parA; c1B ^= parB; c2B ^= parB;               // parity folded into both candidates
 
+#if QL_OPT_EXTEARLY
+    if constexpr (EXT) {   // only the sign of channel + new message is observable: ballot it into the hd vector
+        const u32 eA = heq_mask(habs(teA), min1A), eB = heq_mask(habs(teB), min1B);
+        const u32 rA = ((eA & c1A) | (~eA & c2A)) ^ (teA & kSignMask);
+        const u32 rB = ((eB & c1B) | (~eB & c2B)) ^ (teB & kSignMask);
+        const u32 aA = hadd(ueA, rA), aB = hadd(ueB, rB);
+        const u32 b0 = __ballot_sync(0xffffffffu, (int)(aA << 16) < 0);   // lane i
+        const u32 b1 = __ballot_sync(0xffffffffu, (int)aA < 0);           // lane i + W
+        const u32 b2 = __ballot_sync(0xffffffffu, (int)(aB << 16) < 0);   // lane i + 2W
+        const u32 b3 = __ballot_sync(0xffffffffu, (int)aB < 0);           // lane i + 3W
+        if (cx.lane < 4) {
+            const u32 v = cx.lane == 0 ? b0 : (cx.lane == 1 ? b1 : (cx.lane == 2 ? b2 : b3));
+            cx.hd[ehdw + cx.wis + cx.wq * cx.lane] = v;
+        }
+    }
+#endif
 #pragma unroll
     for (int j = 0; j < DC; ++j) {
         if (MODE == 0 || j < DC - 1 || j < nc) {
-            const u32 eA = heq_mask(habs(tA[j]), min1A), eB = heq_mask(habs(tB[j]), min1B);
+            u32 ta, tb;
+            if constexpr (REG) {   // register rows re-clip instead of keeping t live
+                ta = hmin(hmax(uA[j], cx.cLo), cx.cHi);
+                tb = hmin(hmax(uB[j], cx.cLo), cx.cHi);
+            } else {
+                ta = tA[j]; tb = tB[j];
+            }
+            const u32 eA = heq_mask(habs(ta), min1A), eB = heq_mask(habs(tb), min1B);
             // |t| == min1 ? c1 : c2, then the edge's own sign (:73-75)
-            const u32 rA = ((eA & c1A) | (~eA & c2A)) ^ (tA[j] & kSignMask);
-            const u32 rB = ((eB & c1B) | (~eB & c2B)) ^ (tB[j] & kSignMask);
+            const u32 rA = ((eA & c1A) | (~eA & c2A)) ^ (ta & kSignMask);
+            const u32 rB = ((eB & c1B) | (~eB & c2B)) ^ (tb & kSignMask);
             const u32 bA = hadd(rA, cx.c128), bB = hadd(rB, cx.c128); // biased new message
             const u32 lA = hmin(hadd_relu(uA[j], bA), cx.c255);       // clip(L - R_old + R_new) biased (:88-91)
             const u32 lB = hmin(hadd_relu(uB[j], bB), cx.c255);
@@ -205,6 +247,7 @@ __device__ __forceinline__ void process_layer(const LayerCtx &cx, char *Li, u32 
             }
         }
     }
+#if !QL_OPT_EXTEARLY
     if constexpr (EXT) {   // only the sign of channel + new message is observable: ballot it into the hd vector
         const u32 eA = heq_mask(habs(teA), min1A), eB = heq_mask(habs(teB), min1B);
         const u32 rA = ((eA & c1A) | (~eA & c2A)) ^ (teA & kSignMask);
@@ -219,6 +262,7 @@ __device__ __forceinline__ void process_layer(const LayerCtx &cx, char *Li, u32 
             cx.hd[ehdw + cx.wis + cx.wq * cx.lane] = v;
         }
     }
+#endif
 }
 
 // BIG: rows with more than 10 stored edges exist (never together with register rows: the host
@@ -229,6 +273,15 @@ __device__ __forceinline__ void dispatch_layer(const LayerCtx &cx, char *Li, u32
 {
     u32 dummy[1];
 #define QL_CASE(DCV, MODEV) process_layer<NK, DCV, MODEV, EXT, false, 1>(cx, Li, Rrow, dummy, W, et, nc, i, synbits)
+#if QL_OPT_PAIRS
+    // buckets of two (last slot optional): few code variants keep the instruction working set small
+    switch ((nc + 1) >> 1) {
+    case 1: QL_CASE(2, 1); break;
+    case 2: QL_CASE(4, 1); break;
+    case 3: QL_CASE(6, 1); break;
+    case 4: QL_CASE(8, 1); break;
+    case 5: QL_CASE(10, 1); break;
+#else
     switch (nc) {
     case 1: QL_CASE(1, 0); break;
     case 2: QL_CASE(2, 0); break;
@@ -240,6 +293,7 @@ __device__ __forceinline__ void dispatch_layer(const LayerCtx &cx, char *Li, u32
     case 8: QL_CASE(8, 0); break;
     case 9: QL_CASE(9, 0); break;
     case 10: QL_CASE(10, 0); break;
+#endif
     default:
         if constexpr (BIG) {
             if (nc <= 12) QL_CASE(12, 1);
@@ -334,6 +388,16 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layered_i8_kernel(const LayeredI
         if ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
             // 4 aligned 32-bit loads (one per quarter of the column) -> 4x4 byte transpose -> one 128-bit store
             const int wq4 = W >> 2;
+#if QL_OPT_LOADUNROLL
+            {   // pull this slot's next frame towards L2 while the current one is decoded
+                const int fn = f + gridDim.x * p.slots;
+                if (fn < p.F) {
+                    const char *nx = reinterpret_cast<const char *>(p.llr + (size_t)fn * p.N);
+                    for (int o = i * 128; o < p.N; o += tpg * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
+                }
+            }
+#pragma unroll 6
+#endif
             for (int it = i; it < p.bcols * wq4; it += tpg) {
                 const int c = it / wq4, j = it - c * wq4;
                 const u32 *q = reinterpret_cast<const u32 *>(src + c * Z) + j;
@@ -350,7 +414,12 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layered_i8_kernel(const LayeredI
                 Lw[c * W + i] = (b0 | (b1 << 8) | (b2 << 16) | (b3 << 24)) ^ 0x80808080u;
             }
         }
-        for (int idx = i; idx < p.n_store * W; idx += tpg) Rw[idx] = 0x80808080u;
+        if ((W & 3) == 0) {
+            for (int idx = i; idx < p.n_store * (W >> 2); idx += tpg)
+                reinterpret_cast<uint4 *>(Rw)[idx] = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+        } else {
+            for (int idx = i; idx < p.n_store * W; idx += tpg) Rw[idx] = 0x80808080u;
+        }
         if constexpr (REGDC > 0) {
 #pragma unroll
             for (int j = 0; j < RDC; ++j) Rreg0[j] = Rreg1[j] = Rreg2[j] = Rreg3[j] = 0x80808080u;
@@ -394,12 +463,28 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layered_i8_kernel(const LayeredI
                         const int4 *et = etab + 2 * ly.edge_begin;
                         if (REGDC > 0 && ly.reg_idx >= 0) {
                             if constexpr (REGDC > 0) {
+#if QL_OPT_REGDEDUPE
+                                // one code copy for all register rows: move the row's messages through a working array
+                                u32 Rc[RDC];
+                                const int ri = ly.reg_idx;
+#pragma unroll
+                                for (int j = 0; j < RDC; ++j) Rc[j] = ri == 0 ? Rreg0[j] : (ri == 1 ? Rreg1[j] : (ri == 2 ? Rreg2[j] : Rreg3[j]));
+                                process_layer<NK, RDC, 1, false, true, RDC>(cx, Li, nullptr, Rc, W, et, ly.n_core, i, synbits);
+#pragma unroll
+                                for (int j = 0; j < RDC; ++j) {
+                                    if (ri == 0) Rreg0[j] = Rc[j];
+                                    else if (ri == 1) Rreg1[j] = Rc[j];
+                                    else if (ri == 2) Rreg2[j] = Rc[j];
+                                    else Rreg3[j] = Rc[j];
+                                }
+#else
                                 switch (ly.reg_idx) {
                                 case 0: process_layer<NK, RDC, 1, false, true, RDC>(cx, Li, nullptr, Rreg0, W, et, ly.n_core, i, synbits); break;
                                 case 1: process_layer<NK, RDC, 1, false, true, RDC>(cx, Li, nullptr, Rreg1, W, et, ly.n_core, i, synbits); break;
                                 case 2: process_layer<NK, RDC, 1, false, true, RDC>(cx, Li, nullptr, Rreg2, W, et, ly.n_core, i, synbits); break;
                                 default: process_layer<NK, RDC, 1, false, true, RDC>(cx, Li, nullptr, Rreg3, W, et, ly.n_core, i, synbits); break;
                                 }
+#endif
                             }
                         } else {
                             u32 *Rrow = Rw + ly.r_off * W + i;
@@ -537,12 +622,17 @@ static int launch_nk(const LayeredI8Params &p, int grid, int smem_bytes, cudaStr
 template <int REGDC>
 static int launch_reg(const LayeredI8Params &p, int grid, int smem_bytes, cudaStream_t st)
 {
+#ifdef QL_ONLY_NK6   // experiment builds
+    if (p.rule != QLDPC_RULE_OMS && p.norm_eighths == 6) return launch_nk<6, REGDC>(p, grid, smem_bytes, st);
+    return QLDPC_ERR_UNSUPPORTED;
+#else
     if (p.rule == QLDPC_RULE_OMS) return launch_nk<0, REGDC>(p, grid, smem_bytes, st);
     switch (p.norm_eighths) {
     case 8: return launch_nk<8, REGDC>(p, grid, smem_bytes, st);
     case 6: return launch_nk<6, REGDC>(p, grid, smem_bytes, st);
     default: return launch_nk<-1, REGDC>(p, grid, smem_bytes, st);
     }
+#endif
 }
 
 int launch_layered_i8(const LayeredI8Params &p, int grid, int smem_bytes, cudaStream_t st)

@@ -129,9 +129,12 @@ def test_full_batch_roundtrip_property(q, O, data_dir):
     out, ok, iters, _ = dec.decode(llr)
     assert ok.all()
     assert (q.unpack_bits(out, oc.K) == msg).all()
+    # the fused bits-in call (what the ecd2 handlers use) returns exactly the same
+    out2, ok2, iters2 = dec.decode_bits(q.pack_bits(noisy), 14.0, 31.0, known_mask=q.pack_bits(known))
+    assert (out2 == out).all() and (ok2 == ok).all() and (iters2 == iters).all()
     st = dec.stats()
-    assert st["frames"] == F and st["failures"] == 0
-    assert sum(st["iter_hist"]) == F and st["iter_sum"] == int(iters.sum())
+    assert st["frames"] == 2 * F and st["failures"] == 0
+    assert sum(st["iter_hist"]) == 2 * F and st["iter_sum"] == 2 * int(iters.sum())
     # sampled oracle agreement on iteration counts
     sel = rng.choice(F, 16, replace=False)
     hard, oit, ook, _ = oc.batch_layered_fixed_i8(llr[sel], None, rule=O.RULE_NMS, n_ite=10, early_stop=True, norm_eighths=6)

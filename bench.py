@@ -298,19 +298,17 @@ def run_ours(args, rank, world, local_rank):
                "h2d_llr": F * N, "d2h": F * (dec.out_words * 4 + 1 + 2)}
         del h_llr
 
-    # ---- reductions over ranks: time = max, statistics = sum (host side)
-    vec = torch.tensor([total_ms, e2e["s"] * 1e3 if e2e else 0.0, e2e["s_llr"] * 1e3 if e2e else 0.0], dtype=torch.float64)
-    cnt = torch.tensor([stats["frames"], stats["failures"], stats["iter_sum"], launches] + stats["iter_hist"][:16], dtype=torch.int64)
-    if world > 1:
-        dist.all_reduce(vec, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    # ---- reductions over ranks: time = max, statistics = sum (host side, CPU tensors over gloo)
+    sh = importlib.import_module("qcrypto-ldpc_b200.sharding")
+    red, tmax = sh.reduce_stats(stats, [total_ms, e2e["s"] * 1e3 if e2e else 0.0, e2e["s_llr"] * 1e3 if e2e else 0.0],
+                                dist if world > 1 else None)
     if rank != 0:
         return
-    total_ms, e2e_ms, e2e_llr_ms = float(vec[0]), float(vec[1]), float(vec[2])
+    total_ms, e2e_ms, e2e_llr_ms = tmax
     frames_total = F * world * args.steps
     value = frames_total * K / (total_ms * 1e-3) / 1e6
-    mean_iters = float(cnt[2]) / max(1, int(cnt[0]))
-    fer = float(cnt[1]) / max(1, int(cnt[0]))
+    mean_iters, fer = red["mean_iters"], red["fer"]
+    assert red["frames"] == frames_total, (red["frames"], frames_total)
 
     peak, peak_src = measured_peak_hbm()
     bytes_per_frame = N + dec.out_words * 4 + 1 + 2          # int8 LLRs in; packed info bits, ok, iters out
@@ -327,16 +325,16 @@ def run_ours(args, rank, world, local_rank):
 
     cpu = None
     if not args.no_cpu:
-        n_cpu = 1024
+        n_cpu = min(F, 16384)
         cpu = cpu_reference_run(llr[:n_cpu].cpu().numpy(), args.cpu_seconds)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     line = {"metric": "reconciled info Mbit/s", "value": value, "unit": "Mbit/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "i8", "data": "synthetic", "config": workload_config(args, world),
-            "fer": fer, "mean_iters": mean_iters, "iter_hist": [int(x) for x in cnt[4:16]],
+            "fer": fer, "mean_iters": mean_iters, "iter_hist": red["iter_hist"][:12],
             "codeword_basis_mbps": value * N / K,
-            "clocks": clocks, "gpu_launches": int(cnt[3]), "roofline": roofline, "cpu_baseline": cpu}
+            "clocks": clocks, "gpu_launches": red["kernel_launches"], "roofline": roofline, "cpu_baseline": cpu}
     if e2e:
         line["e2e"] = {"value": F * world * K / (e2e_ms * 1e-3) / 1e6, "unit": "Mbit/s", "h2d_bytes_per_step": e2e["h2d"] * world,
                        "d2h_bytes_per_step": e2e["d2h"] * world, "ms_per_step": e2e_ms, "steps": e2e["steps"],

@@ -1,6 +1,7 @@
 // C ABI of libqldpc_b200 (see include/qldpc.h for the reference interface each entry point replaces).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -64,12 +65,16 @@ int build_qc_tables(qldpc_decoder *d)
 // the kernel's assumptions (the caller then uses the generic kernel).
 bool plan_layered_i8(qldpc_decoder *d, LayeredI8Params &p, bool upload)
 {
+    // QLDPC_LI8_MODE=resident|stream overrides the automatic choice (kernel experiments)
+    const char *mode_env = std::getenv("QLDPC_LI8_MODE");
+    const bool force_stream = mode_env && std::strcmp(mode_env, "stream") == 0;
+    const bool force_resident = mode_env && std::strcmp(mode_env, "resident") == 0;
     const HostCode &c = d->code;
     if (c.z <= 0 || c.z % 4 != 0 || c.max_chk_degree > 20 || d->cfg.max_iter < 1) return false;
     const int W = c.z / 4, ZW32 = (c.z + 31) / 32;
     const int nnz = c.edges / c.z;
     const int tpg = round_up(W, 32);
-    if (tpg > layered_i8_max_threads()) return false;
+    if (tpg > layered_i8_max_threads_stream()) return false;
     const int R = c.base_rows, C = c.base_cols;
     auto B = [&](int r, int col) { return c.base[r * C + col]; };
     const bool fast_bits = (W % 32 == 0) && (c.z % 32 == 0);
@@ -136,23 +141,51 @@ bool plan_layered_i8(qldpc_decoder *d, LayeredI8Params &p, bool upload)
 
     p.Z = c.z; p.W = W; p.ZW32 = ZW32;
     p.brows = R; p.bcols = C; p.nnz = nnz; p.N = c.n;
-    p.n_store = n_store;
     p.n_pack = (int)pack_cols.size();
-    p.regdc = regdc;
     p.tab_bytes = round_up(nnz * (int)(sizeof(Li8Edge) + sizeof(QcEdgeAux)) + R * (int)sizeof(Li8Layer) + C * 2, 16);
     const int L_bytes = C * W * 4;
-    const int R_bytes = n_store * W * 4;
     const int hd_bytes = round_up(C * ZW32 * 4, 16);
     const int syn_bytes = round_up(R * ZW32 * 4, 16);
+    const int avail = d->max_smem_optin - p.tab_bytes;
+
+    // geometry A: messages resident in shared memory (+ register rows)
+    const int R_bytes = n_store * W * 4;
+    const int slot_res = round_up(L_bytes, 16) + round_up(R_bytes, 16) + hd_bytes + syn_bytes;
+    int slots_res = std::min(std::min(avail / slot_res, layered_i8_max_threads() / tpg), 15);
+
+    // geometry B: messages streamed through an L2-resident scratch, 2-deep cp.async ring per frame
+    int g_off = 0, st_max = 4;
+    for (auto &ly : layers) {
+        ly.st = (int16_t)round_up(std::max<int>(ly.n_core, 1), 4);
+        ly.g_off = g_off;
+        g_off += W * ly.st;
+        st_max = std::max<int>(st_max, ly.st);
+    }
+    const int stage_words = W * st_max;
+    const int slot_str = round_up(L_bytes, 16) + 2 * stage_words * 4 + hd_bytes + syn_bytes;
+    int slots_str = std::min(std::min(avail / slot_str, layered_i8_max_threads_stream() / tpg), 15);
+    if (tpg > layered_i8_max_threads_stream()) slots_str = 0;
+
+    bool stream = slots_str > slots_res;
+    if (force_stream && slots_str >= 1) stream = true;
+    if (force_resident && slots_res >= 1) stream = false;
+    const int slots = stream ? slots_str : slots_res;
+    if (slots < 1) return false;
+    if (stream) {   // no register rows in streamed mode: every row's messages go through the ring
+        regdc = 0;
+        int n = 0;
+        for (auto &ly : layers) { ly.reg_idx = -1; ly.r_off = n; n += ly.n_core; }
+        n_store = n;
+    }
+    p.stream = stream ? 1 : 0;
+    p.rg_words = g_off;
+    p.stage_words = stage_words;
+    p.n_store = n_store;
+    p.regdc = regdc;
     p.off_R = round_up(L_bytes, 16);
-    p.off_hd = p.off_R + round_up(R_bytes, 16);
+    p.off_hd = p.off_R + (stream ? 2 * stage_words * 4 : round_up(R_bytes, 16));
     p.off_syn = p.off_hd + hd_bytes;
     p.slot_bytes = p.off_syn + syn_bytes;
-    const int avail = d->max_smem_optin - p.tab_bytes;
-    int slots = avail / p.slot_bytes;
-    slots = std::min(slots, layered_i8_max_threads() / tpg);
-    slots = std::min(slots, 15);   // named barriers 1..15
-    if (slots < 1) return false;
     p.slots = slots;
     p.tpg = tpg;
     d->li8_slots = slots;
@@ -161,6 +194,8 @@ bool plan_layered_i8(qldpc_decoder *d, LayeredI8Params &p, bool upload)
     d->li8_regdc = regdc;
     d->li8_n_store = n_store;
     d->li8_n_pack = p.n_pack;
+    d->li8_stream = stream;
+    d->li8_rg_words = g_off;
     if (upload) {
         if (d->d_li8_edges.upload(edges) || d->d_li8_layers.upload(layers) || d->d_li8_pack_cols.upload(pack_cols)) return false;
     }
@@ -367,6 +402,7 @@ extern "C" int qldpc_decoder_create(const qldpc_code *code, const qldpc_decoder_
         if (fast) {
             d->kernel_family = KF_LAYERED_I8;
             d->kernel_name = "layered_i8_zpack4";
+            if (d->li8_stream && (rc = d->d_li8_rg.ensure((size_t)d->sm_count * d->li8_slots * d->li8_rg_words))) return bail(rc);
         } else {
             d->kernel_family = KF_LAYERED_GENERIC;
             d->kernel_name = "layered_generic";
@@ -457,6 +493,10 @@ extern "C" int qldpc_decode_device(qldpc_decoder *dec, const void *d_llr, const 
         p.max_iter = cfg.max_iter; p.early_stop = cfg.early_stop;
         p.rule = cfg.rule; p.offset = d->offset_int; p.norm_eighths = d->norm_eighths; p.msg_max = cfg.msg_max;
         const int grid = std::min(d->sm_count, (n_frames + p.slots - 1) / p.slots);
+        if (p.stream) {
+            if ((rc = d->d_li8_rg.ensure((size_t)d->sm_count * p.slots * p.rg_words))) return rc;
+            p.rg = d->d_li8_rg.p;
+        }
         if ((rc = launch_layered_i8(p, grid, d->li8_smem, st))) return rc;
         d->kernel_launches++;
         if (!direct) {

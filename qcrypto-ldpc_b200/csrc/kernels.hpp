@@ -30,11 +30,17 @@ struct LayeredI8Params {
     int slots, tpg;           // frames in flight per CTA, threads per frame group
     int tab_bytes;            // shared tables at the start of dynamic smem
     int slot_bytes;           // bytes per frame slot
-    int off_R, off_hd, off_syn;  // byte offsets inside a slot (beliefs start at 0)
+    int off_R, off_hd, off_syn;  // byte offsets inside a slot (beliefs start at 0); off_R = message store or ring
+    // streamed mode (messages in an L2-resident scratch, staged through a 2-deep cp.async ring at off_R)
+    int stream;
+    uint32_t *rg;             // grid * slots * rg_words
+    int rg_words;             // words per frame slot
+    int stage_words;          // words per ring stage
 };
 int launch_layered_i8(const LayeredI8Params &p, int grid, int smem_bytes, cudaStream_t st);
 int layered_i8_max_threads();
 int layered_i8_reg_rows();
+int layered_i8_max_threads_stream();
 
 // ---- generic layered (QC, any Z; f32 / i16 / i8) ---------------------------------------------
 struct LayeredGenParams {

@@ -56,6 +56,7 @@ constexpr u32 kSignMask = 0x80008000u;
 constexpr u32 kInf2 = 0x03ff03ffu;     // 1023 ulp: larger than any message magnitude
 constexpr u32 kOne2 = 0x3c003c00u;     // 1.0h, 1.0h
 constexpr int kMaxBlock = 256;
+constexpr int kMaxBlockStream = 384;
 constexpr int kRegRows = 4;
 
 __device__ __forceinline__ __half2 h2(u32 x) { return *reinterpret_cast<__half2 *>(&x); }
@@ -115,6 +116,12 @@ __device__ __forceinline__ u32 norm_eighths2(u32 x, int k_rt)
     return r;
 }
 
+__device__ __forceinline__ u32 vcomp(const uint4 &v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
+__device__ __forceinline__ void vset(uint4 &v, int k, u32 x)
+{
+    if (k == 0) v.x = x; else if (k == 1) v.y = x; else if (k == 2) v.z = x; else v.w = x;
+}
+
 struct LayerCtx {
     u32 cLo, cHi;         // message clip [-(msg_max+1), msg_max] as half2 ulps
     u32 cM2cap;           // msg_max+1: second minimum of a degree-1 check
@@ -129,16 +136,26 @@ struct LayerCtx {
 //   NK    rule: 0 = offset min-sum, 1..8 = normalised by NK/8, -1 = normalised, factor at run time
 //   DC    unrolled slots of edges with a stored message; MODE 0: exactly DC, 1: DC-1 or DC
 //   EXT   one more edge follows into a weight-1 shift-0 column (no stored message, no belief update)
-//   REG   stored messages live in the register array Rr instead of shared memory
+//   RM    where the stored messages live: 0 shared memory (Rrow, W words apart), 1 the register array Rr,
+//         2 streamed: this thread's 16-byte blocks in the shared ring (ring_me, filled by cp.async from the
+//         L2-resident scratch) in, its blocks in the scratch (rg_me) out
 //   Li    this thread's belief base address (slot beliefs + 4*i)
 //   Rrow  this thread's message word of the row's first stored edge; consecutive edges are W words apart
 //   etab  two int4 per edge: {off0, off1, thresh, hdw} {selA0, selA1, selW0, selW1}
-template <int NK, int DC, int MODE, bool EXT, bool REG, int RDC>
+template <int NK, int DC, int MODE, bool EXT, int RM, int RDC>
 __device__ __forceinline__ void process_layer(const LayerCtx &cx, char *Li, u32 *Rrow, u32 (&Rr)[RDC], int W,
-                                              const int4 *etab, int nc, int i, u32 synbits)
+                                              const int4 *etab, int nc, int i, u32 synbits,
+                                              const uint4 *ring_me = nullptr, uint4 *rg_me = nullptr)
 {
     // register rows recompute the belief address / pack selector in the second pass (register budget)
+    constexpr bool REG = RM == 1 || (RM == 2 && DC > 10);   // recompute instead of keeping per-edge state live
     constexpr int KEEP = REG ? 1 : DC;
+    constexpr int NV = RM == 2 ? (DC + 3) / 4 : 1;
+    uint4 Yv[NV];
+    if constexpr (RM == 2) {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) Yv[q] = ring_me[q];
+    }
     u32 uA[DC], uB[DC], tA[KEEP], tB[KEEP], sw[KEEP];
     char *ad[KEEP];
     // running sign product starts at the syndrome bit of each lane
@@ -157,7 +174,9 @@ __device__ __forceinline__ void process_layer(const LayerCtx &cx, char *Li, u32 
             if constexpr (!REG) { sw[j] = wrap ? sl.w : sl.z; ad[j] = a; }
             const u32 X = *reinterpret_cast<const u32 *>(a);
             u32 Y;
-            if constexpr (REG) Y = Rr[j]; else Y = Rrow[j * W];
+            if constexpr (RM == 1) Y = Rr[j];
+            else if constexpr (RM == 2) Y = vcomp(Yv[j >> 2], j & 3);
+            else Y = Rrow[j * W];
             const u32 xA = prmt(X, 0u, selA), xB = prmt(X, 0u, selA ^ 0x0202u);
             const u32 yA = prmt(Y, 0u, 0x4140u), yB = prmt(Y, 0u, 0x4342u);
             const u32 ua = hsub(xA, yA), ub = hsub(xB, yB);          // L - R_old  (:51)
@@ -235,17 +254,22 @@ __device__ __forceinline__ void process_layer(const LayerCtx &cx, char *Li, u32 
             const u32 lA = hmin(hadd_relu(uA[j], bA), cx.c255);       // clip(L - R_old + R_new) biased (:88-91)
             const u32 lB = hmin(hadd_relu(uB[j], bB), cx.c255);
             const u32 Ynew = prmt(bA, bB, 0x6420u);
+            if constexpr (RM == 1) Rr[j] = Ynew;
+            else if constexpr (RM == 2) vset(Yv[j >> 2], j & 3, Ynew);
+            else Rrow[j * W] = Ynew;
             if constexpr (REG) {
-                Rr[j] = Ynew;
                 const int4 ed = etab[2 * j];
                 const int4 sl = etab[2 * j + 1];
                 const bool wrap = i >= ed.z;
                 *reinterpret_cast<u32 *>(Li + (wrap ? ed.y : ed.x)) = prmt(lA, lB, wrap ? sl.w : sl.z);
             } else {
-                Rrow[j * W] = Ynew;
                 *reinterpret_cast<u32 *>(ad[j]) = prmt(lA, lB, sw[j]);
             }
         }
+    }
+    if constexpr (RM == 2) {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) rg_me[q] = Yv[q];
     }
 #if !QL_OPT_EXTEARLY
     if constexpr (EXT) {   // only the sign of channel + new message is observable: ballot it into the hd vector
@@ -267,12 +291,12 @@ __device__ __forceinline__ void process_layer(const LayerCtx &cx, char *Li, u32 
 
 // BIG: rows with more than 10 stored edges exist (never together with register rows: the host
 // only enables those when every other row has at most 10 stored edges)
-template <int NK, bool EXT, bool BIG>
+template <int NK, bool EXT, bool BIG, int RM>
 __device__ __forceinline__ void dispatch_layer(const LayerCtx &cx, char *Li, u32 *Rrow, int W, const int4 *et, int nc,
-                                               int i, u32 synbits)
+                                               int i, u32 synbits, const uint4 *ring_me = nullptr, uint4 *rg_me = nullptr)
 {
     u32 dummy[1];
-#define QL_CASE(DCV, MODEV) process_layer<NK, DCV, MODEV, EXT, false, 1>(cx, Li, Rrow, dummy, W, et, nc, i, synbits)
+#define QL_CASE(DCV, MODEV) process_layer<NK, DCV, MODEV, EXT, RM, 1>(cx, Li, Rrow, dummy, W, et, nc, i, synbits, ring_me, rg_me)
 #if QL_OPT_PAIRS
     // buckets of two (last slot optional): few code variants keep the instruction working set small
     switch ((nc + 1) >> 1) {
@@ -336,9 +360,19 @@ __device__ __forceinline__ void transpose4x4(const u32 (&in)[4], u32 (&out)[4])
     out[3] = prmt(t2, t3, 0x7632u);
 }
 
-// REGDC: 0, or the unrolled degree of the kRegRows rows whose messages live in registers
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// REGDC: 0, or the unrolled degree of the kRegRows rows whose messages live in registers,
+//        or -1: streamed mode (messages in an L2-resident scratch, 2-deep cp.async ring, up to 384 threads)
 template <int NK, int REGDC>
-__global__ void __launch_bounds__(kMaxBlock, 1) layered_i8_kernel(const LayeredI8Params p)
+__global__ void __launch_bounds__(REGDC < 0 ? kMaxBlockStream : kMaxBlock, 1) layered_i8_kernel(const LayeredI8Params p)
 {
     extern __shared__ __align__(16) char smem[];
     const int tpg = p.tpg, W = p.W, Z = p.Z, ZW32 = p.ZW32;
@@ -379,8 +413,12 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layered_i8_kernel(const LayeredI
     cx.lane = lane;
     cx.wq = W >> 5;
 
+    constexpr bool STREAM = REGDC < 0;
     constexpr int RDC = REGDC > 0 ? REGDC : 1;
     u32 Rreg0[RDC], Rreg1[RDC], Rreg2[RDC], Rreg3[RDC];
+    uint4 *ring = reinterpret_cast<uint4 *>(slot + p.off_R);                       // 2 stages of stage_words
+    u32 *rg_slot = STREAM ? p.rg + ((size_t)blockIdx.x * p.slots + g) * (size_t)p.rg_words : nullptr;
+    const int stage_v = p.stage_words >> 2;
 
     for (int f = blockIdx.x * p.slots + g; f < p.F; f += gridDim.x * p.slots) {
         // ---- load: int8 LLRs -> interleaved biased belief words; messages = 0
@@ -414,7 +452,13 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layered_i8_kernel(const LayeredI
                 Lw[c * W + i] = (b0 | (b1 << 8) | (b2 << 16) | (b3 << 24)) ^ 0x80808080u;
             }
         }
-        if ((W & 3) == 0) {
+        if constexpr (STREAM) {
+            // first row's messages are zero: fill stage 0 (nothing may still be in flight from the previous frame)
+            cp_async_wait<0>();
+            const int nv0 = ltab[0].st >> 2;
+            if (active)
+                for (int q = 0; q < nv0; ++q) ring[i * nv0 + q] = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+        } else if ((W & 3) == 0) {
             for (int idx = i; idx < p.n_store * (W >> 2); idx += tpg)
                 reinterpret_cast<uint4 *>(Rw)[idx] = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
         } else {
@@ -445,6 +489,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layered_i8_kernel(const LayeredI
         bar_sync(bar_id, tpg);
 
         int it = 0;
+        int stage = 0;
         bool conv = false;
         for (;;) {
             if (it < p.max_iter) {
@@ -461,7 +506,26 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layered_i8_kernel(const LayeredI
                         }
                         char *Li = slot + 4 * i;
                         const int4 *et = etab + 2 * ly.edge_begin;
-                        if (REGDC > 0 && ly.reg_idx >= 0) {
+                        if constexpr (STREAM) {
+                            // stage the NEXT row's messages while this row is processed
+                            const int rn = r + 1 < p.brows ? r + 1 : 0;
+                            const Li8Layer nx = ltab[rn];
+                            const int nvn = nx.st >> 2;
+                            uint4 *dst = ring + (stage ^ 1) * stage_v + i * nvn;
+                            if (it == 0 && rn != 0) {          // not written yet in this frame: zero messages
+                                for (int q = 0; q < nvn; ++q) dst[q] = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+                            } else {
+                                const uint4 *src = reinterpret_cast<const uint4 *>(rg_slot + nx.g_off + i * nx.st);
+                                for (int q = 0; q < nvn; ++q) cp_async16(dst + q, src + q);
+                            }
+                            cp_async_commit();
+                            cp_async_wait<1>();                  // this row's stage has landed
+                            const int nv = ly.st >> 2;
+                            const uint4 *ring_me = ring + stage * stage_v + i * nv;
+                            uint4 *rg_me = reinterpret_cast<uint4 *>(rg_slot + ly.g_off + i * ly.st);
+                            if (ly.has_ext) dispatch_layer<NK, true, true, 2>(cx, Li, nullptr, W, et, ly.n_core, i, synbits, ring_me, rg_me);
+                            else dispatch_layer<NK, false, true, 2>(cx, Li, nullptr, W, et, ly.n_core, i, synbits, ring_me, rg_me);
+                        } else if (REGDC > 0 && ly.reg_idx >= 0) {
                             if constexpr (REGDC > 0) {
 #if QL_OPT_REGDEDUPE
                                 // one code copy for all register rows: move the row's messages through a working array
@@ -469,7 +533,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layered_i8_kernel(const LayeredI
                                 const int ri = ly.reg_idx;
 #pragma unroll
                                 for (int j = 0; j < RDC; ++j) Rc[j] = ri == 0 ? Rreg0[j] : (ri == 1 ? Rreg1[j] : (ri == 2 ? Rreg2[j] : Rreg3[j]));
-                                process_layer<NK, RDC, 1, false, true, RDC>(cx, Li, nullptr, Rc, W, et, ly.n_core, i, synbits);
+                                process_layer<NK, RDC, 1, false, 1, RDC>(cx, Li, nullptr, Rc, W, et, ly.n_core, i, synbits);
 #pragma unroll
                                 for (int j = 0; j < RDC; ++j) {
                                     if (ri == 0) Rreg0[j] = Rc[j];
@@ -479,19 +543,20 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layered_i8_kernel(const LayeredI
                                 }
 #else
                                 switch (ly.reg_idx) {
-                                case 0: process_layer<NK, RDC, 1, false, true, RDC>(cx, Li, nullptr, Rreg0, W, et, ly.n_core, i, synbits); break;
-                                case 1: process_layer<NK, RDC, 1, false, true, RDC>(cx, Li, nullptr, Rreg1, W, et, ly.n_core, i, synbits); break;
-                                case 2: process_layer<NK, RDC, 1, false, true, RDC>(cx, Li, nullptr, Rreg2, W, et, ly.n_core, i, synbits); break;
-                                default: process_layer<NK, RDC, 1, false, true, RDC>(cx, Li, nullptr, Rreg3, W, et, ly.n_core, i, synbits); break;
+                                case 0: process_layer<NK, RDC, 1, false, 1, RDC>(cx, Li, nullptr, Rreg0, W, et, ly.n_core, i, synbits); break;
+                                case 1: process_layer<NK, RDC, 1, false, 1, RDC>(cx, Li, nullptr, Rreg1, W, et, ly.n_core, i, synbits); break;
+                                case 2: process_layer<NK, RDC, 1, false, 1, RDC>(cx, Li, nullptr, Rreg2, W, et, ly.n_core, i, synbits); break;
+                                default: process_layer<NK, RDC, 1, false, 1, RDC>(cx, Li, nullptr, Rreg3, W, et, ly.n_core, i, synbits); break;
                                 }
 #endif
                             }
                         } else {
                             u32 *Rrow = Rw + ly.r_off * W + i;
-                            if (ly.has_ext) dispatch_layer<NK, true, REGDC == 0>(cx, Li, Rrow, W, et, ly.n_core, i, synbits);
-                            else dispatch_layer<NK, false, REGDC == 0>(cx, Li, Rrow, W, et, ly.n_core, i, synbits);
+                            if (ly.has_ext) dispatch_layer<NK, true, REGDC == 0, 0>(cx, Li, Rrow, W, et, ly.n_core, i, synbits);
+                            else dispatch_layer<NK, false, REGDC == 0, 0>(cx, Li, Rrow, W, et, ly.n_core, i, synbits);
                         }
                     }
+                    if constexpr (STREAM) stage ^= 1;
                     bar_sync(bar_id, tpg);
                 }
                 ++it;
@@ -609,6 +674,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layered_i8_kernel(const LayeredI
 }  // namespace
 
 int layered_i8_max_threads() { return kMaxBlock; }
+int layered_i8_max_threads_stream() { return kMaxBlockStream; }
 
 template <int NK, int REGDC>
 static int launch_nk(const LayeredI8Params &p, int grid, int smem_bytes, cudaStream_t st)
@@ -637,6 +703,7 @@ static int launch_reg(const LayeredI8Params &p, int grid, int smem_bytes, cudaSt
 
 int launch_layered_i8(const LayeredI8Params &p, int grid, int smem_bytes, cudaStream_t st)
 {
+    if (p.stream) return launch_reg<-1>(p, grid, smem_bytes, st);
     if (p.regdc == 20) return launch_reg<20>(p, grid, smem_bytes, st);
     if (p.regdc == 0) return launch_reg<0>(p, grid, smem_bytes, st);
     return QLDPC_ERR_UNSUPPORTED;

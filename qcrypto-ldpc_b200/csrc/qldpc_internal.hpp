@@ -46,13 +46,16 @@ struct Li8Edge {         // 32 bytes, read as two int4 broadcasts
     int32_t selW0;       // PRMT selector packing two half2 pairs back into a belief word, no wrap
     int32_t selW1;       // ... with wrap
 };
-struct Li8Layer {        // 16 bytes
+struct Li8Layer {        // 24 bytes
     int32_t edge_begin;  // first edge of the block row (edges are row-major, columns ascending)
     int16_t degree;      // all edges of the row
     int16_t n_core;      // edges whose messages are stored (degree - has_ext)
     int32_t r_off;       // index of the row's first stored message (units of W words), -1 for register rows
     int16_t reg_idx;     // 0..3: messages live in registers, -1 otherwise
     int16_t has_ext;     // last edge goes to a weight-1, shift-0 column: no stored message, no belief update
+    int32_t g_off;       // streamed mode: word offset of the row's messages in the per-frame scratch
+    int16_t st;          // streamed mode: words per thread in that row (n_core rounded up to 4)
+    int16_t pad;
 };
 // generic QC tables (syndrome phase of the int8 kernel, generic layered kernel)
 struct QcEdgeAux {       // 8 bytes
@@ -139,4 +142,7 @@ struct qldpc_decoder {
     // layered int8 launch geometry
     int li8_slots = 0, li8_tpg = 0, li8_smem = 0, li8_regdc = 0, li8_n_store = 0, li8_n_pack = 0;
     bool li8_ext = false;
+    bool li8_stream = false;          // messages streamed through an L2-resident scratch (4 frames per SM)
+    int li8_rg_words = 0;             // scratch words per frame slot
+    qldpc::DevBuf<uint32_t> d_li8_rg;
 };

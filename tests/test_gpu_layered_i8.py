@@ -50,6 +50,16 @@ def test_bg1_z384_qber3(q, O, data_dir, mode, rule, k8, offset):
     assert ok.all()
 
 
+@pytest.mark.parametrize("mode", ["resident", "stream"])
+def test_bg1_z384_both_message_placements(q, O, data_dir, mode, monkeypatch):
+    """the kernel keeps check-to-variable messages either resident in shared memory (+ register rows, 2 frames/SM)
+    or streamed through an L2-resident scratch (4 frames/SM); both must be bit-exact"""
+    monkeypatch.setenv("QLDPC_LI8_MODE", mode)
+    _run_case(q, O, data_dir, "NR_1_1_384.qc", 40, 0.05, 12, "syndrome", q.RULE_NMS, 10, True, k8=6, seed=21)
+    _run_case(q, O, data_dir, "NR_1_1_384.qc", 24, 0.03, 14, "parity", q.RULE_OMS, 3, False, offset=2, seed=22)
+    _run_case(q, O, data_dir, "NR_2_3_112.qc", 24, 0.03, 14, "parity", q.RULE_NMS, 10, True, seed=23)
+
+
 def test_bg1_z384_fixed_iterations_matlab_constants(q, O, data_dir):
     # ML/BPSK_nrldpc_sim_FP.m constants: offset 2, no early stop; 20 iterations cut to 6 for test time
     _run_case(q, O, data_dir, "NR_1_1_384.qc", 24, 0.06, 11, "syndrome", q.RULE_OMS, 6, False, offset=2)

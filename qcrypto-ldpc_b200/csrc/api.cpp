@@ -142,7 +142,7 @@ bool plan_layered_i8(qldpc_decoder *d, LayeredI8Params &p, bool upload)
     p.Z = c.z; p.W = W; p.ZW32 = ZW32;
     p.brows = R; p.bcols = C; p.nnz = nnz; p.N = c.n;
     p.n_pack = (int)pack_cols.size();
-    p.tab_bytes = round_up(nnz * (int)(sizeof(Li8Edge) + sizeof(QcEdgeAux)) + R * (int)sizeof(Li8Layer) + C * 2, 16);
+    p.tab_bytes = round_up(nnz * (int)(sizeof(Li8Edge) + sizeof(QcEdgeAux)) + R * (int)sizeof(Li8Layer) + round_up(C, 8) * 2 + 16, 16) + 128;
     const int L_bytes = C * W * 4;
     const int hd_bytes = round_up(C * ZW32 * 4, 16);
     const int syn_bytes = round_up(R * ZW32 * 4, 16);
@@ -492,6 +492,13 @@ extern "C" int qldpc_decode_device(qldpc_decoder *dec, const void *d_llr, const 
         p.syn_words = d->syn_words;
         p.max_iter = cfg.max_iter; p.early_stop = cfg.early_stop;
         p.rule = cfg.rule; p.offset = d->offset_int; p.norm_eighths = d->norm_eighths; p.msg_max = cfg.msg_max;
+        {
+            auto dup = [](uint32_t v) { return (v & 0xffffu) | (v << 16); };
+            p.h2_lo = dup(0x8000u | (uint32_t)(cfg.msg_max + 1));
+            p.h2_hi = dup((uint32_t)cfg.msg_max);
+            p.h2_cap = dup((uint32_t)(cfg.msg_max + 1));
+            p.h2_negoff = dup(0x8000u | (uint32_t)d->offset_int);
+        }
         const int grid = std::min(d->sm_count, (n_frames + p.slots - 1) / p.slots);
         if (p.stream) {
             if ((rc = d->d_li8_rg.ensure((size_t)d->sm_count * p.slots * p.rg_words))) return rc;

@@ -27,6 +27,7 @@ struct LayeredI8Params {
     int out_words, syn_words; // per frame
     int max_iter, early_stop;
     int rule, offset, norm_eighths, msg_max;
+    uint32_t h2_lo, h2_hi, h2_cap, h2_negoff;   // half2 bit patterns: -(msg_max+1), msg_max, msg_max+1, -offset (units of 2^-24)
     int slots, tpg;           // frames in flight per CTA, threads per frame group
     int tab_bytes;            // shared tables at the start of dynamic smem
     int slot_bytes;           // bytes per frame slot

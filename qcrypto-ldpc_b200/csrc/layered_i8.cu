@@ -376,8 +376,9 @@ __global__ void __launch_bounds__(REGDC < 0 ? kMaxBlockStream : kMaxBlock, 1) la
 {
     extern __shared__ __align__(16) char smem[];
     const int tpg = p.tpg, W = p.W, Z = p.Z, ZW32 = p.ZW32;
-    const int g = threadIdx.x / tpg, i = threadIdx.x - g * tpg;
-    const int lane = threadIdx.x & 31, wis = i >> 5;
+    const int g = threadIdx.y, i = threadIdx.x;          // block = (tpg, slots); tpg is a multiple of 32
+    const int lane = i & 31, wis = i >> 5;
+    const int tid = g * tpg + i, nthreads = tpg * blockDim.y;
     const int bar_id = 1 + g;
     const bool active = i < W;
     const bool aligned = (W & 31) == 0;      // every ballot lands on whole words
@@ -388,10 +389,13 @@ __global__ void __launch_bounds__(REGDC < 0 ? kMaxBlockStream : kMaxBlock, 1) la
     QcEdgeAux *atab = reinterpret_cast<QcEdgeAux *>(etab + 2 * p.nnz);
     Li8Layer *ltab = reinterpret_cast<Li8Layer *>(atab + p.nnz);
     uint16_t *pcols = reinterpret_cast<uint16_t *>(ltab + p.brows);
-    for (int e = threadIdx.x; e < 2 * p.nnz; e += blockDim.x) etab[e] = reinterpret_cast<const int4 *>(p.edges)[e];
-    for (int e = threadIdx.x; e < p.nnz; e += blockDim.x) atab[e] = p.aux[e];
-    for (int r = threadIdx.x; r < p.brows; r += blockDim.x) ltab[r] = p.layers[r];
-    for (int c = threadIdx.x; c < p.n_pack; c += blockDim.x) pcols[c] = p.pack_cols[c];
+    for (int e = tid; e < 2 * p.nnz; e += nthreads) etab[e] = reinterpret_cast<const int4 *>(p.edges)[e];
+    for (int e = tid; e < p.nnz; e += nthreads) atab[e] = p.aux[e];
+    for (int r = tid; r < p.brows; r += nthreads) ltab[r] = p.layers[r];
+    for (int c = tid; c < p.n_pack; c += nthreads) pcols[c] = p.pack_cols[c];
+    // 8 x 16 bytes of biased zero messages, 16-byte aligned, right after the tables
+    uint4 *zero_blk = reinterpret_cast<uint4 *>(smem + ((reinterpret_cast<char *>(pcols + p.bcols) - smem + 15) & ~15));
+    if (tid < 8) zero_blk[tid] = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
     __syncthreads();
 
     char *slot = smem + p.tab_bytes + (size_t)g * p.slot_bytes;
@@ -401,13 +405,13 @@ __global__ void __launch_bounds__(REGDC < 0 ? kMaxBlockStream : kMaxBlock, 1) la
     u32 *synl = reinterpret_cast<u32 *>(slot + p.off_syn);
 
     LayerCtx cx;
-    cx.cLo = dup16(0x8000u | (u32)(p.msg_max + 1));
-    cx.cHi = dup16((u32)p.msg_max);
-    cx.cM2cap = dup16((u32)(p.msg_max + 1));
-    cx.c128 = dup16(128u);
-    cx.c255 = dup16(255u);
+    cx.cLo = p.h2_lo;           // half2 constants prepared by the host: they stay constant-bank operands
+    cx.cHi = p.h2_hi;
+    cx.cM2cap = p.h2_cap;
+    cx.c128 = 0x00800080u;
+    cx.c255 = 0x00ff00ffu;
     cx.norm_eighths = p.norm_eighths;
-    cx.negOff = dup16(0x8000u | (u32)p.offset);
+    cx.negOff = p.h2_negoff;
     cx.hd = hd;
     cx.wis = wis;
     cx.lane = lane;
@@ -417,7 +421,7 @@ __global__ void __launch_bounds__(REGDC < 0 ? kMaxBlockStream : kMaxBlock, 1) la
     constexpr int RDC = REGDC > 0 ? REGDC : 1;
     u32 Rreg0[RDC], Rreg1[RDC], Rreg2[RDC], Rreg3[RDC];
     uint4 *ring = reinterpret_cast<uint4 *>(slot + p.off_R);                       // 2 stages of stage_words
-    u32 *rg_slot = STREAM ? p.rg + ((size_t)blockIdx.x * p.slots + g) * (size_t)p.rg_words : nullptr;
+    const u32 rg_off = STREAM ? (blockIdx.x * p.slots + g) * (u32)p.rg_words : 0u;   // word offset of this slot's scratch
     const int stage_v = p.stage_words >> 2;
 
     for (int f = blockIdx.x * p.slots + g; f < p.F; f += gridDim.x * p.slots) {
@@ -453,11 +457,7 @@ __global__ void __launch_bounds__(REGDC < 0 ? kMaxBlockStream : kMaxBlock, 1) la
             }
         }
         if constexpr (STREAM) {
-            // first row's messages are zero: fill stage 0 (nothing may still be in flight from the previous frame)
-            cp_async_wait<0>();
-            const int nv0 = ltab[0].st >> 2;
-            if (active)
-                for (int q = 0; q < nv0; ++q) ring[i * nv0 + q] = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+            cp_async_wait<0>();   // nothing may still be in flight from the previous frame of this slot
         } else if ((W & 3) == 0) {
             for (int idx = i; idx < p.n_store * (W >> 2); idx += tpg)
                 reinterpret_cast<uint4 *>(Rw)[idx] = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
@@ -507,22 +507,23 @@ __global__ void __launch_bounds__(REGDC < 0 ? kMaxBlockStream : kMaxBlock, 1) la
                         char *Li = slot + 4 * i;
                         const int4 *et = etab + 2 * ly.edge_begin;
                         if constexpr (STREAM) {
-                            // stage the NEXT row's messages while this row is processed
+                            // stage the NEXT row's messages while this row is processed; during the first
+                            // iteration every row reads a shared block of zero messages instead
                             const int rn = r + 1 < p.brows ? r + 1 : 0;
-                            const Li8Layer nx = ltab[rn];
-                            const int nvn = nx.st >> 2;
-                            uint4 *dst = ring + (stage ^ 1) * stage_v + i * nvn;
-                            if (it == 0 && rn != 0) {          // not written yet in this frame: zero messages
-                                for (int q = 0; q < nvn; ++q) dst[q] = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
-                            } else {
-                                const uint4 *src = reinterpret_cast<const uint4 *>(rg_slot + nx.g_off + i * nx.st);
-                                for (int q = 0; q < nvn; ++q) cp_async16(dst + q, src + q);
+                            if (it > 0 || rn == 0) {
+                                const Li8Layer nx = ltab[rn];
+                                const int nvn = nx.st >> 2;
+                                uint4 *dst = ring + (stage ^ 1) * stage_v + i * nvn;
+                                const uint4 *src = reinterpret_cast<const uint4 *>(p.rg + (rg_off + nx.g_off + i * nx.st));
+#pragma unroll
+                                for (int q = 0; q < 5; ++q)
+                                    if (q < nvn) cp_async16(dst + q, src + q);
                             }
                             cp_async_commit();
                             cp_async_wait<1>();                  // this row's stage has landed
                             const int nv = ly.st >> 2;
-                            const uint4 *ring_me = ring + stage * stage_v + i * nv;
-                            uint4 *rg_me = reinterpret_cast<uint4 *>(rg_slot + ly.g_off + i * ly.st);
+                            const uint4 *ring_me = it == 0 ? zero_blk : ring + stage * stage_v + i * nv;
+                            uint4 *rg_me = reinterpret_cast<uint4 *>(p.rg + (rg_off + ly.g_off + i * ly.st));
                             if (ly.has_ext) dispatch_layer<NK, true, true, 2>(cx, Li, nullptr, W, et, ly.n_core, i, synbits, ring_me, rg_me);
                             else dispatch_layer<NK, false, true, 2>(cx, Li, nullptr, W, et, ly.n_core, i, synbits, ring_me, rg_me);
                         } else if (REGDC > 0 && ly.reg_idx >= 0) {
@@ -680,7 +681,7 @@ template <int NK, int REGDC>
 static int launch_nk(const LayeredI8Params &p, int grid, int smem_bytes, cudaStream_t st)
 {
     QLDPC_CUDA(cudaFuncSetAttribute(layered_i8_kernel<NK, REGDC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    layered_i8_kernel<NK, REGDC><<<grid, p.slots * p.tpg, smem_bytes, st>>>(p);
+    layered_i8_kernel<NK, REGDC><<<grid, dim3(p.tpg, p.slots), smem_bytes, st>>>(p);
     QLDPC_CUDA(cudaGetLastError());
     return QLDPC_OK;
 }

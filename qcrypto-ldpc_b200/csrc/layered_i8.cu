@@ -144,7 +144,7 @@ struct LayerCtx {
 //   etab  two int4 per edge: {off0, off1, thresh, hdw} {selA0, selA1, selW0, selW1}
 template <int NK, int DC, int MODE, bool EXT, int RM, int RDC>
 __device__ __forceinline__ void process_layer(const LayerCtx &cx, char *Li, u32 *Rrow, u32 (&Rr)[RDC], int W,
-                                              const int4 *etab, int nc, int i, u32 synbits,
+                                              const int4 *etab, int nc, int i, uint2 m1init,
                                               const uint4 *ring_me = nullptr, uint4 *rg_me = nullptr)
 {
     // register rows recompute the belief address / pack selector in the second pass (register budget)
@@ -158,9 +158,8 @@ __device__ __forceinline__ void process_layer(const LayerCtx &cx, char *Li, u32 
     }
     u32 uA[DC], uB[DC], tA[KEEP], tB[KEEP], sw[KEEP];
     char *ad[KEEP];
-    // running sign product starts at the syndrome bit of each lane
-    u32 m1A = kInf2 ^ (((synbits & 1u) << 15) | ((synbits & 2u) << 30));
-    u32 m1B = kInf2 ^ (((synbits & 4u) << 13) | ((synbits & 8u) << 28));
+    // running sign product starts at the syndrome bit of each lane (folded into m1init by the caller)
+    u32 m1A = m1init.x, m1B = m1init.y;
     u32 m2A = kInf2, m2B = kInf2;
 
 #pragma unroll
@@ -230,9 +229,9 @@ __device__ __forceinline__ void process_layer(const LayerCtx &cx, char *Li, u32 
         const u32 b1 = __ballot_sync(0xffffffffu, (int)aA < 0);           // lane i + W
         const u32 b2 = __ballot_sync(0xffffffffu, (int)(aB << 16) < 0);   // lane i + 2W
         const u32 b3 = __ballot_sync(0xffffffffu, (int)aB < 0);           // lane i + 3W
-        if (cx.lane < 4) {
-            const u32 v = cx.lane == 0 ? b0 : (cx.lane == 1 ? b1 : (cx.lane == 2 ? b2 : b3));
-            cx.hd[ehdw + cx.wis + cx.wq * cx.lane] = v;
+        if (cx.lane == 0) {   // one lane stores the four words: no lane-dependent select
+            u32 *h = cx.hd + ehdw + cx.wis;
+            h[0] = b0; h[cx.wq] = b1; h[2 * cx.wq] = b2; h[3 * cx.wq] = b3;
         }
     }
 #endif
@@ -281,9 +280,9 @@ __device__ __forceinline__ void process_layer(const LayerCtx &cx, char *Li, u32 
         const u32 b1 = __ballot_sync(0xffffffffu, (int)aA < 0);           // lane i + W
         const u32 b2 = __ballot_sync(0xffffffffu, (int)(aB << 16) < 0);   // lane i + 2W
         const u32 b3 = __ballot_sync(0xffffffffu, (int)aB < 0);           // lane i + 3W
-        if (cx.lane < 4) {
-            const u32 v = cx.lane == 0 ? b0 : (cx.lane == 1 ? b1 : (cx.lane == 2 ? b2 : b3));
-            cx.hd[ehdw + cx.wis + cx.wq * cx.lane] = v;
+        if (cx.lane == 0) {   // one lane stores the four words: no lane-dependent select
+            u32 *h = cx.hd + ehdw + cx.wis;
+            h[0] = b0; h[cx.wq] = b1; h[2 * cx.wq] = b2; h[3 * cx.wq] = b3;
         }
     }
 #endif
@@ -293,10 +292,10 @@ __device__ __forceinline__ void process_layer(const LayerCtx &cx, char *Li, u32 
 // only enables those when every other row has at most 10 stored edges)
 template <int NK, bool EXT, bool BIG, int RM>
 __device__ __forceinline__ void dispatch_layer(const LayerCtx &cx, char *Li, u32 *Rrow, int W, const int4 *et, int nc,
-                                               int i, u32 synbits, const uint4 *ring_me = nullptr, uint4 *rg_me = nullptr)
+                                               int i, uint2 m1init, const uint4 *ring_me = nullptr, uint4 *rg_me = nullptr)
 {
     u32 dummy[1];
-#define QL_CASE(DCV, MODEV) process_layer<NK, DCV, MODEV, EXT, RM, 1>(cx, Li, Rrow, dummy, W, et, nc, i, synbits, ring_me, rg_me)
+#define QL_CASE(DCV, MODEV) process_layer<NK, DCV, MODEV, EXT, RM, 1>(cx, Li, Rrow, dummy, W, et, nc, i, m1init, ring_me, rg_me)
 #if QL_OPT_PAIRS
     // buckets of two (last slot optional): few code variants keep the instruction working set small
     switch ((nc + 1) >> 1) {
@@ -496,13 +495,16 @@ __global__ void __launch_bounds__(REGDC < 0 ? kMaxBlockStream : kMaxBlock, 1) la
                 for (int r = 0; r < p.brows; ++r) {
                     const Li8Layer ly = ltab[r];
                     if (active) {
-                        u32 synbits = 0;
+                        uint2 synbits = make_uint2(kInf2, kInf2);   // initial (min1, sign) of the two half2 pairs
                         if (p.syn) {
+                            u32 sb = 0;
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const int l = i + W * k;
-                                synbits |= ((synl[r * ZW32 + (l >> 5)] >> (l & 31)) & 1u) << k;
+                                sb |= ((synl[r * ZW32 + (l >> 5)] >> (l & 31)) & 1u) << k;
                             }
+                            synbits.x ^= ((sb & 1u) << 15) | ((sb & 2u) << 30);
+                            synbits.y ^= ((sb & 4u) << 13) | ((sb & 8u) << 28);
                         }
                         char *Li = slot + 4 * i;
                         const int4 *et = etab + 2 * ly.edge_begin;
@@ -575,9 +577,9 @@ __global__ void __launch_bounds__(REGDC < 0 ? kMaxBlockStream : kMaxBlock, 1) la
                         const u32 b1 = __ballot_sync(0xffffffffu, (X & 0x8000u) == 0u);
                         const u32 b2 = __ballot_sync(0xffffffffu, (X & 0x800000u) == 0u);
                         const u32 b3 = __ballot_sync(0xffffffffu, (int)X >= 0);
-                        if (lane < 4) {
-                            const u32 v = lane == 0 ? b0 : (lane == 1 ? b1 : (lane == 2 ? b2 : b3));
-                            hd[col * ZW32 + wis + cx.wq * lane] = v;
+                        if (lane == 0) {
+                            u32 *h = hd + col * ZW32 + wis;
+                            h[0] = b0; h[cx.wq] = b1; h[2 * cx.wq] = b2; h[3 * cx.wq] = b3;
                         }
                     }
                     bar_sync(bar_id, tpg);

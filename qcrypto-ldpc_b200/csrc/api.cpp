@@ -169,7 +169,8 @@ bool plan_layered_i8(qldpc_decoder *d, LayeredI8Params &p, bool upload)
     bool stream = slots_str > slots_res;
     if (force_stream && slots_str >= 1) stream = true;
     if (force_resident && slots_res >= 1) stream = false;
-    const int slots = stream ? slots_str : slots_res;
+    int slots = stream ? slots_str : slots_res;
+    if (const char *cap = std::getenv("QLDPC_LI8_SLOTS")) slots = std::min(slots, std::max(1, std::atoi(cap)));   // experiments
     if (slots < 1) return false;
     if (stream) {   // no register rows in streamed mode: every row's messages go through the ring
         regdc = 0;

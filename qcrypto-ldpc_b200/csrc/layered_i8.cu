@@ -37,7 +37,7 @@
 #define QL_OPT_LOADUNROLL 1
 #endif
 #ifndef QL_OPT_EXTEARLY
-#define QL_OPT_EXTEARLY 0
+#define QL_OPT_EXTEARLY 1
 #endif
 #ifndef QL_OPT_PAIRS
 #define QL_OPT_PAIRS 0
@@ -75,8 +75,23 @@ __device__ __forceinline__ u32 prmt(u32 a, u32 b, u32 sel)
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
     return d;
 }
+// clip to [-(msg_max+1), msg_max]; cap = msg_max+1, hi = msg_max. The lower bound is relu(u+cap)-cap on the
+// FMA pipe (HFMA2.RELU + HADD2) so that only the upper bound occupies the half-rate ALU pipe (HMNMX2)
+#ifndef QL_OPT_FMACLIP
+#define QL_OPT_FMACLIP 0   // measured: 41.5 vs 41.7 Gbit/s, no gain -> keep the shorter sequence
+#endif
 // relu(a + b)
 __device__ __forceinline__ u32 hadd_relu(u32 a, u32 b) { return bits(__hfma2_relu(h2(a), h2(kOne2), h2(b))); }
+__device__ __forceinline__ u32 clip_msg(u32 u, u32 lo, u32 hi, u32 cap)
+{
+#if QL_OPT_FMACLIP
+    (void)lo;
+    return hmin(hsub(hadd_relu(u, cap), cap), hi);
+#else
+    (void)cap;
+    return hmin(hmax(u, lo), hi);
+#endif
+}
 __device__ __forceinline__ u32 heq_mask(u32 a, u32 b) { return __heq2_mask(h2(a), h2(b)); }
 // |d| = min(|a|,|b|), sign(d) = sign(a) ^ sign(b)
 __device__ __forceinline__ u32 min_xorsign_abs(u32 a, u32 b)
@@ -179,8 +194,8 @@ __device__ __forceinline__ void process_layer(const LayerCtx &cx, char *Li, u32 
             const u32 xA = prmt(X, 0u, selA), xB = prmt(X, 0u, selA ^ 0x0202u);
             const u32 yA = prmt(Y, 0u, 0x4140u), yB = prmt(Y, 0u, 0x4342u);
             const u32 ua = hsub(xA, yA), ub = hsub(xB, yB);          // L - R_old  (:51)
-            const u32 ta = hmin(hmax(ua, cx.cLo), cx.cHi);            // clip to the message range (:54-55)
-            const u32 tb = hmin(hmax(ub, cx.cLo), cx.cHi);
+            const u32 ta = clip_msg(ua, cx.cLo, cx.cHi, cx.cM2cap);            // clip to the message range (:54-55)
+            const u32 tb = clip_msg(ub, cx.cLo, cx.cHi, cx.cM2cap);
             uA[j] = ua; uB[j] = ub;
             if constexpr (!REG) { tA[j] = ta; tB[j] = tb; }
             m2A = hmax(habs(m1A), hmin(habs(ta), m2A));               // second minimum (:61)
@@ -198,8 +213,8 @@ __device__ __forceinline__ void process_layer(const LayerCtx &cx, char *Li, u32 
         ehdw = ed.w;
         ueA = hsub(prmt(X, 0u, sl.x), cx.c128);
         ueB = hsub(prmt(X, 0u, sl.x ^ 0x0202u), cx.c128);
-        teA = hmin(hmax(ueA, cx.cLo), cx.cHi);
-        teB = hmin(hmax(ueB, cx.cLo), cx.cHi);
+        teA = clip_msg(ueA, cx.cLo, cx.cHi, cx.cM2cap);
+        teB = clip_msg(ueB, cx.cLo, cx.cHi, cx.cM2cap);
         m2A = hmax(habs(m1A), hmin(habs(teA), m2A));
         m2B = hmax(habs(m1B), hmin(habs(teB), m2B));
         m1A = min_xorsign_abs(m1A, teA);
@@ -240,8 +255,8 @@ __device__ __forceinline__ void process_layer(const LayerCtx &cx, char *Li, u32 
         if (MODE == 0 || j < DC - 1 || j < nc) {
             u32 ta, tb;
             if constexpr (REG) {   // register rows re-clip instead of keeping t live
-                ta = hmin(hmax(uA[j], cx.cLo), cx.cHi);
-                tb = hmin(hmax(uB[j], cx.cLo), cx.cHi);
+                ta = clip_msg(uA[j], cx.cLo, cx.cHi, cx.cM2cap);
+                tb = clip_msg(uB[j], cx.cLo, cx.cHi, cx.cM2cap);
             } else {
                 ta = tA[j]; tb = tB[j];
             }

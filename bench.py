@@ -55,52 +55,76 @@ def parse_args():
 # ------------------------------------------------------------------------------------------ helpers
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).
+    The sampler is started before the warm-up (nvidia-smi needs a few hundred ms to produce its first line) and the
+    samples are filtered to the wall-clock window of the timed region; when that window is shorter than the sampling
+    period the samples taken under the same load just before it (warm-up) are used and `window` says so."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.lines = []   # (wall time, csv line)
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            t = time.time()
+            while not self.lines and time.time() - t < 3.0:   # wait for the first sample
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.03)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
-            p = [x.strip() for x in l.split(",")]
-            if len(p) < 7:
-                continue
-            try:
-                sm.append(float(p[0])); mx.append(float(p[1])); pw.append(float(p[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, p[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
+
+        def parse(lines):
+            sm, mx, pw, reasons = [], [], [], set()
+            for _, l in lines:
+                p = [x.strip() for x in l.split(",")]
+                if len(p) < 7:
+                    continue
+                try:
+                    sm.append(float(p[0])); mx.append(float(p[1])); pw.append(float(p[2]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, p[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            return sm, mx, pw, reasons
+
+        inside = [x for x in self.lines if self.t0 is not None and self.t0 <= x[0] <= (self.t1 or 1e30)]
+        window = "timed region"
+        if len(inside) < 2:   # region shorter than the sampling period: use the loaded samples right before it
+            inside = [x for x in self.lines if self.t0 is None or x[0] >= self.t0 - 0.5]
+            window = "timed region + warm-up (same load)"
+        sm, mx, pw, reasons = parse(inside)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def measured_peak_hbm():
@@ -232,6 +256,9 @@ def run_ours(args, rank, world, local_rank):
         if world > 1:
             dist.barrier()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -239,17 +266,16 @@ def run_ours(args, rank, world, local_rank):
     assert bool((out[:, :kw] == msg).all()) and bool(ok.all()), "decoded bits differ from Alice's key"
     dec.reset_stats()
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
     torch.cuda.synchronize()
+    sampler.mark_begin()
     ev[0].record()
     for s in range(args.steps):
         step()
         ev[s + 1].record()
     torch.cuda.synchronize()
+    sampler.mark_end()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     total_ms = ev[0].elapsed_time(ev[-1])

@@ -403,7 +403,7 @@ extern "C" int qldpc_decoder_create(const qldpc_code *code, const qldpc_decoder_
         if (fast) {
             d->kernel_family = KF_LAYERED_I8;
             d->kernel_name = "layered_i8_zpack4";
-            if (d->li8_stream && (rc = d->d_li8_rg.ensure((size_t)d->sm_count * d->li8_slots * d->li8_rg_words))) return bail(rc);
+            if (d->li8_stream && (rc = d->d_li8_rg.ensure(2 * (size_t)d->sm_count * d->li8_slots * d->li8_rg_words))) return bail(rc);
         } else {
             d->kernel_family = KF_LAYERED_GENERIC;
             d->kernel_name = "layered_generic";
@@ -460,9 +460,12 @@ static int ensure_scratch(qldpc_decoder_full *d)
     return QLDPC_OK;
 }
 
-extern "C" int qldpc_decode_device(qldpc_decoder *dec, const void *d_llr, const uint32_t *d_syndrome, int32_t n_frames,
-                                   uint32_t *d_out_bits, uint8_t *d_ok, uint16_t *d_iters, void *d_posterior,
-                                   void *cuda_stream)
+// scratch_lane: which copy of the streamed-message scratch to use. Launches that may overlap in time (the two
+// streams of the host-pointer pipelines) MUST use different copies; the public device entry point uses copy 0,
+// so a decoder supports one qldpc_decode_device call in flight at a time.
+static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint32_t *d_syndrome, int32_t n_frames,
+                              uint32_t *d_out_bits, uint8_t *d_ok, uint16_t *d_iters, void *d_posterior,
+                              void *cuda_stream, int scratch_lane)
 {
     if (!dec || !d_llr || !d_out_bits || n_frames < 0) return QLDPC_ERR_ARG;
     if (n_frames == 0) return QLDPC_OK;
@@ -502,8 +505,9 @@ extern "C" int qldpc_decode_device(qldpc_decoder *dec, const void *d_llr, const 
         }
         const int grid = std::min(d->sm_count, (n_frames + p.slots - 1) / p.slots);
         if (p.stream) {
-            if ((rc = d->d_li8_rg.ensure((size_t)d->sm_count * p.slots * p.rg_words))) return rc;
-            p.rg = d->d_li8_rg.p;
+            const size_t lane_words = (size_t)d->sm_count * p.slots * p.rg_words;
+            if ((rc = d->d_li8_rg.ensure(2 * lane_words))) return rc;
+            p.rg = d->d_li8_rg.p + (size_t)scratch_lane * lane_words;
         }
         if ((rc = launch_layered_i8(p, grid, d->li8_smem, st))) return rc;
         d->kernel_launches++;
@@ -558,6 +562,24 @@ extern "C" int qldpc_decode_device(qldpc_decoder *dec, const void *d_llr, const 
     return QLDPC_OK;
 }
 
+extern "C" int qldpc_decode_device(qldpc_decoder *dec, const void *d_llr, const uint32_t *d_syndrome, int32_t n_frames,
+                                   uint32_t *d_out_bits, uint8_t *d_ok, uint16_t *d_iters, void *d_posterior,
+                                   void *cuda_stream)
+{
+    return decode_device_impl(dec, d_llr, d_syndrome, n_frames, d_out_bits, d_ok, d_iters, d_posterior, cuda_stream, 0);
+}
+
+// Chunk size of the host-pointer entry points: whole waves of the persistent grid (no ragged last wave), about
+// `target_bytes` of device input per chunk; QLDPC_CHUNK_FRAMES overrides (experiments).
+static int pick_chunk(const qldpc_decoder_full *d, size_t frame_bytes, size_t target_bytes, int n_frames)
+{
+    const int wave = d->sm_count * std::max(1, d->li8_slots);
+    long long chunk = (long long)std::max<size_t>(1, target_bytes / frame_bytes);
+    if (const char *e = std::getenv("QLDPC_CHUNK_FRAMES")) chunk = std::max(1, std::atoi(e));
+    chunk = std::max<long long>(wave, (chunk + wave / 2) / wave * wave);
+    return (int)std::min<long long>(chunk, n_frames);
+}
+
 // Host-pointer entry point: frames are cut into chunks that ping-pong over two streams so the
 // H2D copy of chunk i+1 overlaps the decode of chunk i and the D2H of chunk i-1.
 extern "C" int qldpc_decode(qldpc_decoder *dec, const void *llr, const uint32_t *syndrome, int32_t n_frames,
@@ -571,9 +593,7 @@ extern "C" int qldpc_decode(qldpc_decoder *dec, const void *llr, const uint32_t 
     const size_t esz = dtype_size(d->cfg.dtype);
     const size_t frame_in = (size_t)c.n * esz;
     // chunk: ~64 MiB of LLRs, at least one wave of the persistent grid
-    int chunk = (int)std::max<size_t>(1, (64u << 20) / frame_in);
-    chunk = std::max(chunk, d->sm_count * std::max(1, d->li8_slots));
-    chunk = std::min(chunk, n_frames);
+    const int chunk = pick_chunk(d, frame_in, 128u << 20, n_frames);
     // the scratch of the gather path is shared: those configurations run on one lane only
     const bool shared_scratch = !(d->kernel_family == KF_LAYERED_I8 && !posterior &&
                                   (d->cfg.out_mode == QLDPC_OUT_ALL || d->info_is_prefix));
@@ -595,8 +615,8 @@ extern "C" int qldpc_decode(qldpc_decoder *dec, const void *llr, const uint32_t 
         if (syndrome)
             QLDPC_CUDA(cudaMemcpyAsync(ln.syn.p, syndrome + (size_t)f0 * d->syn_words, (size_t)nf * d->syn_words * 4,
                                        cudaMemcpyHostToDevice, ln.st));
-        rc = qldpc_decode_device(dec, ln.in.p, syndrome ? ln.syn.p : nullptr, nf, ln.out.p, ln.ok.p, ln.iters.p,
-                                 posterior ? ln.post.p : nullptr, ln.st);
+        rc = decode_device_impl(dec, ln.in.p, syndrome ? ln.syn.p : nullptr, nf, ln.out.p, ln.ok.p, ln.iters.p,
+                                posterior ? ln.post.p : nullptr, ln.st, shared_scratch ? 0 : (idx & 1));
         if (rc) break;
         QLDPC_CUDA(cudaMemcpyAsync(out_bits + (size_t)f0 * d->out_words, ln.out.p, (size_t)nf * d->out_words * 4,
                                    cudaMemcpyDeviceToHost, ln.st));
@@ -715,9 +735,7 @@ extern "C" int qldpc_decode_bits(qldpc_decoder *dec, const uint32_t *bits, const
     QLDPC_CUDA(cudaSetDevice(d->cfg.device));
     const size_t esz = dtype_size(d->cfg.dtype);
     const size_t frame_llr = (size_t)c.n * esz;
-    int chunk = (int)std::max<size_t>(1, (128u << 20) / frame_llr);
-    chunk = std::max(chunk, d->sm_count * std::max(1, d->li8_slots) * 4);
-    chunk = std::min(chunk, n_frames);
+    const int chunk = pick_chunk(d, frame_llr, 128u << 20, n_frames);
     const bool shared_scratch = !(d->kernel_family == KF_LAYERED_I8 && (d->cfg.out_mode == QLDPC_OUT_ALL || d->info_is_prefix));
     int rc = QLDPC_OK;
     Lane &l0 = d->lanes.lane[0];
@@ -751,8 +769,8 @@ extern "C" int qldpc_decode_bits(qldpc_decoder *dec, const uint32_t *bits, const
             QLDPC_CUDA(cudaMemcpyAsync(ln.syn.p, syndrome + (size_t)f0 * d->syn_words, (size_t)nf * d->syn_words * 4,
                                        cudaMemcpyHostToDevice, ln.st));
         if ((rc = qldpc_make_llr_device(dec, ln.bits.p, dk, dp, llr_noisy, llr_known, nf, ln.in.p, ln.st))) break;
-        if ((rc = qldpc_decode_device(dec, ln.in.p, syndrome ? ln.syn.p : nullptr, nf, ln.out.p, ln.ok.p, ln.iters.p, nullptr,
-                                      ln.st))) break;
+        if ((rc = decode_device_impl(dec, ln.in.p, syndrome ? ln.syn.p : nullptr, nf, ln.out.p, ln.ok.p, ln.iters.p, nullptr,
+                                     ln.st, shared_scratch ? 0 : (idx & 1)))) break;
         QLDPC_CUDA(cudaMemcpyAsync(out_bits + (size_t)f0 * d->out_words, ln.out.p, (size_t)nf * d->out_words * 4,
                                    cudaMemcpyDeviceToHost, ln.st));
         if (ok) QLDPC_CUDA(cudaMemcpyAsync(ok + f0, ln.ok.p, nf, cudaMemcpyDeviceToHost, ln.st));

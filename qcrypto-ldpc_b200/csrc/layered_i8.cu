@@ -56,7 +56,10 @@ constexpr u32 kSignMask = 0x80008000u;
 constexpr u32 kInf2 = 0x03ff03ffu;     // 1023 ulp: larger than any message magnitude
 constexpr u32 kOne2 = 0x3c003c00u;     // 1.0h, 1.0h
 constexpr int kMaxBlock = 256;
-constexpr int kMaxBlockStream = 384;
+#ifndef QL_MAXBLOCK_STREAM
+#define QL_MAXBLOCK_STREAM 384
+#endif
+constexpr int kMaxBlockStream = QL_MAXBLOCK_STREAM;
 constexpr int kRegRows = 4;
 
 __device__ __forceinline__ __half2 h2(u32 x) { return *reinterpret_cast<__half2 *>(&x); }

@@ -149,3 +149,32 @@ def test_full_batch_roundtrip_property(q, O, data_dir):
     sel = rng.choice(F, 16, replace=False)
     hard, oit, ook, _ = oc.batch_layered_fixed_i8(llr[sel], None, rule=O.RULE_NMS, n_ite=10, early_stop=True, norm_eighths=6)
     assert (oit == iters[sel]).all() and ook.all()
+
+
+def test_host_pipeline_many_small_chunks(q, O, data_dir, monkeypatch):
+    """the host-pointer entry points cut the batch into chunks that ping-pong over two streams; kernels of the two
+    streams overlap in time, so nothing they write may be shared (regression: streamed-message scratch)"""
+    monkeypatch.setenv("QLDPC_CHUNK_FRAMES", "592")
+    path = "%s/NR_1_1_384.qc" % data_dir
+    oc = O.Code.from_qc(path)
+    code = q.Code.from_qc_file(path)
+    dec = q.Decoder(code, schedule=q.SCHED_LAYERED, rule=q.RULE_NMS, dtype=q.DTYPE_I8, max_iter=10, early_stop=True,
+                    norm_factor=0.75, out_mode=q.OUT_INFO)
+    F = 9000
+    rng = np.random.default_rng(31)
+    msg = rng.integers(0, 2, (F, oc.K)).astype(np.uint8)
+    cw = q.unpack_bits(dec.encode_nr(q.pack_bits(msg)), oc.N)
+    noisy = cw.copy()
+    noisy[:, :oc.K] ^= (rng.random((F, oc.K)) < 0.045).astype(np.uint8)     # ~2-3 iterations: every row's messages are re-read
+    known = np.zeros(oc.N, np.uint8)
+    known[oc.K:] = 1
+    for rep in range(3):
+        out, ok, iters = dec.decode_bits(q.pack_bits(noisy), 12.0, 31.0, known_mask=q.pack_bits(known))
+        assert ok.all() and (q.unpack_bits(out, oc.K) == msg).all(), "rep %d: %d frames wrong" % (
+            rep, int((q.unpack_bits(out, oc.K) != msg).any(axis=1).sum()))
+    llr = dec.make_llr(q.pack_bits(noisy), 12.0, 31.0, known_mask=q.pack_bits(known))
+    out2, ok2, iters2, _ = dec.decode(llr)
+    assert (out2 == out).all() and (iters2 == iters).all()
+    sel = rng.choice(F, 24, replace=False)
+    hard, oit, ook, _ = oc.batch_layered_fixed_i8(llr[sel], None, rule=O.RULE_NMS, n_ite=10, early_stop=True, norm_eighths=6)
+    assert (oit == iters[sel]).all() and (hard[:, :oc.K] == msg[sel]).all()

@@ -20,7 +20,7 @@ int CudaCheck::fail(cudaError_t e, const char *what)
 
 namespace {
 
-enum { KF_NONE = 0, KF_LAYERED_I8 = 1, KF_LAYERED_GENERIC = 2, KF_FLOODING = 3 };
+enum { KF_NONE = 0, KF_LAYERED_I8 = 1, KF_LAYERED_GENERIC = 2, KF_FLOODING = 3, KF_LAYERED_I8S = 4 };
 
 int dtype_size(int dtype) { return dtype == QLDPC_DTYPE_F32 ? 4 : (dtype == QLDPC_DTYPE_I16 ? 2 : 1); }
 
@@ -200,6 +200,114 @@ bool plan_layered_i8(qldpc_decoder *d, LayeredI8Params &p, bool upload)
     if (upload) {
         if (d->d_li8_edges.upload(edges) || d->d_li8_layers.upload(layers) || d->d_li8_pack_cols.upload(pack_cols)) return false;
     }
+    return true;
+}
+
+// Tables and shared-memory geometry of the streamed layered int8 kernel (layered_i8s.cu); false when the code
+// does not fit its assumptions (the caller then tries the older layered_i8 kernel).
+bool plan_layered_i8s(qldpc_decoder *d)
+{
+    if (const char *mode_env = std::getenv("QLDPC_LI8_MODE"))
+        if (std::strcmp(mode_env, "resident") == 0 || std::strcmp(mode_env, "stream") == 0) return false;
+    const HostCode &c = d->code;
+    if (c.z <= 0 || c.z % 128 != 0 || d->cfg.max_iter < 1) return false;
+    const int Z = c.z, W = Z / 4, ZW32 = Z / 32;
+    const int R = c.base_rows, C = c.base_cols;
+    if (R < 3 || W > layered_i8s_max_threads()) return false;
+    auto B = [&](int r, int col) { return c.base[r * C + col]; };
+
+    // extension columns = weight 1, shift 0, and the LAST edge of a row with at least one other edge
+    std::vector<int> colw(C, 0), deg(R, 0), last_col(R, -1), has_ext(R, 0), lpos(C, -1);
+    for (int r = 0; r < R; ++r)
+        for (int col = 0; col < C; ++col)
+            if (B(r, col) >= 0) { colw[col]++; deg[r]++; last_col[r] = col; }
+    std::vector<char> is_ext_col(C, 0);
+    for (int r = 0; r < R; ++r) {
+        if (deg[r] < 1) return false;
+        if (deg[r] >= 2 && colw[last_col[r]] == 1 && B(r, last_col[r]) == 0) { has_ext[r] = 1; is_ext_col[last_col[r]] = 1; }
+        if (deg[r] - has_ext[r] > 20) return false;
+    }
+    std::vector<Li8sCol> pcols;
+    for (int col = 0; col < C; ++col)
+        if (!is_ext_col[col]) { lpos[col] = (int)pcols.size(); pcols.push_back(Li8sCol{col * Z, col * 2 * ZW32}); }
+
+    Li8sGeo geo;
+    geo.n_pack = (int)pcols.size();
+    geo.off_rows = 0;
+    int off = R * (int)sizeof(Li8sRow);
+    std::vector<Li8sRow> rows(R);
+    std::vector<uint32_t> etab, thr, synt;
+    int g_off = 0, nv_max = 1;
+    // pass 1: sizes and offsets
+    const int off_etab = off;
+    int n_core_total = 0, thr_total = 0;
+    for (int r = 0; r < R; ++r) { n_core_total += deg[r] - has_ext[r]; thr_total += round_up(deg[r] - has_ext[r], 4); }
+    const int off_thr = off_etab + n_core_total * 32;
+    const int off_synt = off_thr + thr_total * 4;
+    int n_edges_total = 0;
+    for (int r = 0; r < R; ++r) n_edges_total += deg[r];
+    geo.off_pcols = round_up(off_synt + n_edges_total * 4, 16);
+    geo.tab_bytes = round_up(geo.off_pcols + geo.n_pack * (int)sizeof(Li8sCol), 16);
+
+    for (int r = 0; r < R; ++r) {
+        Li8sRow &ly = rows[r];
+        const int nc = deg[r] - has_ext[r];
+        ly.e_off = off_etab + (int)etab.size() * 4;
+        ly.thr_off = off_thr + (int)thr.size() * 4;
+        ly.syn_off = off_synt + (int)synt.size() * 4;
+        const int nv = (nc + 3) / 4;
+        const int variant = nc <= 10 ? (nc - 1) * 2 + has_ext[r] : 20 + ((nc + 1) / 2 * 2 - 12) + has_ext[r];
+        ly.pack = nc | (nv << 8) | (variant << 16);
+        ly.g_off = g_off * 16;
+        g_off += nv * W;
+        nv_max = std::max<int>(nv_max, nv);
+        ly.deg = deg[r];
+        ly.ext_src = has_ext[r] ? last_col[r] * Z : -1;
+        ly.ext_hd = has_ext[r] ? last_col[r] * 2 * ZW32 * 4 : 0;
+        int n_thr = 0;
+        for (int col = 0; col < C; ++col) {
+            const int s = B(r, col);
+            if (s < 0) continue;
+            synt.push_back(((uint32_t)((col * 2 * ZW32 + (s >> 5)) * 4) << 5) | (uint32_t)(s & 31));
+            if (has_ext[r] && col == last_col[r]) continue;
+            const int q = s / W, rr = s % W;
+            const uint32_t off0 = (uint32_t)((lpos[col] * W + rr) * 4);
+            const uint32_t a0 = unpack_selector(q), a1 = unpack_selector(q + 1);
+            const uint32_t e[8] = {off0, a0, a0 ^ 0x0202u, pack_selector(q),
+                                   off0 - 4u * (uint32_t)W, a1, a1 ^ 0x0202u, pack_selector(q + 1)};
+            etab.insert(etab.end(), e, e + 8);
+            thr.push_back((uint32_t)(W - rr));
+            ++n_thr;
+        }
+        for (; n_thr % 4; ++n_thr) thr.push_back((uint32_t)W);
+    }
+    geo.rg_u4 = g_off;
+    geo.stage_bytes = nv_max * W * 16;
+    const int L_bytes = geo.n_pack * W * 4;
+    geo.off_ring = L_bytes;
+    geo.off_ext = geo.off_ring + 2 * geo.stage_bytes;
+    geo.off_hd = geo.off_ext + 3 * Z;
+    geo.off_syn = geo.off_hd + C * 2 * ZW32 * 4;
+    geo.slot_bytes[0] = geo.off_syn;
+    geo.slot_bytes[1] = geo.off_syn + R * ZW32 * 4;
+    const int avail = d->max_smem_optin - geo.tab_bytes - 16;
+    for (int k = 0; k < 2; ++k) {
+        int slots = std::min(std::min(avail / geo.slot_bytes[k], layered_i8s_max_threads() / W), 15);
+        if (const char *cap = std::getenv("QLDPC_LI8_SLOTS")) slots = std::min(slots, std::max(1, std::atoi(cap)));   // experiments
+        geo.slots[k] = slots;
+    }
+    if (geo.slots[1] < 1) return false;
+
+    std::vector<uint8_t> blob(geo.tab_bytes, 0);
+    std::memcpy(blob.data() + geo.off_rows, rows.data(), rows.size() * sizeof(Li8sRow));
+    std::memcpy(blob.data() + off_etab, etab.data(), etab.size() * 4);
+    std::memcpy(blob.data() + off_thr, thr.data(), thr.size() * 4);
+    std::memcpy(blob.data() + off_synt, synt.data(), synt.size() * 4);
+    std::memcpy(blob.data() + geo.off_pcols, pcols.data(), pcols.size() * sizeof(Li8sCol));
+    if (d->d_li8s_tab.upload(blob)) return false;
+    d->li8s_geo = geo;
+    d->li8s = true;
+    d->li8_slots = geo.slots[0];   // chunking of the host-pointer entry points
     return true;
 }
 
@@ -398,9 +506,13 @@ extern "C" int qldpc_decoder_create(const qldpc_code *code, const qldpc_decoder_
 
     if (cfg->schedule == QLDPC_SCHED_LAYERED) {
         LayeredI8Params p{};
-        const bool fast = cfg->dtype == QLDPC_DTYPE_I8 && d->cfg.app_max == 127 && d->cfg.msg_max <= 63 &&
-                          plan_layered_i8(d, p, true);
-        if (fast) {
+        const bool i8_ok = cfg->dtype == QLDPC_DTYPE_I8 && d->cfg.app_max == 127 && d->cfg.msg_max <= 63;
+        const bool fast_s = i8_ok && plan_layered_i8s(d);
+        const bool fast = !fast_s && i8_ok && plan_layered_i8(d, p, true);
+        if (fast_s) {
+            d->kernel_family = KF_LAYERED_I8S;
+            d->kernel_name = "layered_i8_zpack4";
+        } else if (fast) {
             d->kernel_family = KF_LAYERED_I8;
             d->kernel_name = "layered_i8_zpack4";
             if (d->li8_stream && (rc = d->d_li8_rg.ensure(2 * (size_t)d->sm_count * d->li8_slots * d->li8_rg_words))) return bail(rc);
@@ -477,7 +589,57 @@ static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint3
     int rc;
 
     int family = d->kernel_family;
-    if (family == KF_LAYERED_I8 && d_posterior) family = KF_LAYERED_GENERIC;
+    if ((family == KF_LAYERED_I8 || family == KF_LAYERED_I8S) && d_posterior) family = KF_LAYERED_GENERIC;
+    if (family == KF_LAYERED_I8S && (reinterpret_cast<uintptr_t>(d_llr) & 15) != 0) family = KF_LAYERED_GENERIC;   // cp.async staging
+
+    if (family == KF_LAYERED_I8S) {
+        const Li8sGeo &geo = d->li8s_geo;
+        const int k = d_syndrome ? 1 : 0;
+        LayeredI8sParams p{};
+        const bool direct = cfg.out_mode == QLDPC_OUT_ALL || d->info_is_prefix;
+        if (!direct)
+            if ((rc = d->d_allbits.ensure((size_t)n_frames * d->cw_words))) return rc;
+        p.llr = (const int8_t *)d_llr;
+        p.syn = d_syndrome;
+        p.out = direct ? d_out_bits : d->d_allbits.p;
+        p.ok = d_ok; p.iters = d_iters; p.stats = d->d_stats.p;
+        p.tab = d->d_li8s_tab.p;
+        p.F = n_frames;
+        p.Z = c.z; p.W = c.z / 4; p.ZW32 = c.z / 32;
+        p.brows = c.base_rows; p.bcols = c.base_cols; p.N = c.n;
+        p.n_pack = geo.n_pack;
+        p.out_cols = (direct && cfg.out_mode == QLDPC_OUT_INFO) ? c.base_cols - c.base_rows : c.base_cols;
+        p.out_words = p.out_cols * p.ZW32;
+        p.syn_words = d->syn_words;
+        p.max_iter = cfg.max_iter; p.early_stop = cfg.early_stop;
+        p.rule = cfg.rule; p.norm_eighths = d->norm_eighths;
+        {
+            auto dup = [](uint32_t v) { return (v & 0xffffu) | (v << 16); };
+            p.h2_lo = dup(0x8000u | (uint32_t)(cfg.msg_max + 1));
+            p.h2_hi = dup((uint32_t)cfg.msg_max);
+            p.h2_cap = dup((uint32_t)(cfg.msg_max + 1));
+            p.h2_span = dup((uint32_t)(2 * cfg.msg_max + 1));
+            p.h2_negoff = dup(0x8000u | (uint32_t)d->offset_int);
+        }
+        p.slots = geo.slots[k];
+        p.tab_bytes = geo.tab_bytes; p.off_rows = geo.off_rows; p.off_pcols = geo.off_pcols;
+        p.slot_bytes = geo.slot_bytes[k]; p.off_ring = geo.off_ring; p.stage_bytes = geo.stage_bytes;
+        p.off_ext = geo.off_ext; p.off_hd = geo.off_hd; p.off_syn = geo.off_syn;
+        p.rg_u4 = geo.rg_u4;
+        const int grid = std::min(d->sm_count, (n_frames + p.slots - 1) / p.slots);
+        const size_t lane_u4 = (size_t)d->sm_count * std::max(geo.slots[0], geo.slots[1]) * geo.rg_u4;
+        if ((rc = d->d_li8s_rg.ensure(2 * lane_u4))) return rc;
+        p.rg = d->d_li8s_rg.p + (size_t)scratch_lane * lane_u4;
+        const int smem_bytes = geo.tab_bytes + 16 + p.slots * p.slot_bytes;
+        if ((rc = launch_layered_i8s(p, grid, smem_bytes, st))) return rc;
+        d->kernel_launches++;
+        if (!direct) {
+            if ((rc = launch_gather_bits(d->d_allbits.p, d_out_bits, n_frames, d->cw_words, d->out_words, c.k,
+                                         d->d_info_pos.p, st))) return rc;
+            d->kernel_launches++;
+        }
+        return QLDPC_OK;
+    }
 
     if (family == KF_LAYERED_I8) {
         LayeredI8Params p{};
@@ -595,7 +757,7 @@ extern "C" int qldpc_decode(qldpc_decoder *dec, const void *llr, const uint32_t 
     // chunk: ~64 MiB of LLRs, at least one wave of the persistent grid
     const int chunk = pick_chunk(d, frame_in, 128u << 20, n_frames);
     // the scratch of the gather path is shared: those configurations run on one lane only
-    const bool shared_scratch = !(d->kernel_family == KF_LAYERED_I8 && !posterior &&
+    const bool shared_scratch = !((d->kernel_family == KF_LAYERED_I8 || d->kernel_family == KF_LAYERED_I8S) && !posterior &&
                                   (d->cfg.out_mode == QLDPC_OUT_ALL || d->info_is_prefix));
     int rc = QLDPC_OK;
     for (auto &ln : d->lanes.lane) {
@@ -736,7 +898,7 @@ extern "C" int qldpc_decode_bits(qldpc_decoder *dec, const uint32_t *bits, const
     const size_t esz = dtype_size(d->cfg.dtype);
     const size_t frame_llr = (size_t)c.n * esz;
     const int chunk = pick_chunk(d, frame_llr, 128u << 20, n_frames);
-    const bool shared_scratch = !(d->kernel_family == KF_LAYERED_I8 && (d->cfg.out_mode == QLDPC_OUT_ALL || d->info_is_prefix));
+    const bool shared_scratch = !((d->kernel_family == KF_LAYERED_I8 || d->kernel_family == KF_LAYERED_I8S) && (d->cfg.out_mode == QLDPC_OUT_ALL || d->info_is_prefix));
     int rc = QLDPC_OK;
     Lane &l0 = d->lanes.lane[0];
     const uint32_t *dk = nullptr, *dp = nullptr;

@@ -43,6 +43,32 @@ int layered_i8_max_threads();
 int layered_i8_reg_rows();
 int layered_i8_max_threads_stream();
 
+// ---- layered int8, QC, Z % 128 == 0, streamed kernel (layered_i8s.cu) ----------------------------
+struct LayeredI8sParams {
+    const int8_t *llr;        // F * N, 16-byte aligned
+    const uint32_t *syn;      // F * syn_words (MSB-first) or null
+    uint32_t *out;            // F * out_words (MSB-first)
+    uint8_t *ok;
+    uint16_t *iters;
+    DevStats *stats;
+    const uint8_t *tab;       // table blob (tab_bytes, multiple of 16)
+    uint4 *rg;                // message scratch: grid * slots * rg_u4
+    int F;
+    int Z, W, ZW32;
+    int brows, bcols, N;
+    int n_pack;               // core block columns (beliefs in shared memory)
+    int out_cols, out_words, syn_words;
+    int max_iter, early_stop;
+    int rule, norm_eighths;
+    uint32_t h2_lo, h2_hi, h2_cap, h2_span, h2_negoff;   // half2 patterns: -(m+1), m, m+1, 2m+1, -offset (m = msg_max)
+    int slots;
+    int tab_bytes, off_rows, off_pcols;
+    int slot_bytes, off_ring, stage_bytes, off_ext, off_hd, off_syn;
+    int rg_u4;                // uint4 per frame slot in the scratch
+};
+int launch_layered_i8s(const LayeredI8sParams &p, int grid, int smem_bytes, cudaStream_t st);
+int layered_i8s_max_threads();
+
 // ---- generic layered (QC, any Z; f32 / i16 / i8) ---------------------------------------------
 struct LayeredGenParams {
     const void *llr;

@@ -1,0 +1,606 @@
+// Layered int8 min-sum decoder, "streamed" kernel (v5): quasi-cyclic codes with Z % 128 == 0
+// (BG1/BG2 lifting sizes 128, 256, 384).  Same arithmetic as layered_i8.cu -- ML/BPSK_nrldpc_sim_FP.m:35-94
+// generalised by syndrome input, early stop and the shift-normalised rule; bit-exact with
+// oracle/qldpc_oracle.c:ora_decode_layered_fixed -- but a different placement of the state, chosen so that
+// SIX frames (BG1 Z=384) are in flight per SM instead of four:
+//   shared memory, per frame slot:
+//     beliefs of the CORE block columns only (columns that are not weight-1/shift-0 extension columns),
+//       word i of a column = lanes {i, i+W, i+2W, i+3W} as biased bytes (L+128), W = Z/4;
+//     a 2-stage ring of check-to-variable messages (cp.async from / plain stores to an L2-resident scratch);
+//     a 3-deep ring of raw channel LLRs of the extension column of the rows about to be processed
+//       (an extension column is read by exactly one row and never rewritten: its belief minus its message is
+//       the channel LLR for ever, only the SIGN of its a-posteriori value is observable);
+//     hard-decision bit vectors, each stored twice back to back so that a rotated window never wraps.
+//   registers: per-edge state of the row being processed.
+// Per edge and thread (4 check lanes = 2 half2 pairs) the instruction budget is ~36:
+//   the wrap decision (lane i+r >= W) selects between two precomputed table entries with a pair of PREDICATED
+//   128-bit shared loads (no SEL chain), clips run on the FMA pipe (relu forms) so that the half-rate ALU pipe
+//   only carries PRMT / min-max / logic.
+// Early termination: hard decisions are balloted into Z-bit vectors; the syndrome is evaluated word-wise
+// (funnel shift + XOR) for the first 8 block rows, and for the remaining rows only if those were all zero.
+#include <cuda_fp16.h>
+
+#include "kernels.hpp"
+
+#ifndef QL_S_MAXTHREADS
+#define QL_S_MAXTHREADS 480          // 5 frames x 96 threads = 15 warps -> 128 registers per thread (18 warps: 96)
+#endif
+#ifndef QL_S_FMACLIP
+#define QL_S_FMACLIP 1               // message clip as relu forms on the FMA pipe
+#endif
+#ifndef QL_S_CENTRY
+#define QL_S_CENTRY 1                // table entry read in plain C++ (address select) instead of predicated loads
+#endif
+#ifndef QL_S_KEEPT
+#define QL_S_KEEPT 8                 // rows with more core edges re-clip L - R_old in the second pass instead of keeping t
+#endif
+#ifndef QL_S_FMACLIP8
+#define QL_S_FMACLIP8 0              // belief clip (upper bound) on the FMA pipe
+#endif
+
+namespace qldpc {
+
+namespace {
+
+typedef unsigned int u32;
+
+constexpr u32 kSignMask = 0x80008000u;
+constexpr u32 kInf2 = 0x03ff03ffu;     // 1023 ulp: larger than any message magnitude
+constexpr u32 kOne2 = 0x3c003c00u;     // 1.0h, 1.0h
+constexpr u32 kMinusOne2 = 0xbc00bc00u;
+constexpr u32 k128 = 0x00800080u;
+constexpr u32 k255 = 0x00ff00ffu;
+
+__device__ __forceinline__ __half2 h2(u32 x) { return *reinterpret_cast<__half2 *>(&x); }
+__device__ __forceinline__ u32 bits(__half2 h) { return *reinterpret_cast<u32 *>(&h); }
+__device__ __forceinline__ u32 hsub(u32 a, u32 b) { return bits(__hsub2(h2(a), h2(b))); }
+__device__ __forceinline__ u32 hadd(u32 a, u32 b) { return bits(__hadd2(h2(a), h2(b))); }
+__device__ __forceinline__ u32 hmin(u32 a, u32 b) { return bits(__hmin2(h2(a), h2(b))); }
+__device__ __forceinline__ u32 hmax(u32 a, u32 b) { return bits(__hmax2(h2(a), h2(b))); }
+__device__ __forceinline__ u32 habs(u32 a) { return bits(__habs2(h2(a))); }
+__device__ __forceinline__ u32 hadd_relu(u32 a, u32 b) { return bits(__hfma2_relu(h2(a), h2(kOne2), h2(b))); }
+// relu(b - a)
+__device__ __forceinline__ u32 hrsub_relu(u32 a, u32 b) { return bits(__hfma2_relu(h2(a), h2(kMinusOne2), h2(b))); }
+__device__ __forceinline__ u32 heq_mask(u32 a, u32 b) { return __heq2_mask(h2(a), h2(b)); }
+__device__ __forceinline__ u32 prmt(u32 a, u32 b, u32 sel)
+{
+    u32 d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ u32 min_xorsign_abs(u32 a, u32 b)
+{
+    u32 d;
+    asm("min.xorsign.abs.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ void bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ bool bar_red_or(int id, int nthreads, bool pred)
+{
+    u32 r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %3, 0;\n\tbar.red.or.pred q, %1, %2, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(r)
+        : "r"(id), "r"(nthreads), "r"((u32)pred)
+        : "memory");
+    return r != 0;
+}
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// The table entry of an edge for this thread: entry 0 when lane i does not wrap past the end of the column,
+// entry 1 (16 bytes further) when it does.  Two predicated loads, one of which executes: no SEL chain.
+// The tables are written once before the first __syncthreads and never again, so the load may be scheduled freely.
+struct EdgeEntry { u32 off, selA, selB, selW; };
+// VOL: a second, volatile flavour for the re-read in the second pass of the big rows (an identical non-volatile
+// asm would be merged with the first-pass one and its results kept live across the passes)
+template <bool VOL>
+__device__ __forceinline__ EdgeEntry load_entry(u32 saddr, int i, int thresh)
+{
+    EdgeEntry e;
+#if QL_S_CENTRY
+    {
+        const uint4 *tp = reinterpret_cast<const uint4 *>(__cvta_shared_to_generic(saddr)) + (i >= thresh ? 1 : 0);
+        const uint4 v = *tp;
+        e.off = v.x; e.selA = v.y; e.selB = v.z; e.selW = v.w;
+        return e;
+    }
+#endif
+    if constexpr (VOL) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %4, %5;\n\t"
+                     "@p ld.shared.v4.u32 {%0,%1,%2,%3}, [%6+16];\n\t"
+                     "@!p ld.shared.v4.u32 {%0,%1,%2,%3}, [%6];\n\t}"
+                     : "=r"(e.off), "=r"(e.selA), "=r"(e.selB), "=r"(e.selW)
+                     : "r"(i), "r"(thresh), "r"(saddr));
+        return e;
+    }
+    asm("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %4, %5;\n\t"
+        "@p ld.shared.v4.u32 {%0,%1,%2,%3}, [%6+16];\n\t"
+        "@!p ld.shared.v4.u32 {%0,%1,%2,%3}, [%6];\n\t}"
+        : "=r"(e.off), "=r"(e.selA), "=r"(e.selB), "=r"(e.selW)
+        : "r"(i), "r"(thresh), "r"(saddr));
+    return e;
+}
+
+// clip to the message range [-(msg_max+1), msg_max]
+struct Cx {
+    u32 cLo, cHi, cCap, cSpan;   // -(msg_max+1), msg_max, msg_max+1, 2*msg_max+1 as half2 ulps
+    u32 negOff;
+    int norm_eighths;
+    int lane, wis, wq, ZW32;
+};
+__device__ __forceinline__ u32 clip_msg(const Cx &cx, u32 u)
+{
+#if QL_S_FMACLIP
+    // hi - relu(span - relu(u + cap)): three FMA-pipe instructions, none on the ALU pipe
+    return hsub(cx.cHi, hrsub_relu(hadd_relu(u, cx.cCap), cx.cSpan));
+#else
+    return hmin(hmax(u, cx.cLo), cx.cHi);
+#endif
+}
+// clip(L - R_old + R_new) in biased form: relu(u + b) capped at 255
+__device__ __forceinline__ u32 clip_belief(u32 u, u32 b)
+{
+    const u32 l = hadd_relu(u, b);
+#if QL_S_FMACLIP8
+    return hsub(k255, hrsub_relu(l, k255));
+#else
+    return hmin(l, k255);
+#endif
+}
+
+template <int NK>
+__device__ __forceinline__ u32 norm_eighths2(u32 x, int k_rt)
+{
+    const int k = NK < 0 ? k_rt : NK;
+    if (k >= 8) return x;
+    const u32 s1 = (x >> 1) & 0x7fff7fffu, s2 = (x >> 2) & 0x3fff3fffu, s3 = (x >> 3) & 0x1fff1fffu;
+    u32 r = 0;
+    if (k & 4) r += s1;
+    if (k & 2) r += s2;
+    if (k & 1) r += s3;
+    return r;
+}
+
+__device__ __forceinline__ u32 vcomp(const uint4 &v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
+__device__ __forceinline__ int vcomp(const int4 &v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
+__device__ __forceinline__ void vset(uint4 &v, int k, u32 x)
+{
+    if (k == 0) v.x = x; else if (k == 1) v.y = x; else if (k == 2) v.z = x; else v.w = x;
+}
+
+// One block row for the four check lanes of this thread.
+//   NK     rule: 0 = offset min-sum, 1..8 = normalised by NK/8, -1 = normalised, factor at run time
+//   DC     unrolled core-edge slots; EXACT: the row has exactly DC core edges, else DC - 1 or DC (nc)
+//   EXT    one more edge goes to an extension column (channel bytes in extb, sign balloted into hd_ext)
+//   MODE   what stays in registers per edge between the two passes: 0: L - R_old, its clipped value, belief address
+//          and pack selector; 1: no clipped value (re-clip); 2: only L - R_old (re-clip, re-read the table entry)
+//   Li     this thread's belief base (slot beliefs + 4*i); erow: shared address of the row's first table entry
+//   thr4   wrap thresholds of the row's edges, four per int4
+//   ysrc   this thread's message blocks (ystride uint4 apart); gdst: where the new ones go (W uint4 apart)
+template <int NK, int DC, bool EXACT, bool EXT, int MODE>
+__device__ __forceinline__ void process_row(const Cx &cx, char *Li, u32 erow, const int4 *thr4, int nc, int i, uint2 m1init,
+                                            const uint4 *ysrc, int ystride, uint4 *gdst, int W,
+                                            const unsigned char *extb, u32 *hd_ext)
+{
+    constexpr int KEEPT = MODE == 0 ? DC : 1, KEEPA = MODE <= 1 ? DC : 1;
+    u32 uA[DC], uB[DC], tA[KEEPT], tB[KEEPT], sw[KEEPA];
+    char *ad[KEEPA];
+    u32 m1A = m1init.x, m1B = m1init.y;   // running (min1, sign product); the sign starts at the syndrome bit
+    u32 m2A = kInf2, m2B = kInf2;
+
+    uint4 Yq = make_uint4(0, 0, 0, 0);
+    int4 Tq = make_int4(0, 0, 0, 0);
+#pragma unroll
+    for (int j = 0; j < DC; ++j) {
+        if (EXACT || j < DC - 1 || j < nc) {
+            if ((j & 3) == 0) {
+                Yq = ysrc[(j >> 2) * ystride];
+                Tq = thr4[j >> 2];
+            }
+            const EdgeEntry en = load_entry<false>(erow + 32 * j, i, vcomp(Tq, j & 3));
+            char *a = Li + en.off;
+            const u32 X = *reinterpret_cast<const u32 *>(a);
+            const u32 Y = vcomp(Yq, j & 3);
+            const u32 xA = prmt(X, 0u, en.selA), xB = prmt(X, 0u, en.selB);
+            const u32 yA = prmt(Y, 0u, 0x4140u), yB = prmt(Y, 0u, 0x4342u);
+            const u32 ua = hsub(xA, yA), ub = hsub(xB, yB);          // L - R_old  (:51)
+            const u32 ta = clip_msg(cx, ua), tb = clip_msg(cx, ub);   // clip to the message range (:54-55)
+            uA[j] = ua; uB[j] = ub;
+            if constexpr (MODE == 0) { tA[j] = ta; tB[j] = tb; }
+            if constexpr (MODE <= 1) { sw[j] = en.selW; ad[j] = a; }
+            m2A = hmax(habs(m1A), hmin(habs(ta), m2A));               // second minimum (:61)
+            m2B = hmax(habs(m1B), hmin(habs(tb), m2B));
+            m1A = min_xorsign_abs(m1A, ta);                           // first minimum and sign product (:60,:63)
+            m1B = min_xorsign_abs(m1B, tb);
+        }
+    }
+    u32 ueA = 0, ueB = 0, teA = 0, teB = 0;
+    if constexpr (EXT) {   // the extension edge: belief - message == channel LLR
+        const u32 b0 = extb[0], b1 = extb[W], b2 = extb[2 * W], b3 = extb[3 * W];
+        ueA = hsub((b0 | (b1 << 16)) ^ k128, k128);
+        ueB = hsub((b2 | (b3 << 16)) ^ k128, k128);
+        teA = clip_msg(cx, ueA);
+        teB = clip_msg(cx, ueB);
+        m2A = hmax(habs(m1A), hmin(habs(teA), m2A));
+        m2B = hmax(habs(m1B), hmin(habs(teB), m2B));
+        m1A = min_xorsign_abs(m1A, teA);
+        m1B = min_xorsign_abs(m1B, teB);
+    }
+    const u32 parA = m1A & kSignMask, parB = m1B & kSignMask;
+    const u32 min1A = habs(m1A), min1B = habs(m1B);
+    m2A = hmin(m2A, cx.cCap);
+    m2B = hmin(m2B, cx.cCap);
+    u32 c1A, c1B, c2A, c2B;   // c1: magnitude sent to the position of the minimum, c2: to all others
+    if (NK == 0) {                                                    // :65-72
+        c1A = hadd_relu(m2A, cx.negOff); c1B = hadd_relu(m2B, cx.negOff);
+        c2A = hadd_relu(min1A, cx.negOff); c2B = hadd_relu(min1B, cx.negOff);
+    } else {
+        c1A = norm_eighths2<NK>(m2A, cx.norm_eighths); c1B = norm_eighths2<NK>(m2B, cx.norm_eighths);
+        c2A = norm_eighths2<NK>(min1A, cx.norm_eighths); c2B = norm_eighths2<NK>(min1B, cx.norm_eighths);
+    }
+    c1A ^= parA; c2A ^= parA; c1B ^= parB; c2B ^= parB;               // parity folded into both candidates
+
+    if constexpr (EXT) {   // only the sign of channel + new message is observable: ballot it into the hd vector
+        const u32 eA = heq_mask(habs(teA), min1A), eB = heq_mask(habs(teB), min1B);
+        const u32 rA = ((eA & c1A) | (~eA & c2A)) ^ (teA & kSignMask);
+        const u32 rB = ((eB & c1B) | (~eB & c2B)) ^ (teB & kSignMask);
+        const u32 aA = hadd(ueA, rA), aB = hadd(ueB, rB);
+        const u32 b0 = __ballot_sync(0xffffffffu, (int)(aA << 16) < 0);   // lane i
+        const u32 b1 = __ballot_sync(0xffffffffu, (int)aA < 0);           // lane i + W
+        const u32 b2 = __ballot_sync(0xffffffffu, (int)(aB << 16) < 0);   // lane i + 2W
+        const u32 b3 = __ballot_sync(0xffffffffu, (int)aB < 0);           // lane i + 3W
+        if (cx.lane == 0) {
+            u32 *h = hd_ext + cx.wis;
+            const int wq = cx.wq, zw = cx.ZW32;
+            h[0] = b0; h[wq] = b1; h[2 * wq] = b2; h[3 * wq] = b3;
+            h[zw] = b0; h[zw + wq] = b1; h[zw + 2 * wq] = b2; h[zw + 3 * wq] = b3;
+        }
+    }
+    uint4 Yn = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+#pragma unroll
+    for (int j = 0; j < DC; ++j) {
+        if (EXACT || j < DC - 1 || j < nc) {
+            u32 ta, tb, selW;
+            char *a;
+            if constexpr (MODE == 2) {
+                if ((j & 3) == 0) Tq = thr4[j >> 2];
+                const EdgeEntry en = load_entry<true>(erow + 32 * j, i, vcomp(Tq, j & 3));
+                a = Li + en.off;
+                selW = en.selW;
+            } else {
+                selW = sw[j]; a = ad[j];
+            }
+            if constexpr (MODE == 0) {
+                ta = tA[j]; tb = tB[j];
+            } else {
+                ta = clip_msg(cx, uA[j]);
+                tb = clip_msg(cx, uB[j]);
+            }
+            const u32 eA = heq_mask(habs(ta), min1A), eB = heq_mask(habs(tb), min1B);
+            // |t| == min1 ? c1 : c2, then the edge's own sign (:73-75)
+            const u32 rA = ((eA & c1A) | (~eA & c2A)) ^ (ta & kSignMask);
+            const u32 rB = ((eB & c1B) | (~eB & c2B)) ^ (tb & kSignMask);
+            const u32 bA = hadd(rA, k128), bB = hadd(rB, k128);       // biased new message
+            const u32 lA = clip_belief(uA[j], bA);                    // clip(L - R_old + R_new) biased (:88-91)
+            const u32 lB = clip_belief(uB[j], bB);
+            vset(Yn, j & 3, prmt(bA, bB, 0x6420u));
+            *reinterpret_cast<u32 *>(a) = prmt(lA, lB, selW);
+        }
+        if ((j & 3) == 3 || j == DC - 1) gdst[(j >> 2) * W] = Yn;
+    }
+}
+
+template <int NK>
+__device__ __forceinline__ void dispatch_row(int variant, const Cx &cx, char *Li, u32 erow, const int4 *thr4, int nc, int i,
+                                             uint2 m1init, const uint4 *ysrc, int ystride, uint4 *gdst, int W,
+                                             const unsigned char *extb, u32 *hd_ext)
+{
+#define QL_ROW(DCV, EXACTV, EXTV, BIGV) \
+    process_row<NK, DCV, EXACTV, EXTV, (BIGV ? 2 : (DCV > QL_S_KEEPT ? 1 : 0))>(cx, Li, erow, thr4, nc, i, m1init, ysrc, ystride, gdst, \
+                                                                                W, extb, hd_ext)
+    switch (variant) {
+    case 0: QL_ROW(1, true, false, false); break;
+    case 1: QL_ROW(1, true, true, false); break;
+    case 2: QL_ROW(2, true, false, false); break;
+    case 3: QL_ROW(2, true, true, false); break;
+    case 4: QL_ROW(3, true, false, false); break;
+    case 5: QL_ROW(3, true, true, false); break;
+    case 6: QL_ROW(4, true, false, false); break;
+    case 7: QL_ROW(4, true, true, false); break;
+    case 8: QL_ROW(5, true, false, false); break;
+    case 9: QL_ROW(5, true, true, false); break;
+    case 10: QL_ROW(6, true, false, false); break;
+    case 11: QL_ROW(6, true, true, false); break;
+    case 12: QL_ROW(7, true, false, false); break;
+    case 13: QL_ROW(7, true, true, false); break;
+    case 14: QL_ROW(8, true, false, false); break;
+    case 15: QL_ROW(8, true, true, false); break;
+    case 16: QL_ROW(9, true, false, false); break;
+    case 17: QL_ROW(9, true, true, false); break;
+    case 18: QL_ROW(10, true, false, false); break;
+    case 19: QL_ROW(10, true, true, false); break;
+    case 20: QL_ROW(12, false, false, true); break;
+    case 21: QL_ROW(12, false, true, true); break;
+    case 22: QL_ROW(14, false, false, true); break;
+    case 23: QL_ROW(14, false, true, true); break;
+    case 24: QL_ROW(16, false, false, true); break;
+    case 25: QL_ROW(16, false, true, true); break;
+    case 26: QL_ROW(18, false, false, true); break;
+    case 27: QL_ROW(18, false, true, true); break;
+    case 28: QL_ROW(20, false, false, true); break;
+    default: QL_ROW(20, false, true, true); break;
+    }
+#undef QL_ROW
+}
+
+// 4x4 byte transpose: in[k] holds lanes 4j..4j+3 of quarter k; out[m] = belief word of lane 4j+m
+__device__ __forceinline__ void transpose4x4(const u32 (&in)[4], u32 (&out)[4])
+{
+    const u32 t0 = prmt(in[0], in[1], 0x5140u), t1 = prmt(in[2], in[3], 0x5140u);
+    const u32 t2 = prmt(in[0], in[1], 0x7362u), t3 = prmt(in[2], in[3], 0x7362u);
+    out[0] = prmt(t0, t1, 0x5410u);
+    out[1] = prmt(t0, t1, 0x7632u);
+    out[2] = prmt(t2, t3, 0x5410u);
+    out[3] = prmt(t2, t3, 0x7632u);
+}
+
+// WT: W = Z/4 at compile time (0: read it from the parameters); with a constant W every stride of the staging,
+// ballot and syndrome code folds into instruction immediates.
+template <int NK, int WT>
+__global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const LayeredI8sParams p)
+{
+    extern __shared__ __align__(16) char smem[];
+    const int W = WT ? WT : p.W;
+    const int Z = 4 * W, ZW32 = W >> 3, wq = W >> 5, wq4 = W >> 2;
+    const int R = p.brows;
+    const int g = threadIdx.y, i = threadIdx.x;          // block = (W, slots); W is a multiple of 32
+    const int lane = i & 31, wis = i >> 5;
+    const int bar_id = 1 + g;
+
+    {   // shared tables (all slots) + one block of biased zero messages
+        const int tid = g * W + i, nthreads = W * blockDim.y;
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.tab);
+        uint4 *dst = reinterpret_cast<uint4 *>(smem);
+        for (int k = tid; k < (p.tab_bytes >> 4); k += nthreads) dst[k] = src[k];
+        if (tid == 0) dst[p.tab_bytes >> 4] = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+    }
+    __syncthreads();
+    const char *rowsc = smem + p.off_rows;               // Li8sRow[brows], read as int4 pairs
+    const Li8sCol *pcols = reinterpret_cast<const Li8sCol *>(smem + p.off_pcols);
+    const uint4 *zero_blk = reinterpret_cast<const uint4 *>(smem + p.tab_bytes);
+    const u32 tab_saddr = (u32)__cvta_generic_to_shared(smem);
+
+    char *slot = smem + p.tab_bytes + 16 + g * p.slot_bytes;
+    u32 *Lw = reinterpret_cast<u32 *>(slot);
+    char *Li = slot + 4 * i;
+    char *ring_i = slot + p.off_ring + 16 * i;                        // 2 stages of stage_bytes
+    unsigned char *extb = reinterpret_cast<unsigned char *>(slot + p.off_ext);   // 3 buffers of Z bytes
+    u32 *hd = reinterpret_cast<u32 *>(slot + p.off_hd);              // bcols vectors of 2*ZW32 words
+    u32 *synl = reinterpret_cast<u32 *>(slot + p.off_syn);
+    char *rg_i = reinterpret_cast<char *>(p.rg + (size_t)(blockIdx.x * p.slots + g) * p.rg_u4 + i);   // this slot's scratch
+    const bool has_syn = p.syn != nullptr;
+    const bool ext_thread = i < wq4;                                  // threads that stage 16 bytes of an extension column
+
+    Cx cx;
+    cx.cLo = p.h2_lo; cx.cHi = p.h2_hi; cx.cCap = p.h2_cap; cx.cSpan = p.h2_span;
+    cx.negOff = p.h2_negoff;
+    cx.norm_eighths = p.norm_eighths;
+    cx.lane = lane; cx.wis = wis; cx.wq = wq; cx.ZW32 = ZW32;
+
+    // fixed decompositions of the thread index
+    const int lc = i / wq4, lj = i - lc * wq4;        // load phase: (column step, word quad)
+    const int rs = i / ZW32, w = i - rs * ZW32;       // syndrome / output phases: (row step, 32-bit word); W / ZW32 == 8
+
+    // All frame groups of the CTA run their iterations in step (one CTA-wide barrier per iteration): every warp then
+    // executes the same block-row code at about the same time, and the large unrolled code is fetched once per SM
+    // instead of once per group (without it 37 % of the issue slots were lost to instruction-cache misses).
+    int f = blockIdx.x * p.slots + g;
+    const int fstride = gridDim.x * p.slots;
+    const int nthreads_cta = W * blockDim.y;
+    bool active = false, need_load = true, conv = false;
+    int it = 0, stage = 0, k3 = 0, r2 = 0;   // k3: trip % 3, r2: row of trip + 2
+    const int8_t *llr_i = nullptr;
+#pragma unroll 1
+    for (;;) {
+      if (need_load) {
+        need_load = false;
+        active = f < p.F;
+        if (active) {
+        cp_async_wait<0>();   // nothing may still be in flight from the previous frame of this slot
+        const int8_t *src = p.llr + (size_t)f * p.N;
+        llr_i = src + 16 * i;
+        // ---- prologue: channel bytes of the extension columns of the first two rows
+        if (ext_thread) {
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int es = *reinterpret_cast<const int *>(rowsc + 32 * t + 16);
+                if (es >= 0) cp_async16(extb + t * Z + 16 * i, llr_i + es);
+            }
+        }
+        cp_async_commit();
+        {   // pull this slot's next frame towards L2 while the current one is decoded
+            const int fn = f + gridDim.x * p.slots;
+            if (fn < p.F) {
+                const char *nx = reinterpret_cast<const char *>(p.llr + (size_t)fn * p.N);
+                for (int o = i * 128; o < p.N; o += W * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
+            }
+        }
+        // ---- load: int8 LLRs of the core columns -> interleaved biased belief words
+        // 4 aligned 32-bit loads (one per quarter of the column) -> 4x4 byte transpose -> one 128-bit store
+#pragma unroll 4
+        for (int c = lc; c < p.n_pack; c += 4) {
+            const u32 *q = reinterpret_cast<const u32 *>(src + pcols[c].llr_off) + lj;
+            u32 in[4], out[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) in[k] = __ldg(q + k * wq4) ^ 0x80808080u;
+            transpose4x4(in, out);
+            *reinterpret_cast<uint4 *>(Lw + c * W + 4 * lj) = make_uint4(out[0], out[1], out[2], out[3]);
+        }
+        if (has_syn) {   // syndrome rows, Z-bit little-endian vectors (row r, lane l -> bit l)
+            const u32 *sf = p.syn + (size_t)f * p.syn_words;
+            for (int r = rs; r < R; r += 8) synl[r * ZW32 + w] = __brev(__ldg(sf + r * ZW32 + w));
+        }
+        cp_async_wait<0>();
+        bar_sync(bar_id, W);
+        it = 0; stage = 0; k3 = 0; r2 = 2 % R;
+        conv = false;
+        }
+      }
+      if (!bar_red_or(0, nthreads_cta, active)) break;   // also the alignment barrier of the iteration
+      if (active) {
+            bool finished = false;
+            if (it < p.max_iter) {
+#pragma unroll 1
+                for (int r = 0; r < R; ++r) {
+                    const int4 la = *reinterpret_cast<const int4 *>(rowsc + 32 * r);        // e_off, thr_off, g_off, nc|nv|variant
+                    const int4 lb = *reinterpret_cast<const int4 *>(rowsc + 32 * r + 16);   // ext_src, ext_hd, syn_off, deg
+                    {   // stage the NEXT row's messages (none exist during the first iteration) and the extension
+                        // bytes of the row after it, while this row is processed
+                        const int rn = r + 1 < R ? r + 1 : 0;
+                        if (it > 0 || rn == 0) {
+                            const int2 nx = *reinterpret_cast<const int2 *>(rowsc + 32 * rn + 8);   // g_off, nc|nv|variant
+                            const int nvn = (nx.y >> 8) & 0xff;
+                            char *dst = ring_i + (stage ^ 1) * p.stage_bytes;
+                            const char *s = rg_i + nx.x;
+#pragma unroll
+                            for (int q = 0; q < 5; ++q)
+                                if (q < nvn) cp_async16(dst + q * W * 16, s + q * W * 16);
+                        }
+                        if (ext_thread) {
+                            const int es = *reinterpret_cast<const int *>(rowsc + 32 * r2 + 16);
+                            const int kb = k3 >= 1 ? k3 - 1 : 2;   // (k3 + 2) % 3
+                            if (es >= 0) cp_async16(extb + kb * Z + 16 * i, llr_i + es);
+                        }
+                        cp_async_commit();
+                        cp_async_wait<1>();   // everything but the group just committed has landed
+                    }
+                    uint2 m1init = make_uint2(kInf2, kInf2);   // initial (min1, sign) of the two half2 pairs
+                    if (has_syn) {
+                        const u32 *sr = synl + r * ZW32 + wis;
+                        const u32 s0 = (sr[0] >> lane) & 1u, s1 = (sr[wq] >> lane) & 1u;
+                        const u32 s2 = (sr[2 * wq] >> lane) & 1u, s3 = (sr[3 * wq] >> lane) & 1u;
+                        m1init.x ^= (s0 << 15) | (s1 << 31);
+                        m1init.y ^= (s2 << 15) | (s3 << 31);
+                    }
+                    const uint4 *ysrc = it == 0 ? zero_blk : reinterpret_cast<const uint4 *>(ring_i + stage * p.stage_bytes);
+                    const int ystride = it == 0 ? 0 : W;
+                    dispatch_row<NK>(la.w >> 16, cx, Li, tab_saddr + la.x, reinterpret_cast<const int4 *>(smem + la.y),
+                                     la.w & 0xff, i, m1init, ysrc, ystride, reinterpret_cast<uint4 *>(rg_i + la.z), W,
+                                     extb + k3 * Z + i, reinterpret_cast<u32 *>(reinterpret_cast<char *>(hd) + lb.y));
+                    stage ^= 1;
+                    k3 = k3 == 2 ? 0 : k3 + 1;
+                    r2 = r2 + 1 < R ? r2 + 1 : 0;
+                    bar_sync(bar_id, W);
+                }
+                ++it;
+            }
+            // the syndrome / hard-decision phase runs after every iteration when early stop is on,
+            // otherwise once after the last iteration
+            if (p.early_stop || it >= p.max_iter) {
+                // hard decisions of the core columns (extension columns were balloted in their rows)
+                u32 *hl = hd + wis;
+#pragma unroll 2
+                for (int c = 0; c < p.n_pack; ++c) {
+                    const u32 X = Lw[c * W + i];                 // biased: bit 7 clear <=> L < 0
+                    const u32 b0 = __ballot_sync(0xffffffffu, (X & 0x80u) == 0u);
+                    const u32 b1 = __ballot_sync(0xffffffffu, (X & 0x8000u) == 0u);
+                    const u32 b2 = __ballot_sync(0xffffffffu, (X & 0x800000u) == 0u);
+                    const u32 b3 = __ballot_sync(0xffffffffu, (int)X >= 0);
+                    if (lane == 0) {
+                        u32 *h = hl + pcols[c].hd_off;
+                        h[0] = b0; h[wq] = b1; h[2 * wq] = b2; h[3 * wq] = b3;
+                        h[ZW32] = b0; h[ZW32 + wq] = b1; h[ZW32 + 2 * wq] = b2; h[ZW32 + 3 * wq] = b3;
+                    }
+                }
+                bar_sync(bar_id, W);
+                // syndrome words: thread -> (row rs + 8k, word w); the doubled vectors make every rotated
+                // window contiguous: word (w + shift/32), funnel-shifted by shift%32
+                const char *hdw = reinterpret_cast<const char *>(hd + w);
+                u32 bad = 0;
+                if (rs < R) {
+                    const int4 lb = *reinterpret_cast<const int4 *>(rowsc + 32 * rs + 16);
+                    u32 acc = has_syn ? synl[rs * ZW32 + w] : 0u;
+                    const u32 *se = reinterpret_cast<const u32 *>(smem + lb.z);
+#pragma unroll 4
+                    for (int e = 0; e < lb.w; ++e) {
+                        const u32 en = se[e];
+                        const char *a = hdw + (en >> 5);
+                        acc ^= __funnelshift_r(*reinterpret_cast<const u32 *>(a), *reinterpret_cast<const u32 *>(a + 4), en);
+                    }
+                    bad = acc;
+                }
+                bool any_bad = bar_red_or(bar_id, W, bad != 0u);
+                if (!any_bad && R > 8) {
+                    bad = 0;
+#pragma unroll 1
+                    for (int r = rs + 8; r < R; r += 8) {
+                        const int4 lb = *reinterpret_cast<const int4 *>(rowsc + 32 * r + 16);
+                        u32 acc = has_syn ? synl[r * ZW32 + w] : 0u;
+                        const u32 *se = reinterpret_cast<const u32 *>(smem + lb.z);
+#pragma unroll 4
+                        for (int e = 0; e < lb.w; ++e) {
+                            const u32 en = se[e];
+                            const char *a = hdw + (en >> 5);
+                            acc ^= __funnelshift_r(*reinterpret_cast<const u32 *>(a), *reinterpret_cast<const u32 *>(a + 4), en);
+                        }
+                        bad |= acc;
+                    }
+                    any_bad = bar_red_or(bar_id, W, bad != 0u);
+                }
+                conv = !any_bad;
+                finished = conv || it >= p.max_iter;
+            }
+        if (finished) {
+        // ---- outputs: MSB-first packed hard decisions of the first out_cols block columns
+        uint32_t *of = p.out + (size_t)f * p.out_words;
+        for (int c = rs; c < p.out_cols; c += 8) of[c * ZW32 + w] = __brev(hd[c * 2 * ZW32 + w]);
+        if (i == 0) {
+            if (p.ok) p.ok[f] = conv ? 1 : 0;
+            if (p.iters) p.iters[f] = (uint16_t)it;
+            if (p.stats) {
+                atomicAdd(&p.stats->frames, 1ull);
+                if (!conv) atomicAdd(&p.stats->failures, 1ull);
+                atomicAdd(&p.stats->iter_sum, (unsigned long long)it);
+                atomicAdd(&p.stats->hist[min(it, QLDPC_ITER_HIST_BINS - 1)], 1ull);
+            }
+        }
+        bar_sync(bar_id, W);   // hd / beliefs are reused by the next frame of this slot
+        f += fstride;
+        need_load = true;
+        }
+      }
+    }
+    cp_async_wait<0>();
+}
+
+template <int NK, int WT>
+int launch_nkw(const LayeredI8sParams &p, int grid, int smem_bytes, cudaStream_t st)
+{
+    QLDPC_CUDA(cudaFuncSetAttribute(layered_i8s_kernel<NK, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    layered_i8s_kernel<NK, WT><<<grid, dim3(p.W, p.slots), smem_bytes, st>>>(p);
+    QLDPC_CUDA(cudaGetLastError());
+    return QLDPC_OK;
+}
+
+}  // namespace
+
+int layered_i8s_max_threads() { return QL_S_MAXTHREADS; }
+
+int launch_layered_i8s(const LayeredI8sParams &p, int grid, int smem_bytes, cudaStream_t st)
+{
+    if (p.rule == QLDPC_RULE_OMS) return launch_nkw<0, 0>(p, grid, smem_bytes, st);
+    if (p.norm_eighths == 6) return p.W == 96 ? launch_nkw<6, 96>(p, grid, smem_bytes, st) : launch_nkw<6, 0>(p, grid, smem_bytes, st);
+    return launch_nkw<-1, 0>(p, grid, smem_bytes, st);
+}
+
+}  // namespace qldpc

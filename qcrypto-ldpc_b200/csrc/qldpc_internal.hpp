@@ -57,6 +57,27 @@ struct Li8Layer {        // 24 bytes
     int16_t st;          // streamed mode: words per thread in that row (n_core rounded up to 4)
     int16_t pad;
 };
+// streamed layered int8 kernel (layered_i8s.cu): one table blob copied to shared memory
+struct Li8sRow {         // 32 bytes, read as two int4 broadcasts
+    int32_t e_off;       // byte offset (in the blob) of the row's first core-edge entry pair (2 x 16 bytes per edge:
+                         //   {belief byte offset, selA, selB, selW} without and with wrap)
+    int32_t thr_off;     // byte offset of the row's wrap thresholds (int32 each, 16-byte aligned)
+    int32_t g_off;       // BYTE offset of the row's messages in the per-frame scratch ([nv][W] uint4)
+    int32_t pack;        // nc | nv << 8 | variant << 16: core edges, uint4 per thread = ceil(nc / 4), code variant
+    int32_t ext_src;     // byte offset of the row's extension column in a frame of LLRs, -1 if none
+    int32_t ext_hd;      // BYTE offset of that column's (doubled) hard-decision vector
+    int32_t syn_off;     // byte offset of the row's syndrome-phase entries (one u32 per edge incl. the extension edge)
+    int32_t deg;         // all edges
+};
+struct Li8sCol {         // 8 bytes: a core block column
+    int32_t llr_off;     // byte offset of the column in a frame of LLRs (col * Z)
+    int32_t hd_off;      // word offset of its (doubled) hard-decision vector (col * 2 * ZW32)
+};
+struct Li8sGeo {         // launch geometry of the streamed kernel; index 0: no syndrome input, 1: with syndrome rows
+    int tab_bytes = 0, off_rows = 0, off_pcols = 0, n_pack = 0;
+    int rg_u4 = 0, stage_bytes = 0, off_ring = 0, off_ext = 0, off_hd = 0, off_syn = 0;
+    int slot_bytes[2] = {0, 0}, slots[2] = {0, 0};
+};
 // generic QC tables (syndrome phase of the int8 kernel, generic layered kernel)
 struct QcEdgeAux {       // 8 bytes
     int32_t hdw;         // col * ZW32
@@ -145,4 +166,9 @@ struct qldpc_decoder {
     bool li8_stream = false;          // messages streamed through an L2-resident scratch (4 frames per SM)
     int li8_rg_words = 0;             // scratch words per frame slot
     qldpc::DevBuf<uint32_t> d_li8_rg;
+    // streamed layered int8 kernel (layered_i8s.cu)
+    bool li8s = false;
+    qldpc::Li8sGeo li8s_geo;
+    qldpc::DevBuf<uint8_t> d_li8s_tab;
+    qldpc::DevBuf<uint4> d_li8s_rg;
 };

@@ -286,10 +286,13 @@ bool plan_layered_i8s(qldpc_decoder *d)
     const int L_bytes = geo.n_pack * W * 4;
     geo.off_ring = L_bytes;
     geo.off_ext = geo.off_ring + 2 * geo.stage_bytes;
-    geo.off_hd = geo.off_ext + 3 * Z;
+    geo.off_hd = geo.off_ext + 2 * Z;
     geo.off_syn = geo.off_hd + C * 2 * ZW32 * 4;
-    geo.slot_bytes[0] = geo.off_syn;
-    geo.slot_bytes[1] = geo.off_syn + R * ZW32 * 4;
+    // three mbarriers (32 bytes) close the slot; without syndrome input the syndrome rows are not allocated
+    geo.off_mbar[0] = geo.off_syn;
+    geo.off_mbar[1] = geo.off_syn + R * ZW32 * 4;
+    geo.slot_bytes[0] = geo.off_mbar[0] + 32;
+    geo.slot_bytes[1] = geo.off_mbar[1] + 32;
     const int avail = d->max_smem_optin - geo.tab_bytes - 16;
     for (int k = 0; k < 2; ++k) {
         int slots = std::min(std::min(avail / geo.slot_bytes[k], layered_i8s_max_threads() / W), 15);
@@ -624,7 +627,7 @@ static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint3
         p.slots = geo.slots[k];
         p.tab_bytes = geo.tab_bytes; p.off_rows = geo.off_rows; p.off_pcols = geo.off_pcols;
         p.slot_bytes = geo.slot_bytes[k]; p.off_ring = geo.off_ring; p.stage_bytes = geo.stage_bytes;
-        p.off_ext = geo.off_ext; p.off_hd = geo.off_hd; p.off_syn = geo.off_syn;
+        p.off_ext = geo.off_ext; p.off_hd = geo.off_hd; p.off_syn = geo.off_syn; p.off_mbar = geo.off_mbar[k];
         p.rg_u4 = geo.rg_u4;
         const int grid = std::min(d->sm_count, (n_frames + p.slots - 1) / p.slots);
         const size_t lane_u4 = (size_t)d->sm_count * std::max(geo.slots[0], geo.slots[1]) * geo.rg_u4;

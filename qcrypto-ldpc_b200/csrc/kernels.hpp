@@ -63,7 +63,7 @@ struct LayeredI8sParams {
     uint32_t h2_lo, h2_hi, h2_cap, h2_span, h2_negoff;   // half2 patterns: -(m+1), m, m+1, 2m+1, -offset (m = msg_max)
     int slots;
     int tab_bytes, off_rows, off_pcols;
-    int slot_bytes, off_ring, stage_bytes, off_ext, off_hd, off_syn;
+    int slot_bytes, off_ring, stage_bytes, off_ext, off_hd, off_syn, off_mbar;
     int rg_u4;                // uint4 per frame slot in the scratch
 };
 int launch_layered_i8s(const LayeredI8sParams &p, int grid, int smem_bytes, cudaStream_t st);

@@ -6,8 +6,8 @@
 //   shared memory, per frame slot:
 //     beliefs of the CORE block columns only (columns that are not weight-1/shift-0 extension columns),
 //       word i of a column = lanes {i, i+W, i+2W, i+3W} as biased bytes (L+128), W = Z/4;
-//     a 2-stage ring of check-to-variable messages (cp.async from / plain stores to an L2-resident scratch);
-//     a 3-deep ring of raw channel LLRs of the extension column of the rows about to be processed
+//     a 2-stage ring of check-to-variable messages (bulk copies from / plain stores to an L2-resident scratch);
+//     a 2-deep ring of raw channel LLRs of the extension column of the row being processed / staged
 //       (an extension column is read by exactly one row and never rewritten: its belief minus its message is
 //       the channel LLR for ever, only the SIGN of its a-posteriori value is observable);
 //     hard-decision bit vectors, each stored twice back to back so that a rotated window never wraps.
@@ -33,6 +33,15 @@
 #endif
 #ifndef QL_S_KEEPT
 #define QL_S_KEEPT 8                 // rows with more core edges re-clip L - R_old in the second pass instead of keeping t
+#endif
+#ifndef QL_S_ALIGN_ROWS
+#define QL_S_ALIGN_ROWS 0            // > 0: re-align the frame groups with a CTA-wide barrier every so many block rows
+#endif
+#ifndef QL_S_BELMBAR
+#define QL_S_BELMBAR 0               // 1: belief hand-over between rows through an arrive/wait mbarrier, 0: bar.sync
+#endif
+#ifndef QL_S_BIGMODE
+#define QL_S_BIGMODE 3   // per-edge register diet of the rows with more than 10 core edges
 #endif
 #ifndef QL_S_FMACLIP8
 #define QL_S_FMACLIP8 0              // belief clip (upper bound) on the FMA pipe
@@ -88,14 +97,32 @@ __device__ __forceinline__ bool bar_red_or(int id, int nthreads, bool pred)
         : "memory");
     return r != 0;
 }
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+__device__ __forceinline__ void mbar_init(u32 mb, u32 count)
 {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(u32 mb)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mb) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_tx(u32 mb, u32 bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u32 mb, u32 parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}"
+        ::"r"(mb), "r"(parity) : "memory");
+}
+// bulk copy global -> shared, completion counted in bytes on an mbarrier (size and addresses multiples of 16)
+__device__ __forceinline__ void bulk_g2s(u32 dst, const void *src, u32 bytes, u32 mb)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mb) : "memory");
+}
 
 // The table entry of an edge for this thread: entry 0 when lane i does not wrap past the end of the column,
 // entry 1 (16 bytes further) when it does.  Two predicated loads, one of which executes: no SEL chain.
@@ -129,6 +156,16 @@ __device__ __forceinline__ EdgeEntry load_entry(u32 saddr, int i, int thresh)
         : "=r"(e.off), "=r"(e.selA), "=r"(e.selB), "=r"(e.selW)
         : "r"(i), "r"(thresh), "r"(saddr));
     return e;
+}
+
+// re-read of a message block in the second pass (volatile: must not be merged with the first-pass read)
+__device__ __forceinline__ uint4 lds128_volatile(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"((u32)__cvta_generic_to_shared(p)));
+    return v;
 }
 
 // clip to the message range [-(msg_max+1), msg_max]
@@ -183,7 +220,8 @@ __device__ __forceinline__ void vset(uint4 &v, int k, u32 x)
 //   DC     unrolled core-edge slots; EXACT: the row has exactly DC core edges, else DC - 1 or DC (nc)
 //   EXT    one more edge goes to an extension column (channel bytes in extb, sign balloted into hd_ext)
 //   MODE   what stays in registers per edge between the two passes: 0: L - R_old, its clipped value, belief address
-//          and pack selector; 1: no clipped value (re-clip); 2: only L - R_old (re-clip, re-read the table entry)
+//          and pack selector; 1: no clipped value (re-clip); 2: only L - R_old (re-clip, re-read the table entry);
+//          3: only the belief word (re-read the table entry and the old message, redo the subtraction and the clip)
 //   Li     this thread's belief base (slot beliefs + 4*i); erow: shared address of the row's first table entry
 //   thr4   wrap thresholds of the row's edges, four per int4
 //   ysrc   this thread's message blocks (ystride uint4 apart); gdst: where the new ones go (W uint4 apart)
@@ -192,8 +230,8 @@ __device__ __forceinline__ void process_row(const Cx &cx, char *Li, u32 erow, co
                                             const uint4 *ysrc, int ystride, uint4 *gdst, int W,
                                             const unsigned char *extb, u32 *hd_ext)
 {
-    constexpr int KEEPT = MODE == 0 ? DC : 1, KEEPA = MODE <= 1 ? DC : 1;
-    u32 uA[DC], uB[DC], tA[KEEPT], tB[KEEPT], sw[KEEPA];
+    constexpr int KEEPT = MODE == 0 ? DC : 1, KEEPA = MODE <= 1 ? DC : 1, KEEPU = MODE <= 2 ? DC : 1, KEEPX = MODE == 3 ? DC : 1;
+    u32 uA[KEEPU], uB[KEEPU], tA[KEEPT], tB[KEEPT], sw[KEEPA], xk[KEEPX];
     char *ad[KEEPA];
     u32 m1A = m1init.x, m1B = m1init.y;   // running (min1, sign product); the sign starts at the syndrome bit
     u32 m2A = kInf2, m2B = kInf2;
@@ -215,7 +253,7 @@ __device__ __forceinline__ void process_row(const Cx &cx, char *Li, u32 erow, co
             const u32 yA = prmt(Y, 0u, 0x4140u), yB = prmt(Y, 0u, 0x4342u);
             const u32 ua = hsub(xA, yA), ub = hsub(xB, yB);          // L - R_old  (:51)
             const u32 ta = clip_msg(cx, ua), tb = clip_msg(cx, ub);   // clip to the message range (:54-55)
-            uA[j] = ua; uB[j] = ub;
+            if constexpr (MODE <= 2) { uA[j] = ua; uB[j] = ub; } else { xk[j] = X; }
             if constexpr (MODE == 0) { tA[j] = ta; tB[j] = tb; }
             if constexpr (MODE <= 1) { sw[j] = en.selW; ad[j] = a; }
             m2A = hmax(habs(m1A), hmin(habs(ta), m2A));               // second minimum (:61)
@@ -270,29 +308,37 @@ __device__ __forceinline__ void process_row(const Cx &cx, char *Li, u32 erow, co
 #pragma unroll
     for (int j = 0; j < DC; ++j) {
         if (EXACT || j < DC - 1 || j < nc) {
-            u32 ta, tb, selW;
+            u32 ta, tb, selW, ua, ub;
             char *a;
-            if constexpr (MODE == 2) {
+            if constexpr (MODE >= 2) {
                 if ((j & 3) == 0) Tq = thr4[j >> 2];
                 const EdgeEntry en = load_entry<true>(erow + 32 * j, i, vcomp(Tq, j & 3));
                 a = Li + en.off;
                 selW = en.selW;
+                if constexpr (MODE == 3) {
+                    if ((j & 3) == 0) Yq = lds128_volatile(ysrc + (j >> 2) * ystride);
+                    const u32 Y = vcomp(Yq, j & 3);
+                    ua = hsub(prmt(xk[j], 0u, en.selA), prmt(Y, 0u, 0x4140u));
+                    ub = hsub(prmt(xk[j], 0u, en.selB), prmt(Y, 0u, 0x4342u));
+                } else {
+                    ua = uA[j]; ub = uB[j];
+                }
             } else {
-                selW = sw[j]; a = ad[j];
+                selW = sw[j]; a = ad[j]; ua = uA[j]; ub = uB[j];
             }
             if constexpr (MODE == 0) {
                 ta = tA[j]; tb = tB[j];
             } else {
-                ta = clip_msg(cx, uA[j]);
-                tb = clip_msg(cx, uB[j]);
+                ta = clip_msg(cx, ua);
+                tb = clip_msg(cx, ub);
             }
             const u32 eA = heq_mask(habs(ta), min1A), eB = heq_mask(habs(tb), min1B);
             // |t| == min1 ? c1 : c2, then the edge's own sign (:73-75)
             const u32 rA = ((eA & c1A) | (~eA & c2A)) ^ (ta & kSignMask);
             const u32 rB = ((eB & c1B) | (~eB & c2B)) ^ (tb & kSignMask);
             const u32 bA = hadd(rA, k128), bB = hadd(rB, k128);       // biased new message
-            const u32 lA = clip_belief(uA[j], bA);                    // clip(L - R_old + R_new) biased (:88-91)
-            const u32 lB = clip_belief(uB[j], bB);
+            const u32 lA = clip_belief(ua, bA);                       // clip(L - R_old + R_new) biased (:88-91)
+            const u32 lB = clip_belief(ub, bB);
             vset(Yn, j & 3, prmt(bA, bB, 0x6420u));
             *reinterpret_cast<u32 *>(a) = prmt(lA, lB, selW);
         }
@@ -306,9 +352,10 @@ __device__ __forceinline__ void dispatch_row(int variant, const Cx &cx, char *Li
                                              const unsigned char *extb, u32 *hd_ext)
 {
 #define QL_ROW(DCV, EXACTV, EXTV, BIGV) \
-    process_row<NK, DCV, EXACTV, EXTV, (BIGV ? 2 : (DCV > QL_S_KEEPT ? 1 : 0))>(cx, Li, erow, thr4, nc, i, m1init, ysrc, ystride, gdst, \
+    process_row<NK, DCV, EXACTV, EXTV, (BIGV ? QL_S_BIGMODE : (DCV > QL_S_KEEPT ? 1 : 0))>(cx, Li, erow, thr4, nc, i, m1init, ysrc, ystride, gdst, \
                                                                                 W, extb, hd_ext)
     switch (variant) {
+#ifndef QL_S_NOSMALL
     case 0: QL_ROW(1, true, false, false); break;
     case 1: QL_ROW(1, true, true, false); break;
     case 2: QL_ROW(2, true, false, false); break;
@@ -329,6 +376,8 @@ __device__ __forceinline__ void dispatch_row(int variant, const Cx &cx, char *Li
     case 17: QL_ROW(9, true, true, false); break;
     case 18: QL_ROW(10, true, false, false); break;
     case 19: QL_ROW(10, true, true, false); break;
+#endif
+#ifndef QL_S_NOBIG
     case 20: QL_ROW(12, false, false, true); break;
     case 21: QL_ROW(12, false, true, true); break;
     case 22: QL_ROW(14, false, false, true); break;
@@ -339,6 +388,9 @@ __device__ __forceinline__ void dispatch_row(int variant, const Cx &cx, char *Li
     case 27: QL_ROW(18, false, true, true); break;
     case 28: QL_ROW(20, false, false, true); break;
     default: QL_ROW(20, false, true, true); break;
+#else
+    default: break;
+#endif
     }
 #undef QL_ROW
 }
@@ -354,8 +406,19 @@ __device__ __forceinline__ void transpose4x4(const u32 (&in)[4], u32 (&out)[4])
     out[3] = prmt(t2, t3, 0x7632u);
 }
 
-// WT: W = Z/4 at compile time (0: read it from the parameters); with a constant W every stride of the staging,
-// ballot and syndrome code folds into instruction immediates.
+// WT: W = Z/4 at compile time (0: read it from the parameters); with a constant W every stride of the ballot and
+// syndrome code folds into instruction immediates.
+//
+// Synchronisation inside a frame group (W threads, one frame):
+//   full[2]  transaction mbarriers: ONE elected thread stages the next block row -- its check-to-variable messages
+//            (bulk copy from the L2-resident scratch) and the raw channel bytes of its extension column (bulk copy
+//            from the frame's LLRs) -- into ring stage (trip+1)&1; every thread waits on full[trip&1] before it
+//            reads the stage.  No per-thread cp.async, no address arithmetic in the other 95 threads.
+//   bel      arrival mbarrier (count W): a thread arrives when its belief updates of a row are written and waits
+//            only right before it reads beliefs again, so the row header runs in the shadow of slower warps.
+// The messages are written with plain stores and read back, one iteration later, by the bulk-copy engine (async
+// proxy): every thread issues fence.proxy.async.global after its last store of an iteration, and the first row of
+// the next iteration is staged only after all threads of the group have passed that fence.
 template <int NK, int WT>
 __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const LayeredI8sParams p)
 {
@@ -367,12 +430,22 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
     const int lane = i & 31, wis = i >> 5;
     const int bar_id = 1 + g;
 
-    {   // shared tables (all slots) + one block of biased zero messages
+    char *slot = smem + p.tab_bytes + 16 + g * p.slot_bytes;
+    const u32 slot_saddr = (u32)__cvta_generic_to_shared(slot);
+    const u32 mb_full = slot_saddr + p.off_mbar, mb_bel = mb_full + 16;   // full[0], full[1] (8 bytes each), bel
+    {   // shared tables (all slots) + one block of biased zero messages; mbarriers of this group
         const int tid = g * W + i, nthreads = W * blockDim.y;
         const uint4 *src = reinterpret_cast<const uint4 *>(p.tab);
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
         for (int k = tid; k < (p.tab_bytes >> 4); k += nthreads) dst[k] = src[k];
         if (tid == 0) dst[p.tab_bytes >> 4] = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+        if (i == 0) {
+            mbar_init(mb_full, 1);
+            mbar_init(mb_full + 8, 1);
+            mbar_init(mb_bel, (u32)W);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
     }
     __syncthreads();
     const char *rowsc = smem + p.off_rows;               // Li8sRow[brows], read as int4 pairs
@@ -380,16 +453,15 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
     const uint4 *zero_blk = reinterpret_cast<const uint4 *>(smem + p.tab_bytes);
     const u32 tab_saddr = (u32)__cvta_generic_to_shared(smem);
 
-    char *slot = smem + p.tab_bytes + 16 + g * p.slot_bytes;
     u32 *Lw = reinterpret_cast<u32 *>(slot);
     char *Li = slot + 4 * i;
     char *ring_i = slot + p.off_ring + 16 * i;                        // 2 stages of stage_bytes
-    unsigned char *extb = reinterpret_cast<unsigned char *>(slot + p.off_ext);   // 3 buffers of Z bytes
+    unsigned char *extb_i = reinterpret_cast<unsigned char *>(slot + p.off_ext) + i;   // 2 buffers of Z bytes
     u32 *hd = reinterpret_cast<u32 *>(slot + p.off_hd);              // bcols vectors of 2*ZW32 words
     u32 *synl = reinterpret_cast<u32 *>(slot + p.off_syn);
-    char *rg_i = reinterpret_cast<char *>(p.rg + (size_t)(blockIdx.x * p.slots + g) * p.rg_u4 + i);   // this slot's scratch
+    char *rg_slot = reinterpret_cast<char *>(p.rg + (size_t)(blockIdx.x * p.slots + g) * p.rg_u4);   // this slot's scratch
+    char *rg_i = rg_slot + 16 * i;
     const bool has_syn = p.syn != nullptr;
-    const bool ext_thread = i < wq4;                                  // threads that stage 16 bytes of an extension column
 
     Cx cx;
     cx.cLo = p.h2_lo; cx.cHi = p.h2_hi; cx.cCap = p.h2_cap; cx.cSpan = p.h2_span;
@@ -401,6 +473,27 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
     const int lc = i / wq4, lj = i - lc * wq4;        // load phase: (column step, word quad)
     const int rs = i / ZW32, w = i - rs * ZW32;       // syndrome / output phases: (row step, 32-bit word); W / ZW32 == 8
 
+#if QL_S_BELMBAR
+#define QL_BEL_ARRIVE() mbar_arrive(mb_bel)
+#define QL_BEL_WAIT() do { mbar_wait(mb_bel, bt & 1u); ++bt; } while (0)
+#else
+#define QL_BEL_ARRIVE() bar_sync(bar_id, W)
+#define QL_BEL_WAIT() do { } while (0)
+#endif
+    // Stage block row `rn` (messages only when `with_msgs`) for trip `trip` -- elected thread only.
+    auto stage_row = [&](int rn, bool with_msgs, u32 trip, const int8_t *frame) {
+        const int4 na = *reinterpret_cast<const int4 *>(rowsc + 32 * rn);        // e_off, thr_off, g_off, nc|nv|variant
+        const int es = *reinterpret_cast<const int *>(rowsc + 32 * rn + 16);     // ext_src
+        const u32 st = trip & 1u;
+        const u32 mb = mb_full + 8 * st;
+        const u32 msg_bytes = with_msgs ? (u32)(((na.w >> 8) & 0xff) * W * 16) : 0u;
+        const u32 ext_bytes = es >= 0 ? (u32)Z : 0u;
+        if (msg_bytes + ext_bytes) mbar_arrive_tx(mb, msg_bytes + ext_bytes);
+        else mbar_arrive(mb);
+        if (msg_bytes) bulk_g2s(slot_saddr + p.off_ring + st * p.stage_bytes, rg_slot + na.z, msg_bytes, mb);
+        if (ext_bytes) bulk_g2s(slot_saddr + p.off_ext + st * Z, frame + es, ext_bytes, mb);
+    };
+
     // All frame groups of the CTA run their iterations in step (one CTA-wide barrier per iteration): every warp then
     // executes the same block-row code at about the same time, and the large unrolled code is fetched once per SM
     // instead of once per group (without it 37 % of the issue slots were lost to instruction-cache misses).
@@ -408,28 +501,19 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
     const int fstride = gridDim.x * p.slots;
     const int nthreads_cta = W * blockDim.y;
     bool active = false, need_load = true, conv = false;
-    int it = 0, stage = 0, k3 = 0, r2 = 0;   // k3: trip % 3, r2: row of trip + 2
-    const int8_t *llr_i = nullptr;
+    int it = 0;
+    u32 tt = 0;
+    [[maybe_unused]] u32 bt = 0;   // trips staged / waited on full[], phases waited on bel (both run on across frames)
 #pragma unroll 1
     for (;;) {
       if (need_load) {
         need_load = false;
         active = f < p.F;
         if (active) {
-        cp_async_wait<0>();   // nothing may still be in flight from the previous frame of this slot
         const int8_t *src = p.llr + (size_t)f * p.N;
-        llr_i = src + 16 * i;
-        // ---- prologue: channel bytes of the extension columns of the first two rows
-        if (ext_thread) {
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                const int es = *reinterpret_cast<const int *>(rowsc + 32 * t + 16);
-                if (es >= 0) cp_async16(extb + t * Z + 16 * i, llr_i + es);
-            }
-        }
-        cp_async_commit();
+        if (i == 0) stage_row(0, false, tt, src);   // extension bytes of the first row
         {   // pull this slot's next frame towards L2 while the current one is decoded
-            const int fn = f + gridDim.x * p.slots;
+            const int fn = f + fstride;
             if (fn < p.F) {
                 const char *nx = reinterpret_cast<const char *>(p.llr + (size_t)fn * p.N);
                 for (int o = i * 128; o < p.N; o += W * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
@@ -450,63 +534,47 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
             const u32 *sf = p.syn + (size_t)f * p.syn_words;
             for (int r = rs; r < R; r += 8) synl[r * ZW32 + w] = __brev(__ldg(sf + r * ZW32 + w));
         }
-        cp_async_wait<0>();
-        bar_sync(bar_id, W);
-        it = 0; stage = 0; k3 = 0; r2 = 2 % R;
+        QL_BEL_ARRIVE();
+        it = 0;
         conv = false;
         }
       }
       if (!bar_red_or(0, nthreads_cta, active)) break;   // also the alignment barrier of the iteration
       if (active) {
             bool finished = false;
-            if (it < p.max_iter) {
+            const int8_t *frame = p.llr + (size_t)f * p.N;
 #pragma unroll 1
-                for (int r = 0; r < R; ++r) {
-                    const int4 la = *reinterpret_cast<const int4 *>(rowsc + 32 * r);        // e_off, thr_off, g_off, nc|nv|variant
-                    const int4 lb = *reinterpret_cast<const int4 *>(rowsc + 32 * r + 16);   // ext_src, ext_hd, syn_off, deg
-                    {   // stage the NEXT row's messages (none exist during the first iteration) and the extension
-                        // bytes of the row after it, while this row is processed
-                        const int rn = r + 1 < R ? r + 1 : 0;
-                        if (it > 0 || rn == 0) {
-                            const int2 nx = *reinterpret_cast<const int2 *>(rowsc + 32 * rn + 8);   // g_off, nc|nv|variant
-                            const int nvn = (nx.y >> 8) & 0xff;
-                            char *dst = ring_i + (stage ^ 1) * p.stage_bytes;
-                            const char *s = rg_i + nx.x;
-#pragma unroll
-                            for (int q = 0; q < 5; ++q)
-                                if (q < nvn) cp_async16(dst + q * W * 16, s + q * W * 16);
-                        }
-                        if (ext_thread) {
-                            const int es = *reinterpret_cast<const int *>(rowsc + 32 * r2 + 16);
-                            const int kb = k3 >= 1 ? k3 - 1 : 2;   // (k3 + 2) % 3
-                            if (es >= 0) cp_async16(extb + kb * Z + 16 * i, llr_i + es);
-                        }
-                        cp_async_commit();
-                        cp_async_wait<1>();   // everything but the group just committed has landed
-                    }
-                    uint2 m1init = make_uint2(kInf2, kInf2);   // initial (min1, sign) of the two half2 pairs
-                    if (has_syn) {
-                        const u32 *sr = synl + r * ZW32 + wis;
-                        const u32 s0 = (sr[0] >> lane) & 1u, s1 = (sr[wq] >> lane) & 1u;
-                        const u32 s2 = (sr[2 * wq] >> lane) & 1u, s3 = (sr[3 * wq] >> lane) & 1u;
-                        m1init.x ^= (s0 << 15) | (s1 << 31);
-                        m1init.y ^= (s2 << 15) | (s3 << 31);
-                    }
-                    const uint4 *ysrc = it == 0 ? zero_blk : reinterpret_cast<const uint4 *>(ring_i + stage * p.stage_bytes);
-                    const int ystride = it == 0 ? 0 : W;
-                    dispatch_row<NK>(la.w >> 16, cx, Li, tab_saddr + la.x, reinterpret_cast<const int4 *>(smem + la.y),
-                                     la.w & 0xff, i, m1init, ysrc, ystride, reinterpret_cast<uint4 *>(rg_i + la.z), W,
-                                     extb + k3 * Z + i, reinterpret_cast<u32 *>(reinterpret_cast<char *>(hd) + lb.y));
-                    stage ^= 1;
-                    k3 = k3 == 2 ? 0 : k3 + 1;
-                    r2 = r2 + 1 < R ? r2 + 1 : 0;
-                    bar_sync(bar_id, W);
+            for (int r = 0; r < R; ++r) {
+                const int4 la = *reinterpret_cast<const int4 *>(rowsc + 32 * r);        // e_off, thr_off, g_off, nc|nv|variant
+                const int4 lb = *reinterpret_cast<const int4 *>(rowsc + 32 * r + 16);   // ext_src, ext_hd, syn_off, deg
+                const u32 stage = tt & 1u;
+                QL_BEL_WAIT();   // every belief update of the previous row is visible
+                if (i == 0 && r + 1 < R) stage_row(r + 1, it > 0, tt + 1, frame);
+                uint2 m1init = make_uint2(kInf2, kInf2);   // initial (min1, sign) of the two half2 pairs
+                if (has_syn) {
+                    const u32 *sr = synl + r * ZW32 + wis;
+                    const u32 s0 = (sr[0] >> lane) & 1u, s1 = (sr[wq] >> lane) & 1u;
+                    const u32 s2 = (sr[2 * wq] >> lane) & 1u, s3 = (sr[3 * wq] >> lane) & 1u;
+                    m1init.x ^= (s0 << 15) | (s1 << 31);
+                    m1init.y ^= (s2 << 15) | (s3 << 31);
                 }
-                ++it;
+                const uint4 *ysrc = it == 0 ? zero_blk : reinterpret_cast<const uint4 *>(ring_i + stage * p.stage_bytes);
+                const int ystride = it == 0 ? 0 : W;
+                mbar_wait(mb_full + 8 * stage, (tt >> 1) & 1u);   // this row's messages / extension bytes have landed
+                ++tt;
+                dispatch_row<NK>(la.w >> 16, cx, Li, tab_saddr + la.x, reinterpret_cast<const int4 *>(smem + la.y),
+                                 la.w & 0xff, i, m1init, ysrc, ystride, reinterpret_cast<uint4 *>(rg_i + la.z), W,
+                                 extb_i + stage * Z, reinterpret_cast<u32 *>(reinterpret_cast<char *>(hd) + lb.y));
+                if (r == R - 1) asm volatile("fence.proxy.async.global;" ::: "memory");
+                QL_BEL_ARRIVE();
             }
+            ++it;
+            const bool more = it < p.max_iter;
+            QL_BEL_WAIT();
+            if (i == 0 && more) stage_row(0, true, tt, frame);   // first row of the next iteration (dropped if the frame ends)
             // the syndrome / hard-decision phase runs after every iteration when early stop is on,
             // otherwise once after the last iteration
-            if (p.early_stop || it >= p.max_iter) {
+            if (p.early_stop || !more) {
                 // hard decisions of the core columns (extension columns were balloted in their rows)
                 u32 *hl = hd + wis;
 #pragma unroll 2
@@ -558,9 +626,13 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
                     any_bad = bar_red_or(bar_id, W, bad != 0u);
                 }
                 conv = !any_bad;
-                finished = conv || it >= p.max_iter;
+                finished = conv || !more;
             }
-        if (finished) {
+        if (!finished) {
+#if QL_S_BELMBAR
+            mbar_arrive(mb_bel);   // matched by the wait of the next iteration's first row
+#endif
+        } else {
         // ---- outputs: MSB-first packed hard decisions of the first out_cols block columns
         uint32_t *of = p.out + (size_t)f * p.out_words;
         for (int c = rs; c < p.out_cols; c += 8) of[c * ZW32 + w] = __brev(hd[c * 2 * ZW32 + w]);
@@ -574,13 +646,16 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
                 atomicAdd(&p.stats->hist[min(it, QLDPC_ITER_HIST_BINS - 1)], 1ull);
             }
         }
-        bar_sync(bar_id, W);   // hd / beliefs are reused by the next frame of this slot
+        if (more) {   // the speculative stage of the next iteration's first row: let it land, then forget it
+            mbar_wait(mb_full + 8 * (tt & 1u), (tt >> 1) & 1u);
+            ++tt;
+        }
+        bar_sync(bar_id, W);   // hd / beliefs / ring are reused by the next frame of this slot
         f += fstride;
         need_load = true;
         }
       }
     }
-    cp_async_wait<0>();
 }
 
 template <int NK, int WT>

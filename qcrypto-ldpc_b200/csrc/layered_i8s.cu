@@ -43,6 +43,15 @@
 #ifndef QL_S_BIGMODE
 #define QL_S_BIGMODE 3   // per-edge register diet of the rows with more than 10 core edges
 #endif
+#ifndef QL_S_LOADUNROLL
+#define QL_S_LOADUNROLL 4            // column steps of the frame load in flight per thread (BG1: 26 core columns = 7 steps)
+#endif
+#ifndef QL_S_FMANORM
+#define QL_S_FMANORM 1               // k/8 normalisation with two FMA-pipe instructions per term instead of shift+mask+add
+#endif
+#ifndef QL_S_BIGKEEPU
+#define QL_S_BIGKEEPU 10             // edges of a big row whose L - R_old stays in registers between the passes
+#endif
 #ifndef QL_S_FMACLIP8
 #define QL_S_FMACLIP8 0              // belief clip (upper bound) on the FMA pipe
 #endif
@@ -59,6 +68,7 @@ constexpr u32 kOne2 = 0x3c003c00u;     // 1.0h, 1.0h
 constexpr u32 kMinusOne2 = 0xbc00bc00u;
 constexpr u32 k128 = 0x00800080u;
 constexpr u32 k255 = 0x00ff00ffu;
+constexpr int kLoadUnroll = QL_S_LOADUNROLL;
 
 __device__ __forceinline__ __half2 h2(u32 x) { return *reinterpret_cast<__half2 *>(&x); }
 __device__ __forceinline__ u32 bits(__half2 h) { return *reinterpret_cast<u32 *>(&h); }
@@ -195,11 +205,26 @@ __device__ __forceinline__ u32 clip_belief(u32 u, u32 b)
 #endif
 }
 
+// integer k/8 normalisation on two packed non-negative fields: sum of floor(x/2), floor(x/4), floor(x/8) terms
+// (AFF3CT's integer normalize).  FMA form: floor(x / 2^s) = (x with its s low bits cleared) * 2^-s, exact in fp16
+// for integers held as subnormals; one LOP3 on the ALU pipe per term, the multiply-adds run on the FMA pipe.
 template <int NK>
 __device__ __forceinline__ u32 norm_eighths2(u32 x, int k_rt)
 {
     const int k = NK < 0 ? k_rt : NK;
     if (k >= 8) return x;
+#if QL_S_FMANORM
+    if (NK > 0) {
+        u32 r = 0;
+        bool first = true;
+        if (k & 4) { r = bits(__hmul2(h2(x & 0xfffefffeu), h2(0x38003800u))); first = false; }                      // * 0.5
+        if (k & 2) { r = first ? bits(__hmul2(h2(x & 0xfffcfffcu), h2(0x34003400u)))
+                               : bits(__hfma2(h2(x & 0xfffcfffcu), h2(0x34003400u), h2(r))); first = false; }     // * 0.25
+        if (k & 1) { r = first ? bits(__hmul2(h2(x & 0xfff8fff8u), h2(0x30003000u)))
+                               : bits(__hfma2(h2(x & 0xfff8fff8u), h2(0x30003000u), h2(r))); }                    // * 0.125
+        return r;
+    }
+#endif
     const u32 s1 = (x >> 1) & 0x7fff7fffu, s2 = (x >> 2) & 0x3fff3fffu, s3 = (x >> 3) & 0x1fff1fffu;
     u32 r = 0;
     if (k & 4) r += s1;
@@ -230,7 +255,9 @@ __device__ __forceinline__ void process_row(const Cx &cx, char *Li, u32 erow, co
                                             const uint4 *ysrc, int ystride, uint4 *gdst, int W,
                                             const unsigned char *extb, u32 *hd_ext)
 {
-    constexpr int KEEPT = MODE == 0 ? DC : 1, KEEPA = MODE <= 1 ? DC : 1, KEEPU = MODE <= 2 ? DC : 1, KEEPX = MODE == 3 ? DC : 1;
+    // MODE 3 keeps L - R_old for its first QL_S_BIGKEEPU edges and only the belief word for the others
+    constexpr int KU = MODE <= 2 ? DC : (QL_S_BIGKEEPU < DC ? QL_S_BIGKEEPU : DC);
+    constexpr int KEEPT = MODE == 0 ? DC : 1, KEEPA = MODE <= 1 ? DC : 1, KEEPU = KU > 0 ? KU : 1, KEEPX = MODE == 3 ? DC : 1;
     u32 uA[KEEPU], uB[KEEPU], tA[KEEPT], tB[KEEPT], sw[KEEPA], xk[KEEPX];
     char *ad[KEEPA];
     u32 m1A = m1init.x, m1B = m1init.y;   // running (min1, sign product); the sign starts at the syndrome bit
@@ -253,7 +280,7 @@ __device__ __forceinline__ void process_row(const Cx &cx, char *Li, u32 erow, co
             const u32 yA = prmt(Y, 0u, 0x4140u), yB = prmt(Y, 0u, 0x4342u);
             const u32 ua = hsub(xA, yA), ub = hsub(xB, yB);          // L - R_old  (:51)
             const u32 ta = clip_msg(cx, ua), tb = clip_msg(cx, ub);   // clip to the message range (:54-55)
-            if constexpr (MODE <= 2) { uA[j] = ua; uB[j] = ub; } else { xk[j] = X; }
+            if (j < KU) { uA[j] = ua; uB[j] = ub; } else { xk[j] = X; }
             if constexpr (MODE == 0) { tA[j] = ta; tB[j] = tb; }
             if constexpr (MODE <= 1) { sw[j] = en.selW; ad[j] = a; }
             m2A = hmax(habs(m1A), hmin(habs(ta), m2A));               // second minimum (:61)
@@ -299,9 +326,8 @@ __device__ __forceinline__ void process_row(const Cx &cx, char *Li, u32 erow, co
         const u32 b3 = __ballot_sync(0xffffffffu, (int)aB < 0);           // lane i + 3W
         if (cx.lane == 0) {
             u32 *h = hd_ext + cx.wis;
-            const int wq = cx.wq, zw = cx.ZW32;
+            const int wq = cx.wq;   // shift 0: the syndrome phase never reads the second copy of this vector
             h[0] = b0; h[wq] = b1; h[2 * wq] = b2; h[3 * wq] = b3;
-            h[zw] = b0; h[zw + wq] = b1; h[zw + 2 * wq] = b2; h[zw + 3 * wq] = b3;
         }
     }
     uint4 Yn = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
@@ -315,8 +341,8 @@ __device__ __forceinline__ void process_row(const Cx &cx, char *Li, u32 erow, co
                 const EdgeEntry en = load_entry<true>(erow + 32 * j, i, vcomp(Tq, j & 3));
                 a = Li + en.off;
                 selW = en.selW;
-                if constexpr (MODE == 3) {
-                    if ((j & 3) == 0) Yq = lds128_volatile(ysrc + (j >> 2) * ystride);
+                if (j >= KU) {
+                    if ((j & 3) == 0 || j == KU) Yq = lds128_volatile(ysrc + (j >> 2) * ystride);
                     const u32 Y = vcomp(Yq, j & 3);
                     ua = hsub(prmt(xk[j], 0u, en.selA), prmt(Y, 0u, 0x4140u));
                     ub = hsub(prmt(xk[j], 0u, en.selB), prmt(Y, 0u, 0x4342u));
@@ -521,7 +547,7 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
         }
         // ---- load: int8 LLRs of the core columns -> interleaved biased belief words
         // 4 aligned 32-bit loads (one per quarter of the column) -> 4x4 byte transpose -> one 128-bit store
-#pragma unroll 4
+#pragma unroll kLoadUnroll
         for (int c = lc; c < p.n_pack; c += 4) {
             const u32 *q = reinterpret_cast<const u32 *>(src + pcols[c].llr_off) + lj;
             u32 in[4], out[4];

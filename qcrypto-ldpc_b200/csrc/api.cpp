@@ -513,6 +513,17 @@ extern "C" int qldpc_decoder_create(const qldpc_code *code, const qldpc_decoder_
         const bool fast_s = i8_ok && plan_layered_i8s(d);
         const bool fast = !fast_s && i8_ok && plan_layered_i8(d, p, true);
         if (fast_s) {
+            {   // L2 set-aside for the message scratch: the streamed LLRs would otherwise evict it (ncu: DRAM traffic halves).
+                // This is a device-wide limit of the CUDA context; QLDPC_L2_PERSIST=<MiB> overrides, 0 leaves it alone.
+                size_t want = (size_t)d->sm_count * d->li8s_geo.slots[0] * d->li8s_geo.rg_u4 * 16;
+                if (const char *e = std::getenv("QLDPC_L2_PERSIST")) want = (size_t)std::max(0, std::atoi(e)) << 20;
+                const size_t lim = std::min<size_t>(want, (size_t)prop.persistingL2CacheMaxSize);
+                if (lim > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, lim) == cudaSuccess) {
+                    d->l2_persist_bytes = lim;
+                    d->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+                }
+                cudaGetLastError();
+            }
             d->kernel_family = KF_LAYERED_I8S;
             d->kernel_name = "layered_i8_zpack4";
         } else if (fast) {
@@ -634,6 +645,18 @@ static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint3
         if ((rc = d->d_li8s_rg.ensure(2 * lane_u4))) return rc;
         p.rg = d->d_li8s_rg.p + (size_t)scratch_lane * lane_u4;
         const int smem_bytes = geo.tab_bytes + 16 + p.slots * p.slot_bytes;
+        if (d->l2_persist_bytes > 0) {
+            // keep (a share of) the message scratch resident in L2 while the LLR stream flows through it
+            const size_t win = std::min<size_t>((size_t)grid * p.slots * geo.rg_u4 * 16, (size_t)d->l2_window_max);
+            cudaStreamAttrValue av{};
+            av.accessPolicyWindow.base_ptr = p.rg;
+            av.accessPolicyWindow.num_bytes = win;
+            av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)d->l2_persist_bytes / (double)std::max<size_t>(win, 1));
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+            cudaGetLastError();
+        }
         if ((rc = launch_layered_i8s(p, grid, smem_bytes, st))) return rc;
         d->kernel_launches++;
         if (!direct) {

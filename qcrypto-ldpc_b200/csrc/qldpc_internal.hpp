@@ -171,4 +171,5 @@ struct qldpc_decoder {
     qldpc::Li8sGeo li8s_geo;
     qldpc::DevBuf<uint8_t> d_li8s_tab;
     qldpc::DevBuf<uint4> d_li8s_rg;
+    size_t l2_persist_bytes = 0, l2_window_max = 0;   // L2 set-aside for the message scratch (0: off)
 };

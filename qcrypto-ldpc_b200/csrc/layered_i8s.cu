@@ -52,6 +52,9 @@
 #ifndef QL_S_BIGKEEPU
 #define QL_S_BIGKEEPU 10             // edges of a big row whose L - R_old stays in registers between the passes
 #endif
+#ifndef QL_S_FIRSTSPEC
+#define QL_S_FIRSTSPEC 0             // separate code for the first iteration of a frame: -8 % (groups at different iterations stop sharing code)
+#endif
 #ifndef QL_S_FMACLIP8
 #define QL_S_FMACLIP8 0              // belief clip (upper bound) on the FMA pipe
 #endif
@@ -250,7 +253,8 @@ __device__ __forceinline__ void vset(uint4 &v, int k, u32 x)
 //   Li     this thread's belief base (slot beliefs + 4*i); erow: shared address of the row's first table entry
 //   thr4   wrap thresholds of the row's edges, four per int4
 //   ysrc   this thread's message blocks (ystride uint4 apart); gdst: where the new ones go (W uint4 apart)
-template <int NK, int DC, bool EXACT, bool EXT, int MODE>
+//   FIRST  first iteration of a frame: every old message is zero, nothing is read from the ring
+template <int NK, int DC, bool EXACT, bool EXT, int MODE, bool FIRST>
 __device__ __forceinline__ void process_row(const Cx &cx, char *Li, u32 erow, const int4 *thr4, int nc, int i, uint2 m1init,
                                             const uint4 *ysrc, int ystride, uint4 *gdst, int W,
                                             const unsigned char *extb, u32 *hd_ext)
@@ -269,15 +273,18 @@ __device__ __forceinline__ void process_row(const Cx &cx, char *Li, u32 erow, co
     for (int j = 0; j < DC; ++j) {
         if (EXACT || j < DC - 1 || j < nc) {
             if ((j & 3) == 0) {
-                Yq = ysrc[(j >> 2) * ystride];
+                if constexpr (!FIRST) Yq = ysrc[(j >> 2) * ystride];
                 Tq = thr4[j >> 2];
             }
             const EdgeEntry en = load_entry<false>(erow + 32 * j, i, vcomp(Tq, j & 3));
             char *a = Li + en.off;
             const u32 X = *reinterpret_cast<const u32 *>(a);
-            const u32 Y = vcomp(Yq, j & 3);
             const u32 xA = prmt(X, 0u, en.selA), xB = prmt(X, 0u, en.selB);
-            const u32 yA = prmt(Y, 0u, 0x4140u), yB = prmt(Y, 0u, 0x4342u);
+            u32 yA = k128, yB = k128;                                 // biased zero message
+            if constexpr (!FIRST) {
+                const u32 Y = vcomp(Yq, j & 3);
+                yA = prmt(Y, 0u, 0x4140u); yB = prmt(Y, 0u, 0x4342u);
+            }
             const u32 ua = hsub(xA, yA), ub = hsub(xB, yB);          // L - R_old  (:51)
             const u32 ta = clip_msg(cx, ua), tb = clip_msg(cx, ub);   // clip to the message range (:54-55)
             if (j < KU) { uA[j] = ua; uB[j] = ub; } else { xk[j] = X; }
@@ -342,10 +349,14 @@ __device__ __forceinline__ void process_row(const Cx &cx, char *Li, u32 erow, co
                 a = Li + en.off;
                 selW = en.selW;
                 if (j >= KU) {
-                    if ((j & 3) == 0 || j == KU) Yq = lds128_volatile(ysrc + (j >> 2) * ystride);
-                    const u32 Y = vcomp(Yq, j & 3);
-                    ua = hsub(prmt(xk[j], 0u, en.selA), prmt(Y, 0u, 0x4140u));
-                    ub = hsub(prmt(xk[j], 0u, en.selB), prmt(Y, 0u, 0x4342u));
+                    u32 yA = k128, yB = k128;
+                    if constexpr (!FIRST) {
+                        if ((j & 3) == 0 || j == KU) Yq = lds128_volatile(ysrc + (j >> 2) * ystride);
+                        const u32 Y = vcomp(Yq, j & 3);
+                        yA = prmt(Y, 0u, 0x4140u); yB = prmt(Y, 0u, 0x4342u);
+                    }
+                    ua = hsub(prmt(xk[j], 0u, en.selA), yA);
+                    ub = hsub(prmt(xk[j], 0u, en.selB), yB);
                 } else {
                     ua = uA[j]; ub = uB[j];
                 }
@@ -372,13 +383,13 @@ __device__ __forceinline__ void process_row(const Cx &cx, char *Li, u32 erow, co
     }
 }
 
-template <int NK>
+template <int NK, bool FIRST>
 __device__ __forceinline__ void dispatch_row(int variant, const Cx &cx, char *Li, u32 erow, const int4 *thr4, int nc, int i,
                                              uint2 m1init, const uint4 *ysrc, int ystride, uint4 *gdst, int W,
                                              const unsigned char *extb, u32 *hd_ext)
 {
 #define QL_ROW(DCV, EXACTV, EXTV, BIGV) \
-    process_row<NK, DCV, EXACTV, EXTV, (BIGV ? QL_S_BIGMODE : (DCV > QL_S_KEEPT ? 1 : 0))>(cx, Li, erow, thr4, nc, i, m1init, ysrc, ystride, gdst, \
+    process_row<NK, DCV, EXACTV, EXTV, (BIGV ? QL_S_BIGMODE : (DCV > QL_S_KEEPT ? 1 : 0)), FIRST>(cx, Li, erow, thr4, nc, i, m1init, ysrc, ystride, gdst, \
                                                                                 W, extb, hd_ext)
     switch (variant) {
 #ifndef QL_S_NOSMALL
@@ -584,13 +595,20 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
                     m1init.x ^= (s0 << 15) | (s1 << 31);
                     m1init.y ^= (s2 << 15) | (s3 << 31);
                 }
-                const uint4 *ysrc = it == 0 ? zero_blk : reinterpret_cast<const uint4 *>(ring_i + stage * p.stage_bytes);
-                const int ystride = it == 0 ? 0 : W;
+                const uint4 *ysrc = reinterpret_cast<const uint4 *>(ring_i + stage * p.stage_bytes);
                 mbar_wait(mb_full + 8 * stage, (tt >> 1) & 1u);   // this row's messages / extension bytes have landed
                 ++tt;
-                dispatch_row<NK>(la.w >> 16, cx, Li, tab_saddr + la.x, reinterpret_cast<const int4 *>(smem + la.y),
-                                 la.w & 0xff, i, m1init, ysrc, ystride, reinterpret_cast<uint4 *>(rg_i + la.z), W,
-                                 extb_i + stage * Z, reinterpret_cast<u32 *>(reinterpret_cast<char *>(hd) + lb.y));
+#if QL_S_FIRSTSPEC
+                if (it == 0)
+                    dispatch_row<NK, true>(la.w >> 16, cx, Li, tab_saddr + la.x, reinterpret_cast<const int4 *>(smem + la.y),
+                                           la.w & 0xff, i, m1init, ysrc, W, reinterpret_cast<uint4 *>(rg_i + la.z), W,
+                                           extb_i + stage * Z, reinterpret_cast<u32 *>(reinterpret_cast<char *>(hd) + lb.y));
+                else
+#endif
+                dispatch_row<NK, false>(la.w >> 16, cx, Li, tab_saddr + la.x, reinterpret_cast<const int4 *>(smem + la.y),
+                                        la.w & 0xff, i, m1init, QL_S_FIRSTSPEC || it ? ysrc : zero_blk, QL_S_FIRSTSPEC || it ? W : 0,
+                                        reinterpret_cast<uint4 *>(rg_i + la.z), W,
+                                        extb_i + stage * Z, reinterpret_cast<u32 *>(reinterpret_cast<char *>(hd) + lb.y));
                 if (r == R - 1) asm volatile("fence.proxy.async.global;" ::: "memory");
                 QL_BEL_ARRIVE();
             }

@@ -215,6 +215,31 @@ def run_reference(args, rank, world):
 
 # --------------------------------------------------------------------------------------------- ours
 
+def synth_frames_device(torch, dec, F, K, N, seed, dev, st):
+    """Synthetic sifted-key frames generated on the device with the library's own encoder / LLR kernels: Alice's
+    random key, NR-encoded; Bob's copy with every information bit flipped with probability QBER; parity known.
+    Returns (msg words [F,K/32], Bob's noisy codeword words, known mask words, int8 LLRs [F,N])."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    kw = K // 32
+    msg = torch.randint(-2**31, 2**31 - 1, (F, kw), dtype=torch.int32, device=dev, generator=g)
+    cw = torch.empty((F, dec.cw_words), dtype=torch.int32, device=dev)
+    dec.encode_nr_device(msg.data_ptr(), F, cw.data_ptr(), st)
+    # BSC on the information part: flip each of the K bits with probability QBER
+    flips = (torch.rand((F, K), device=dev, generator=g) < QBER).view(F, kw, 32)
+    weights = (2 ** torch.arange(31, -1, -1, device=dev, dtype=torch.int64))
+    fw = (flips.to(torch.int64) * weights).sum(dim=2)
+    fw = torch.where(fw >= 2**31, fw - 2**32, fw).to(torch.int32)
+    noisy = cw
+    noisy[:, :kw] ^= fw
+    del flips, weights, fw
+    known = torch.zeros(dec.cw_words, dtype=torch.int32, device=dev)
+    known[kw:] = -1
+    llr = torch.empty((F, N), dtype=torch.int8, device=dev)
+    dec.make_llr_device(noisy.data_ptr(), known.data_ptr(), 0, LLR_NOISY, LLR_KNOWN, F, llr.data_ptr(), st)
+    return msg, noisy, known, llr
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -231,25 +256,8 @@ def run_ours(args, rank, world, local_rank):
     F, N, K = args.frames, code.n, code.k
     st = torch.cuda.current_stream().cuda_stream
 
-    # ---- synthetic sifted-key frames, generated on the device with the library's own encoder / LLR kernels
-    g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
+    msg, noisy, known, llr = synth_frames_device(torch, dec, F, K, N, 1234 + rank, dev, st)
     kw = K // 32
-    msg = torch.randint(-2**31, 2**31 - 1, (F, kw), dtype=torch.int32, device=dev, generator=g)
-    cw = torch.empty((F, dec.cw_words), dtype=torch.int32, device=dev)
-    dec.encode_nr_device(msg.data_ptr(), F, cw.data_ptr(), st)
-    # BSC on the information part: flip each of the K bits with probability QBER
-    flips = (torch.rand((F, K), device=dev, generator=g) < QBER).view(F, kw, 32)
-    weights = (2 ** torch.arange(31, -1, -1, device=dev, dtype=torch.int64))
-    fw = (flips.to(torch.int64) * weights).sum(dim=2)
-    fw = torch.where(fw >= 2**31, fw - 2**32, fw).to(torch.int32)
-    noisy = cw.clone()
-    noisy[:, :kw] ^= fw
-    del flips, weights, fw
-    known = torch.zeros(dec.cw_words, dtype=torch.int32, device=dev)
-    known[kw:] = -1
-    llr = torch.empty((F, N), dtype=torch.int8, device=dev)
-    dec.make_llr_device(noisy.data_ptr(), known.data_ptr(), 0, LLR_NOISY, LLR_KNOWN, F, llr.data_ptr(), st)
     out = torch.empty((F, dec.out_words), dtype=torch.int32, device=dev)
     ok = torch.empty(F, dtype=torch.uint8, device=dev)
     iters = torch.empty(F, dtype=torch.int16, device=dev)

@@ -1,0 +1,103 @@
+#!/usr/bin/env python3
+"""BASELINE config 3 measurement: QBER sweep 1..8 % on the N = 65536 QKD code (qkd_psdpeg_n65536.qc), float flooding
+SPA vs normalised min-sum, rate adaptation by puncturing (p) / shortening (s) a public pseudo-random position set.
+Runs on the GPU box; writes a markdown table (FER, mean iterations, efficiency f = leak / h(QBER), decode Mbit/s of key).
+
+    python tools_qber_sweep.py [--frames 192] [--out gpurun_out/qber_sweep.md]
+"""
+import argparse
+import importlib
+import math
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def h2(p):
+    return -p * math.log2(p) - (1 - p) * math.log2(1 - p)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=192)
+    ap.add_argument("--max-iter", type=int, default=50)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "qber_sweep.md"))
+    args = ap.parse_args()
+    import torch
+    q = importlib.import_module("qcrypto-ldpc_b200")
+    dev = torch.device("cuda", 0)
+    code = q.Code.from_qc_file(q.data_path("qkd_psdpeg_n65536.qc"))
+    N, M = code.n, code.m
+    F = args.frames
+    decs = {"SPA": q.Decoder(code, schedule=q.SCHED_FLOODING, rule=q.RULE_SPA, dtype=q.DTYPE_F32, max_iter=args.max_iter,
+                             early_stop=True, out_mode=q.OUT_ALL),
+            "NMS 13/16": q.Decoder(code, schedule=q.SCHED_FLOODING, rule=q.RULE_NMS, dtype=q.DTYPE_F32, max_iter=args.max_iter,
+                                   early_stop=True, norm_factor=0.8125, out_mode=q.OUT_ALL)}
+    any_dec = decs["SPA"]
+    cw, sw = any_dec.cw_words, any_dec.syn_words
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device=dev); g.manual_seed(99)
+    perm = torch.from_numpy(np.random.default_rng(7).permutation(N)).to(dev)
+    weights = (2 ** torch.arange(31, -1, -1, device=dev, dtype=torch.int64))
+
+    def pack(bits):   # [.., N] uint8 on device -> MSB-first int32 words
+        v = (bits.view(*bits.shape[:-1], -1, 32).to(torch.int64) * weights).sum(dim=-1)
+        return torch.where(v >= 2**31, v - 2**32, v).to(torch.int32).contiguous()
+
+    rows = []
+    for qber in (0.01, 0.02, 0.03, 0.04, 0.05, 0.06, 0.07, 0.08):
+        for pf, sf in ((0.0, 0.0), (0.05, 0.0), (0.10, 0.0), (0.15, 0.0), (0.20, 0.0), (0.25, 0.0), (0.0, 0.05), (0.10, 0.05)):
+            n_p, n_s = int(pf * N), int(sf * N)
+            punct = torch.zeros(N, dtype=torch.uint8, device=dev); punct[perm[:n_p]] = 1
+            short = torch.zeros(N, dtype=torch.uint8, device=dev); short[perm[n_p:n_p + n_s]] = 1
+            x = torch.randint(0, 2, (F, N), dtype=torch.uint8, device=dev, generator=g)
+            e = (torch.rand((F, N), device=dev, generator=g) < qber).to(torch.uint8)
+            e[:, (punct | short) == 1] = 0
+            xb, yb = pack(x), pack(x ^ e)
+            syn = torch.empty((F, sw), dtype=torch.int32, device=dev)
+            any_dec.syndrome_device(xb.data_ptr(), F, syn.data_ptr(), st)
+            pm, km = pack(punct), pack(short)
+            llr = torch.empty((F, N), dtype=torch.float32, device=dev)
+            mag = math.log((1 - qber) / qber)
+            any_dec.make_llr_device(yb.data_ptr(), km.data_ptr(), pm.data_ptr(), mag, 23.02585, F, llr.data_ptr(), st)
+            n_key = N - n_p - n_s
+            leak = (M - n_p) / n_key            # syndrome bits minus the filler bits they are spent on, per key bit
+            eff = leak / h2(qber)
+            cell = [("%.0f %%" % (100 * qber)), "%.2f" % pf, "%.2f" % sf, "%.3f" % leak, "%.2f" % eff]
+            for name, dec in decs.items():
+                out = torch.empty((F, cw), dtype=torch.int32, device=dev)
+                ok = torch.empty(F, dtype=torch.uint8, device=dev)
+                it = torch.empty(F, dtype=torch.int16, device=dev)
+                dec.decode_device(llr.data_ptr(), syn.data_ptr(), F, out.data_ptr(), ok.data_ptr(), it.data_ptr(), 0, st)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                dec.decode_device(llr.data_ptr(), syn.data_ptr(), F, out.data_ptr(), ok.data_ptr(), it.data_ptr(), 0, st)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                good = ok.bool() & (out == xb).all(dim=1)      # converged AND equal to Alice's word
+                fer = 1.0 - float(good.float().mean())
+                undet = int((ok.bool() & ~(out == xb).all(dim=1)).sum())
+                cell += ["%.3f" % fer, "%.1f" % float(it.float().mean()), "%.0f" % (F * n_key / dt / 1e6), str(undet)]
+            rows.append(cell)
+            print(" | ".join(cell), flush=True)
+    hdr = ["QBER", "p/N", "s/N", "leak/key bit", "f"]
+    for name in decs:
+        hdr += ["FER %s" % name, "iters", "key Mbit/s", "undetected"]
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    with open(args.out, "w") as f:
+        f.write("# QBER sweep, N = 65536 PSD-PEG (3,6) QC code, flooding fp32, max %d iterations, %d frames per cell, B200\n\n" % (args.max_iter, F))
+        f.write("Syndrome decoding with a public pseudo-random modulation pattern: p punctured (filler, LLR 0), s shortened (known, LLR 23.03).\n")
+        f.write("FER counts frames that did not converge to Alice's word; `undetected` = converged to a different word.\n\n")
+        f.write("| " + " | ".join(hdr) + " |\n|" + "---|" * len(hdr) + "\n")
+        for r in rows:
+            f.write("| " + " | ".join(r) + " |\n")
+    print("wrote", args.out)
+
+
+if __name__ == "__main__":
+    main()

@@ -759,13 +759,31 @@ extern "C" int qldpc_decode_device(qldpc_decoder *dec, const void *d_llr, const 
 
 // Chunk size of the host-pointer entry points: whole waves of the persistent grid (no ragged last wave), about
 // `target_bytes` of device input per chunk; QLDPC_CHUNK_FRAMES overrides (experiments).
-static int pick_chunk(const qldpc_decoder_full *d, size_t frame_bytes, size_t target_bytes, int n_frames)
+// Chunk schedule of the host-pointer entry points.  Chunks are whole waves of the persistent grid; they start small
+// (two waves: the first kernel starts after a 5 MB copy) and double up to about `target_bytes` of device input, so that
+// a large batch needs few launches (every launch ends with a partly idle wave) without paying for it in pipeline fill.
+// QLDPC_CHUNK_FRAMES forces one uniform size (experiments).
+struct ChunkPlan {
+    int wave = 1, first = 1, max = 1;
+    bool uniform = false;
+    int at(int idx) const
+    {
+        if (uniform) return max;
+        long long c = first;
+        for (int k = 0; k < idx && c < max; ++k) c *= 2;
+        return (int)std::min<long long>(c, max);
+    }
+};
+static ChunkPlan pick_chunk(const qldpc_decoder_full *d, size_t frame_bytes, size_t target_bytes, int n_frames)
 {
-    const int wave = d->sm_count * std::max(1, d->li8_slots);
+    ChunkPlan cp;
+    cp.wave = d->sm_count * std::max(1, d->li8_slots);
     long long chunk = (long long)std::max<size_t>(1, target_bytes / frame_bytes);
-    if (const char *e = std::getenv("QLDPC_CHUNK_FRAMES")) chunk = std::max(1, std::atoi(e));
-    chunk = std::max<long long>(wave, (chunk + wave / 2) / wave * wave);
-    return (int)std::min<long long>(chunk, n_frames);
+    if (const char *e = std::getenv("QLDPC_CHUNK_FRAMES")) { chunk = std::max(1, std::atoi(e)); cp.uniform = true; }
+    chunk = std::max<long long>(cp.wave, (chunk + cp.wave / 2) / cp.wave * cp.wave);
+    cp.max = (int)std::min<long long>(chunk, n_frames);
+    cp.first = std::min(cp.max, 2 * cp.wave);
+    return cp;
 }
 
 // Host-pointer entry point: frames are cut into chunks that ping-pong over two streams so the
@@ -781,7 +799,8 @@ extern "C" int qldpc_decode(qldpc_decoder *dec, const void *llr, const uint32_t 
     const size_t esz = dtype_size(d->cfg.dtype);
     const size_t frame_in = (size_t)c.n * esz;
     // chunk: ~64 MiB of LLRs, at least one wave of the persistent grid
-    const int chunk = pick_chunk(d, frame_in, 128u << 20, n_frames);
+    const ChunkPlan plan = pick_chunk(d, frame_in, 320u << 20, n_frames);
+    const int chunk = plan.max;
     // the scratch of the gather path is shared: those configurations run on one lane only
     const bool shared_scratch = !((d->kernel_family == KF_LAYERED_I8 || d->kernel_family == KF_LAYERED_I8S) && !posterior &&
                                   (d->cfg.out_mode == QLDPC_OUT_ALL || d->info_is_prefix));
@@ -795,9 +814,9 @@ extern "C" int qldpc_decode(qldpc_decoder *dec, const void *llr, const uint32_t 
         if (posterior && (rc = ln.post.ensure((size_t)chunk * c.n * 4))) return rc;
     }
     int idx = 0;
-    for (int f0 = 0; f0 < n_frames; f0 += chunk, ++idx) {
+    for (int f0 = 0, nf = 0; f0 < n_frames; f0 += nf, ++idx) {
         Lane &ln = d->lanes.lane[shared_scratch ? 0 : (idx & 1)];
-        const int nf = std::min(chunk, n_frames - f0);
+        nf = std::min(plan.at(idx), n_frames - f0);
         QLDPC_CUDA(cudaMemcpyAsync(ln.in.p, (const char *)llr + (size_t)f0 * frame_in, (size_t)nf * frame_in,
                                    cudaMemcpyHostToDevice, ln.st));
         if (syndrome)
@@ -923,7 +942,8 @@ extern "C" int qldpc_decode_bits(qldpc_decoder *dec, const uint32_t *bits, const
     QLDPC_CUDA(cudaSetDevice(d->cfg.device));
     const size_t esz = dtype_size(d->cfg.dtype);
     const size_t frame_llr = (size_t)c.n * esz;
-    const int chunk = pick_chunk(d, frame_llr, 128u << 20, n_frames);
+    const ChunkPlan plan = pick_chunk(d, frame_llr, 320u << 20, n_frames);
+    const int chunk = plan.max;
     const bool shared_scratch = !((d->kernel_family == KF_LAYERED_I8 || d->kernel_family == KF_LAYERED_I8S) && (d->cfg.out_mode == QLDPC_OUT_ALL || d->info_is_prefix));
     int rc = QLDPC_OK;
     Lane &l0 = d->lanes.lane[0];
@@ -948,9 +968,9 @@ extern "C" int qldpc_decode_bits(qldpc_decoder *dec, const uint32_t *bits, const
         if (syndrome && (rc = ln.syn.ensure((size_t)chunk * d->syn_words))) return rc;
     }
     int idx = 0;
-    for (int f0 = 0; f0 < n_frames; f0 += chunk, ++idx) {
+    for (int f0 = 0, nf = 0; f0 < n_frames; f0 += nf, ++idx) {
         Lane &ln = d->lanes.lane[shared_scratch ? 0 : (idx & 1)];
-        const int nf = std::min(chunk, n_frames - f0);
+        nf = std::min(plan.at(idx), n_frames - f0);
         QLDPC_CUDA(cudaMemcpyAsync(ln.bits.p, bits + (size_t)f0 * d->cw_words, (size_t)nf * d->cw_words * 4,
                                    cudaMemcpyHostToDevice, ln.st));
         if (syndrome)

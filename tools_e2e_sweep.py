@@ -1,6 +1,6 @@
 """e2e chunk-size sweep (run on the GPU box): python tools_e2e_sweep.py"""
 import importlib, os, subprocess, sys, json
-for ch in (2368, 4736, 5328, 8288, 11840, 16576, 32560):
+for ch in (1480, 2960, 4440, 5920, 8880, 11840, 16280, 32560):
     env = dict(os.environ, QLDPC_CHUNK_FRAMES=str(ch))
     p = subprocess.run([sys.executable, "bench.py", "--steps", "4", "--warmup", "2", "--no-cpu"], env=env, capture_output=True, text=True)
     try:

@@ -294,10 +294,17 @@ bool plan_layered_i8s(qldpc_decoder *d)
     geo.slot_bytes[0] = geo.off_mbar[0] + 32;
     geo.slot_bytes[1] = geo.off_mbar[1] + 32;
     const int avail = d->max_smem_optin - geo.tab_bytes - 16;
+    const bool want_stg = !std::getenv("QLDPC_LI8_NOSTAGE");
     for (int k = 0; k < 2; ++k) {
         int slots = std::min(std::min(avail / geo.slot_bytes[k], layered_i8s_max_threads() / W), 15);
         if (const char *cap = std::getenv("QLDPC_LI8_SLOTS")) slots = std::min(slots, std::max(1, std::atoi(cap)));   // experiments
         geo.slots[k] = slots;
+        // frame-prefetch staging buffer, if it fits without giving up a frame slot
+        const int with_stg = geo.slot_bytes[k] + L_bytes;
+        if (want_stg && slots >= 1 && avail / with_stg >= slots) {
+            geo.off_stg[k] = geo.slot_bytes[k];
+            geo.slot_bytes[k] = with_stg;
+        }
     }
     if (geo.slots[1] < 1) return false;
 
@@ -638,7 +645,7 @@ static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint3
         p.slots = geo.slots[k];
         p.tab_bytes = geo.tab_bytes; p.off_rows = geo.off_rows; p.off_pcols = geo.off_pcols;
         p.slot_bytes = geo.slot_bytes[k]; p.off_ring = geo.off_ring; p.stage_bytes = geo.stage_bytes;
-        p.off_ext = geo.off_ext; p.off_hd = geo.off_hd; p.off_syn = geo.off_syn; p.off_mbar = geo.off_mbar[k];
+        p.off_ext = geo.off_ext; p.off_hd = geo.off_hd; p.off_syn = geo.off_syn; p.off_mbar = geo.off_mbar[k]; p.off_stg = geo.off_stg[k];
         p.rg_u4 = geo.rg_u4;
         const int grid = std::min(d->sm_count, (n_frames + p.slots - 1) / p.slots);
         const size_t lane_u4 = (size_t)d->sm_count * std::max(geo.slots[0], geo.slots[1]) * geo.rg_u4;

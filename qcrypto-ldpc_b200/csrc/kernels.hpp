@@ -64,6 +64,7 @@ struct LayeredI8sParams {
     int slots;
     int tab_bytes, off_rows, off_pcols;
     int slot_bytes, off_ring, stage_bytes, off_ext, off_hd, off_syn, off_mbar;
+    int off_stg;              // staging buffer of the next frame's core LLRs (n_pack * Z bytes), -1: none
     int rg_u4;                // uint4 per frame slot in the scratch
 };
 int launch_layered_i8s(const LayeredI8sParams &p, int grid, int smem_bytes, cudaStream_t st);

@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
 
     char *slot = smem + p.tab_bytes + 16 + g * p.slot_bytes;
     const u32 slot_saddr = (u32)__cvta_generic_to_shared(slot);
-    const u32 mb_full = slot_saddr + p.off_mbar, mb_bel = mb_full + 16;   // full[0], full[1] (8 bytes each), bel
+    const u32 mb_full = slot_saddr + p.off_mbar, mb_bel = mb_full + 16, mb_stg = mb_full + 24;   // full[0], full[1], bel, stg
     {   // shared tables (all slots) + one block of biased zero messages; mbarriers of this group
         const int tid = g * W + i, nthreads = W * blockDim.y;
         const uint4 *src = reinterpret_cast<const uint4 *>(p.tab);
@@ -480,6 +480,7 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
             mbar_init(mb_full, 1);
             mbar_init(mb_full + 8, 1);
             mbar_init(mb_bel, (u32)W);
+            mbar_init(mb_stg, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
@@ -534,8 +535,21 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
     // All frame groups of the CTA run their iterations in step (one CTA-wide barrier per iteration): every warp then
     // executes the same block-row code at about the same time, and the large unrolled code is fetched once per SM
     // instead of once per group (without it 37 % of the issue slots were lost to instruction-cache misses).
+    // Frame prefetch (when the slot has room for it, p.off_stg >= 0): the raw LLR bytes of the core columns of the slot's
+    // NEXT frame are bulk-copied into a staging buffer while the current frame is decoded, so that the frame switch --
+    // which every other group of the CTA waits for at the iteration barrier -- is a shared-memory transpose instead of
+    // two rounds of global-load latency.
+    const bool use_stg = p.off_stg >= 0;
+    auto stage_frame = [&](int fr) {   // elected thread only
+        const int8_t *fsrc = p.llr + (size_t)fr * p.N;
+        mbar_arrive_tx(mb_stg, (u32)(p.n_pack * Z));
+        for (int c = 0; c < p.n_pack; ++c) bulk_g2s(slot_saddr + p.off_stg + c * Z, fsrc + pcols[c].llr_off, (u32)Z, mb_stg);
+    };
+    u32 sp = 0;   // parity of the staging barrier
+
     int f = blockIdx.x * p.slots + g;
     const int fstride = gridDim.x * p.slots;
+    if (use_stg && i == 0 && f < p.F) stage_frame(f);
     const int nthreads_cta = W * blockDim.y;
     bool active = false, need_load = true, conv = false;
     int it = 0;
@@ -558,6 +572,20 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
         }
         // ---- load: int8 LLRs of the core columns -> interleaved biased belief words
         // 4 aligned 32-bit loads (one per quarter of the column) -> 4x4 byte transpose -> one 128-bit store
+        if (use_stg) {
+            mbar_wait(mb_stg, sp);
+            sp ^= 1u;
+            const char *stg = slot + p.off_stg;
+#pragma unroll kLoadUnroll
+            for (int c = lc; c < p.n_pack; c += 4) {
+                const u32 *q = reinterpret_cast<const u32 *>(stg + c * Z) + lj;
+                u32 in[4], out[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) in[k] = q[k * wq4] ^ 0x80808080u;
+                transpose4x4(in, out);
+                *reinterpret_cast<uint4 *>(Lw + c * W + 4 * lj) = make_uint4(out[0], out[1], out[2], out[3]);
+            }
+        } else {
 #pragma unroll kLoadUnroll
         for (int c = lc; c < p.n_pack; c += 4) {
             const u32 *q = reinterpret_cast<const u32 *>(src + pcols[c].llr_off) + lj;
@@ -567,11 +595,18 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
             transpose4x4(in, out);
             *reinterpret_cast<uint4 *>(Lw + c * W + 4 * lj) = make_uint4(out[0], out[1], out[2], out[3]);
         }
+        }
         if (has_syn) {   // syndrome rows, Z-bit little-endian vectors (row r, lane l -> bit l)
             const u32 *sf = p.syn + (size_t)f * p.syn_words;
             for (int r = rs; r < R; r += 8) synl[r * ZW32 + w] = __brev(__ldg(sf + r * ZW32 + w));
         }
         QL_BEL_ARRIVE();
+        if (use_stg) {
+#if QL_S_BELMBAR
+            bar_sync(bar_id, W);   // every thread has read the staging buffer
+#endif
+            if (i == 0 && f + fstride < p.F) stage_frame(f + fstride);
+        }
         it = 0;
         conv = false;
         }

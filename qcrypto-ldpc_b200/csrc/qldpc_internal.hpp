@@ -76,7 +76,7 @@ struct Li8sCol {         // 8 bytes: a core block column
 struct Li8sGeo {         // launch geometry of the streamed kernel; index 0: no syndrome input, 1: with syndrome rows
     int tab_bytes = 0, off_rows = 0, off_pcols = 0, n_pack = 0;
     int rg_u4 = 0, stage_bytes = 0, off_ring = 0, off_ext = 0, off_hd = 0, off_syn = 0;
-    int slot_bytes[2] = {0, 0}, slots[2] = {0, 0}, off_mbar[2] = {0, 0};
+    int slot_bytes[2] = {0, 0}, slots[2] = {0, 0}, off_mbar[2] = {0, 0}, off_stg[2] = {-1, -1};
 };
 // generic QC tables (syndrome phase of the int8 kernel, generic layered kernel)
 struct QcEdgeAux {       // 8 bytes

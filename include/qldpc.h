@@ -193,6 +193,31 @@ typedef struct qldpc_stats {
 int qldpc_get_stats(qldpc_decoder *dec, qldpc_stats *out);   /* synchronises the decoder's device */
 int qldpc_reset_stats(qldpc_decoder *dec);
 
+/* ---- after reconciliation: confirmation CRC and privacy amplification ---------------
+ *
+ * qldpc_privacy_amplify replaces the loop of errorcorrection/subcomponents/priv_amp.c:213-218 (privAmp_doPrivAmp) and
+ * its PRNG, errorcorrection/subcomponents/rnd.c:118-127 (rnd_getPrngValue2_32, feedback 0xe0000200, rnd.h:46), bit for
+ * bit: final key bit i = parity( XOR_j key[j] & prng_word[i*numwords + j] ), bits beyond workbits of the last key word
+ * cleared first (priv_amp.c:189-191), final bits MSB-first (helpers.h:66-68).  A call serves n_blocks process blocks:
+ *   key          n_blocks * key_stride_words words (pb->mainBufPtr of each block, MSB-first)
+ *   workbits     n_blocks values (pb->workbits), each <= 32 * key_stride_words
+ *   final_bits   n_blocks values (pb->finalKeyBits, computed by the caller from leakage / sneakloss as priv_amp.c:166 does)
+ *   seeds        n_blocks PRNG seeds (the seed of EC packet subtype 8, priv_amp.c:45,54,76)
+ *   final_key    n_blocks * out_stride_words words, out_stride_words >= ceil(max final_bits / 32); words past a block's
+ *                ceil(final_bits/32) are left untouched
+ * HOST pointers; `device` is the CUDA device ordinal.  There is no CPU fallback (QLDPC_ERR_NO_DEVICE).
+ *
+ * qldpc_crc32_frames: CRC-32 (IEEE 802.3 / zlib) of every frame of packed bits, over the frame's bytes in transmission
+ * order (MSB-first words = big-endian bytes) -- the confirmation step the reference planned but never wrote
+ * (errorcorrection/README_LDPC.md:784-788, README_AFF3CT.md:94): both sides compare the CRCs of their corrected frames.
+ *   bits  n_frames * stride_words words; the first words_per_frame words of each frame are hashed.
+ */
+int qldpc_privacy_amplify(int32_t device, const uint32_t *key, int32_t key_stride_words, const int32_t *workbits,
+                          const int32_t *final_bits, const uint32_t *seeds, int32_t n_blocks, uint32_t *final_key,
+                          int32_t out_stride_words);
+int qldpc_crc32_frames(int32_t device, const uint32_t *bits, int32_t n_frames, int32_t words_per_frame, int32_t stride_words,
+                       uint32_t *crc_out);
+
 /* name of the kernel family the decoder dispatches to (for logs / tests) */
 const char *qldpc_decoder_kernel_name(const qldpc_decoder *dec);
 const char *qldpc_strerror(int code);

@@ -66,8 +66,46 @@ def lib():
         L.ora_batch_flooding_f32.argtypes = [vp, vp, vp, ci, ci, ci, ci, cf, cf, vp, vp, vp, vp, ci]
         L.ora_normalize_eighths.restype = ci
         L.ora_normalize_eighths.argtypes = [ci, ci]
+        L.ora_privacy_amplify.restype = None
+        L.ora_privacy_amplify.argtypes = [vp, ci, ci, C.c_uint32, vp, vp]
+        L.ora_prng32.restype = C.c_uint32
+        L.ora_prng32.argtypes = [vp]
+        L.ora_crc32_words.restype = C.c_uint32
+        L.ora_crc32_words.argtypes = [vp, ci]
         _lib = L
     return _lib
+
+
+_REF_RND = os.path.join(_HERE, "_ref", "librnd_ref.so")
+
+
+def ref_rnd():
+    """the reference's own PRNG (errorcorrection/subcomponents/rnd.c compiled by `make -C oracle ref`), or None when
+    oracle/_ref has not been built (it is built in the container that has /root/reference and travels to the GPU box)"""
+    if not os.path.exists(_REF_RND):
+        return None
+    R = C.CDLL(_REF_RND)
+    R.rnd_getPrngValue2_32.restype = C.c_uint32
+    R.rnd_getPrngValue2_32.argtypes = [C.c_void_p]
+    return R
+
+
+def privacy_amplify(key_words, workbits, final_bits, seed, use_ref_prng=False):
+    """priv_amp.c:186-218 on one block; use_ref_prng=True draws the PRNG words from the reference's rnd.c (oracle/_ref)"""
+    key = np.ascontiguousarray(key_words, dtype=np.uint32)
+    out = np.zeros(max(1, (final_bits + 31) // 32), dtype=np.uint32)
+    fn = None
+    if use_ref_prng:
+        R = ref_rnd()
+        assert R is not None, "oracle/_ref/librnd_ref.so is missing (make -C oracle ref)"
+        fn = C.cast(R.rnd_getPrngValue2_32, C.c_void_p)
+    lib().ora_privacy_amplify(_p(key), int(workbits), int(final_bits), int(seed) & 0xffffffff, _p(out), fn)
+    return out[:(final_bits + 31) // 32]
+
+
+def crc32_words(words):
+    w = np.ascontiguousarray(words, dtype=np.uint32)
+    return int(lib().ora_crc32_words(_p(w), int(w.size)))
 
 
 def _p(a):

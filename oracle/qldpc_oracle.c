@@ -731,3 +731,42 @@ int ora_batch_flooding_f32(const ora_code *c, const float *llr, const uint8_t *s
     j.post = post; j.hard = hard; j.iters = iters; j.ok = ok;
     return run_batch(&j, n_threads);
 }
+
+/* ---- privacy amplification (errorcorrection/subcomponents/priv_amp.c:186-218, rnd.c:118-127) ------------------- */
+unsigned int ora_prng32(unsigned int *state)
+{
+    for (int k0 = 32; k0; k0--) {                                   /* rnd.c:120-124 */
+        const int b = __builtin_parity(*state & 0xe0000200u);       /* PRNG_FEEDBACK, rnd.h:46; calcParity, rnd.h:49 */
+        *state <<= 1;
+        *state += (unsigned int)b;
+    }
+    return *state;
+}
+
+void ora_privacy_amplify(const uint32_t *key, int workbits, int final_bits, uint32_t seed, uint32_t *out, ora_prng32_fn prng32)
+{
+    const int numwords = (workbits + 31) / 32;                      /* wordCount, helpers.h:67 */
+    uint32_t *k = (uint32_t *)malloc((size_t)(numwords > 0 ? numwords : 1) * sizeof(uint32_t));
+    unsigned int state = seed;                                      /* priv_amp.c:187 */
+    if (!prng32) prng32 = ora_prng32;
+    for (int j = 0; j < numwords; ++j) k[j] = key[j];
+    if ((workbits & 31) != 0) k[numwords - 1] &= 0xffffffffu << (32 - (workbits & 31));   /* :189-191 */
+    for (int j = 0; j < (final_bits + 31) / 32; ++j) out[j] = 0;    /* :207 */
+    for (int i = 0; i < final_bits; i++) {                          /* :213-218 */
+        uint32_t m = 0;
+        for (int j = 0; j < numwords; j++) m ^= k[j] & prng32(&state);
+        if (__builtin_parity(m)) out[i / 32] |= 1u << (31 - (i & 31));   /* uint32AllZeroExceptAtN, helpers.h:69 */
+    }
+    free(k);
+}
+
+uint32_t ora_crc32_words(const uint32_t *words, int n_words)
+{
+    uint32_t c = 0xffffffffu;
+    for (int w = 0; w < n_words; ++w)
+        for (int byte = 3; byte >= 0; --byte) {
+            c ^= (words[w] >> (8 * byte)) & 0xffu;
+            for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xedb88320u ^ (c >> 1) : c >> 1;
+        }
+    return c ^ 0xffffffffu;
+}

@@ -112,6 +112,17 @@ int ora_batch_flooding_f32(const ora_code *c, const float *llr, const uint8_t *s
                            int rule, int n_ite, int early_stop, float norm, float offset,
                            float *post, uint8_t *hard, int *iters, uint8_t *ok, int n_threads);
 
+/* Privacy amplification, restating errorcorrection/subcomponents/priv_amp.c:186-218 with the PRNG of
+ * errorcorrection/subcomponents/rnd.c:118-127 (rnd_getPrngValue2_32: 32 steps of state <<= 1, state += parity(state &
+ * 0xe0000200), rnd.h:46).  key: ceil(workbits/32) words MSB-first (the last word is masked as priv_amp.c:189-191 does, on a
+ * copy); out: ceil(final_bits/32) words, zeroed first (priv_amp.c:207).  `prng32` = NULL uses the restatement below; tests
+ * pass the reference's own rnd_getPrngValue2_32 from oracle/_ref/librnd_ref.so to pin it. */
+typedef unsigned int (*ora_prng32_fn)(unsigned int *state);
+unsigned int ora_prng32(unsigned int *state);
+void ora_privacy_amplify(const uint32_t *key, int workbits, int final_bits, uint32_t seed, uint32_t *out, ora_prng32_fn prng32);
+/* CRC-32 (IEEE 802.3 / zlib), bit-serial, over words taken MSB-first (big-endian bytes) */
+uint32_t ora_crc32_words(const uint32_t *words, int n_words);
+
 /* integer normalisation by k/8 with shifts (AFF3CT Update_rule_NMS for integer Q) */
 int ora_normalize_eighths(int v, int eighths);
 

@@ -36,7 +36,7 @@ ABI_SYMBOLS = [
     "qldpc_decode", "qldpc_decode_device", "qldpc_syndrome", "qldpc_syndrome_device",
     "qldpc_make_llr", "qldpc_make_llr_device", "qldpc_decode_bits", "qldpc_decode_bits_device", "qldpc_encode_nr", "qldpc_encode_nr_device",
     "qldpc_get_stats", "qldpc_reset_stats", "qldpc_decoder_kernel_name", "qldpc_strerror",
-    "qldpc_last_cuda_error", "qldpc_version",
+    "qldpc_last_cuda_error", "qldpc_version", "qldpc_privacy_amplify", "qldpc_crc32_frames",
 ]
 
 
@@ -111,6 +111,8 @@ def lib():
         L.qldpc_strerror.restype = C.c_char_p
         L.qldpc_last_cuda_error.restype = C.c_char_p
         L.qldpc_version.restype = C.c_int
+        L.qldpc_privacy_amplify.argtypes = [i32, vp, i32, vp, vp, vp, i32, vp, i32]
+        L.qldpc_crc32_frames.argtypes = [i32, vp, i32, i32, i32, vp]
         _lib = L
     return _lib
 
@@ -308,3 +310,27 @@ def unpack_bits(words, n):
     words = np.ascontiguousarray(words, dtype=np.uint32)
     by = words.astype(">u4").view(np.uint8)
     return np.unpackbits(by, axis=-1, bitorder="big")[..., :n]
+
+
+def privacy_amplify(keys, workbits, final_bits, seeds, device=0):
+    """qldpc_privacy_amplify on a batch of blocks: keys [B, words] uint32 (MSB-first), per-block workbits / final_bits / seeds.
+    Returns [B, ceil(max(final_bits)/32)] uint32 (words beyond a block's own length are zero)."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint32)
+    B = keys.shape[0]
+    wb = np.ascontiguousarray(workbits, dtype=np.int32)
+    fb = np.ascontiguousarray(final_bits, dtype=np.int32)
+    sd = np.ascontiguousarray(seeds, dtype=np.uint32)
+    ow = max(1, (int(fb.max()) + 31) // 32) if B else 1
+    out = np.zeros((B, ow), dtype=np.uint32)
+    _chk(lib().qldpc_privacy_amplify(device, _np_ptr(keys), keys.shape[1], _np_ptr(wb), _np_ptr(fb), _np_ptr(sd), B, _np_ptr(out), ow),
+         "qldpc_privacy_amplify")
+    return out
+
+
+def crc32_frames(bits_packed, words_per_frame=None, device=0):
+    bits = np.ascontiguousarray(bits_packed, dtype=np.uint32)
+    F, stride = bits.shape
+    wpf = stride if words_per_frame is None else words_per_frame
+    out = np.zeros(F, dtype=np.uint32)
+    _chk(lib().qldpc_crc32_frames(device, _np_ptr(bits), F, wpf, stride, _np_ptr(out)), "qldpc_crc32_frames")
+    return out

@@ -1079,3 +1079,72 @@ extern "C" const char *qldpc_strerror(int code)
 
 extern "C" const char *qldpc_last_cuda_error(void) { return CudaCheck::last.c_str(); }
 extern "C" int qldpc_version(void) { return QLDPC_VERSION; }
+
+// ----------------------------------------------------------------------- after reconciliation
+
+static int select_sm100_device(int device)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return QLDPC_ERR_NO_DEVICE; }
+    if (device < 0 || device >= ndev) return QLDPC_ERR_ARG;
+    QLDPC_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    QLDPC_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return QLDPC_ERR_NO_DEVICE;
+    return QLDPC_OK;
+}
+
+extern "C" int qldpc_privacy_amplify(int32_t device, const uint32_t *key, int32_t key_stride_words, const int32_t *workbits,
+                                     const int32_t *final_bits, const uint32_t *seeds, int32_t n_blocks, uint32_t *final_key,
+                                     int32_t out_stride_words)
+{
+    if (!key || !workbits || !final_bits || !seeds || !final_key || n_blocks < 0 || key_stride_words <= 0 || out_stride_words < 0)
+        return QLDPC_ERR_ARG;
+    if (n_blocks == 0) return QLDPC_OK;
+    int max_wb = 0, max_fb = 0;
+    for (int b = 0; b < n_blocks; ++b) {
+        if (workbits[b] < 0 || workbits[b] > 32 * key_stride_words || final_bits[b] < 0 || final_bits[b] > 32 * out_stride_words)
+            return QLDPC_ERR_ARG;
+        max_wb = std::max(max_wb, workbits[b]);
+        max_fb = std::max(max_fb, final_bits[b]);
+    }
+    if (max_wb > 32 * 50000) return QLDPC_ERR_UNSUPPORTED;   // key words of a block live in shared memory
+    int rc;
+    if ((rc = select_sm100_device(device))) return rc;
+    static thread_local int tables_on = -1;
+    if (tables_on != device) {
+        if ((rc = pa_upload_jump_tables())) return rc;
+        tables_on = device;
+    }
+    DevBuf<uint32_t> d_key, d_seed, d_out;
+    DevBuf<int32_t> d_wb, d_fb;
+    const size_t nk = (size_t)n_blocks * key_stride_words, no = (size_t)n_blocks * std::max(1, out_stride_words);
+    if ((rc = d_key.ensure(nk)) || (rc = d_seed.ensure(n_blocks)) || (rc = d_out.ensure(no)) || (rc = d_wb.ensure(n_blocks)) ||
+        (rc = d_fb.ensure(n_blocks))) return rc;
+    QLDPC_CUDA(cudaMemcpy(d_key.p, key, nk * 4, cudaMemcpyHostToDevice));
+    QLDPC_CUDA(cudaMemcpy(d_seed.p, seeds, (size_t)n_blocks * 4, cudaMemcpyHostToDevice));
+    QLDPC_CUDA(cudaMemcpy(d_wb.p, workbits, (size_t)n_blocks * 4, cudaMemcpyHostToDevice));
+    QLDPC_CUDA(cudaMemcpy(d_fb.p, final_bits, (size_t)n_blocks * 4, cudaMemcpyHostToDevice));
+    if (out_stride_words > 0) QLDPC_CUDA(cudaMemcpy(d_out.p, final_key, no * 4, cudaMemcpyHostToDevice));   // untouched words survive
+    if ((rc = launch_privacy_amplify(d_key.p, d_wb.p, d_fb.p, d_seed.p, n_blocks, key_stride_words, max_wb, max_fb, d_out.p,
+                                     out_stride_words, nullptr))) return rc;
+    QLDPC_CUDA(cudaDeviceSynchronize());
+    if (out_stride_words > 0) QLDPC_CUDA(cudaMemcpy(final_key, d_out.p, no * 4, cudaMemcpyDeviceToHost));
+    return QLDPC_OK;
+}
+
+extern "C" int qldpc_crc32_frames(int32_t device, const uint32_t *bits, int32_t n_frames, int32_t words_per_frame,
+                                  int32_t stride_words, uint32_t *crc_out)
+{
+    if (!bits || !crc_out || n_frames < 0 || words_per_frame < 0 || stride_words < words_per_frame) return QLDPC_ERR_ARG;
+    if (n_frames == 0) return QLDPC_OK;
+    int rc;
+    if ((rc = select_sm100_device(device))) return rc;
+    DevBuf<uint32_t> d_bits, d_crc;
+    if ((rc = d_bits.ensure((size_t)n_frames * stride_words)) || (rc = d_crc.ensure(n_frames))) return rc;
+    QLDPC_CUDA(cudaMemcpy(d_bits.p, bits, (size_t)n_frames * stride_words * 4, cudaMemcpyHostToDevice));
+    if ((rc = launch_crc32_frames(d_bits.p, n_frames, words_per_frame, stride_words, d_crc.p, nullptr))) return rc;
+    QLDPC_CUDA(cudaDeviceSynchronize());
+    QLDPC_CUDA(cudaMemcpy(crc_out, d_crc.p, (size_t)n_frames * 4, cudaMemcpyDeviceToHost));
+    return QLDPC_OK;
+}

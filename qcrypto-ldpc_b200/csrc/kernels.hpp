@@ -126,4 +126,12 @@ int launch_make_llr(const uint32_t *bits, const uint32_t *known, const uint32_t 
 int launch_encode_nr(const uint32_t *msg, uint32_t *cword, int F, int Z, int brows, int bcols, const int32_t *base,
                      int msg_words, int cw_words, cudaStream_t st);
 
+
+// ---- post-reconciliation (postproc.cu) -------------------------------------------------------------
+int pa_upload_jump_tables();
+int launch_privacy_amplify(const uint32_t *d_key, const int32_t *d_workbits, const int32_t *d_final_bits, const uint32_t *d_seeds,
+                           int n_blocks, int key_stride, int max_workbits, int max_final_bits, uint32_t *d_out, int out_stride,
+                           cudaStream_t st);
+int launch_crc32_frames(const uint32_t *d_bits, int n_frames, int words_per_frame, int stride_words, uint32_t *d_crc, cudaStream_t st);
+
 }  // namespace qldpc

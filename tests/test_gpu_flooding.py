@@ -170,3 +170,25 @@ def test_syndrome_and_make_llr_kernels(q, O, data_dir):
         llr = dec.make_llr(q.pack_bits(bits), 3.4761, 23.02585, q.pack_bits(known), q.pack_bits(punct))
         mag = np.where(punct == 1, 0.0, np.where(known == 1, 23.02585, 3.4761)).astype(np.float32)
         np.testing.assert_array_equal(llr, np.where(bits == 1, -mag, mag).astype(np.float32))
+
+
+def test_config1_n1944_spa_flooding_vs_oracle(q, O, data_dir):
+    """BASELINE config 1 on the GPU path: same frames as the CPU plumbing test, bit-exact bits / iterations / ok"""
+    path = "%s/wifi_n1944_r12.qc" % data_dir
+    oc = O.Code.from_qc(path)
+    code = q.Code.from_qc_file(path)
+    rng = np.random.default_rng(1944)
+    F, qb = 64, 0.03
+    x = rng.integers(0, 2, (F, oc.N)).astype(np.uint8)
+    e = (rng.random((F, oc.N)) < qb).astype(np.uint8)
+    syn = np.stack([oc.syndrome(x[f]) for f in range(F)])
+    mag = np.float32(np.log((1 - qb) / qb))
+    llr = np.where(x ^ e, -mag, mag).astype(np.float32)
+    dec = q.Decoder(code, schedule=q.SCHED_FLOODING, rule=q.RULE_SPA, dtype=q.DTYPE_F32, max_iter=20, early_stop=True,
+                    out_mode=q.OUT_ALL)
+    out, ok, iters, post = dec.decode(llr, q.pack_bits(syn), want_posterior=True)
+    hard, opost, oit, ook, _ = oc.batch_flooding_f32(llr, syn, rule=O.RULE_SPA, n_ite=20, early_stop=True)
+    assert (q.unpack_bits(out, oc.N) == hard).all() and (hard == x).all()
+    assert (iters == oit).all() and (ok == ook).all() and ok.all()
+    np.testing.assert_allclose(post, opost, rtol=RTOL, atol=1e-4)
+    dec.close()

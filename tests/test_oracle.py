@@ -239,3 +239,21 @@ def test_pack_bits_msb_first(O):
     w = O.pack_bits_msb(bits)
     assert w.tolist() == [0x80000000, 0x40000000]                         # helpers.h:68 uint32AllZeroExceptAtN
     assert (O.unpack_bits_msb(w, 40) == bits).all()
+
+
+def test_config1_n1944_spa_flooding_syndrome_decoding_on_cpu(O, data_dir):
+    """BASELINE config 1 (plumbing, no GPU): rate-1/2 N=1944 code, float SPA flooding, 20 iterations, BSC QBER 3 %,
+    syndrome decoding as the ldpc_examples chain does it (LLR = +-ln((1-q)/q), early stop on the syndrome)."""
+    oc = O.Code.from_qc("%s/wifi_n1944_r12.qc" % data_dir)
+    assert (oc.N, oc.M) == (1944, 972)
+    rng = np.random.default_rng(1944)
+    F, q = 64, 0.03
+    x = rng.integers(0, 2, (F, oc.N)).astype(np.uint8)
+    e = (rng.random((F, oc.N)) < q).astype(np.uint8)
+    syn = np.stack([oc.syndrome(x[f]) for f in range(F)])
+    mag = np.float32(np.log((1 - q) / q))
+    llr = np.where(x ^ e, -mag, mag).astype(np.float32)
+    hard, post, iters, ok, _ = oc.batch_flooding_f32(llr, syn, rule=O.RULE_SPA, n_ite=20, early_stop=True)
+    assert ok.all() and (hard == x).all()
+    assert 2 <= iters.mean() <= 8 and iters.max() <= 20
+    assert (np.sign(post) == np.where(x, -1, 1)).all()

@@ -2,7 +2,7 @@
 // (BG1/BG2 lifting sizes 128, 256, 384).  Same arithmetic as layered_i8.cu -- ML/BPSK_nrldpc_sim_FP.m:35-94
 // generalised by syndrome input, early stop and the shift-normalised rule; bit-exact with
 // oracle/qldpc_oracle.c:ora_decode_layered_fixed -- but a different placement of the state, chosen so that
-// SIX frames (BG1 Z=384) are in flight per SM instead of four:
+// FIVE frames (BG1 Z=384) are in flight per SM, 15 warps at 128 registers:
 //   shared memory, per frame slot:
 //     beliefs of the CORE block columns only (columns that are not weight-1/shift-0 extension columns),
 //       word i of a column = lanes {i, i+W, i+2W, i+3W} as biased bytes (L+128), W = Z/4;
@@ -10,14 +10,18 @@
 //     a 2-deep ring of raw channel LLRs of the extension column of the row being processed / staged
 //       (an extension column is read by exactly one row and never rewritten: its belief minus its message is
 //       the channel LLR for ever, only the SIGN of its a-posteriori value is observable);
-//     hard-decision bit vectors, each stored twice back to back so that a rotated window never wraps.
+//     hard-decision bit vectors, each stored twice back to back so that a rotated window never wraps;
+//     a staging buffer into which the core LLRs of the slot's NEXT frame are bulk-copied during the decode.
 //   registers: per-edge state of the row being processed.
-// Per edge and thread (4 check lanes = 2 half2 pairs) the instruction budget is ~36:
-//   the wrap decision (lane i+r >= W) selects between two precomputed table entries with a pair of PREDICATED
-//   128-bit shared loads (no SEL chain), clips run on the FMA pipe (relu forms) so that the half-rate ALU pipe
-//   only carries PRMT / min-max / logic.
+// Per edge and thread (4 check lanes = 2 half2 pairs) the instruction budget is ~43:
+//   the wrap decision (lane i+r >= W) selects between two precomputed 16-byte table entries (address select + one
+//   128-bit shared load, no SEL chain); clips and the k/8 normalisation run on the FMA pipe (relu / multiply forms)
+//   so that the half-rate ALU pipe only carries PRMT / min-max / logic.
+// All frame groups of a CTA start every iteration together, so that the 255 KB of unrolled row code are fetched once
+// per SM (see the comment at the iteration barrier).
 // Early termination: hard decisions are balloted into Z-bit vectors; the syndrome is evaluated word-wise
 // (funnel shift + XOR) for the first 8 block rows, and for the remaining rows only if those were all zero.
+// The QL_S_* switches below are the measured alternatives (profiles/r1_experiments.md); the defaults are the best set.
 #include <cuda_fp16.h>
 
 #include "kernels.hpp"

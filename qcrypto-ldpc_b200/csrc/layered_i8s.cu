@@ -59,6 +59,9 @@
 #ifndef QL_S_FIRSTSPEC
 #define QL_S_FIRSTSPEC 0             // separate code for the first iteration of a frame: -8 % (groups at different iterations stop sharing code)
 #endif
+#ifndef QL_S_SMSP_LOCAL
+#define QL_S_SMSP_LOCAL 0            // warps of a frame group on one scheduler: 50.2 vs 51.6 Gbit/s spread over the schedulers (off)
+#endif
 #ifndef QL_S_FMACLIP8
 #define QL_S_FMACLIP8 0              // belief clip (upper bound) on the FMA pipe
 #endif
@@ -467,7 +470,28 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
     const int W = WT ? WT : p.W;
     const int Z = 4 * W, ZW32 = W >> 3, wq = W >> 5, wq4 = W >> 2;
     const int R = p.brows;
-    const int g = threadIdx.y, i = threadIdx.x;          // block = (W, slots); W is a multiple of 32
+    // Thread -> (frame group g, lane-word i).  The hardware assigns warp w to scheduler w % 4.  Default: group = threadIdx.y,
+    // its warps land on different schedulers and run in parallel.  QL_S_SMSP_LOCAL puts the warps of a group on ONE
+    // scheduler (they reach the row barrier together, but a row then takes longer): measured slower.
+    int g, i;
+    {
+        const int tid_lin = threadIdx.y * W + threadIdx.x, wl = tid_lin >> 5, wpg = W >> 5, S = blockDim.y;
+#if QL_S_SMSP_LOCAL
+        const int quad = 4 * wpg;                           // warps of four groups
+        if (wl < (S / 4) * quad) {
+            const int b = wl / quad, r = wl - b * quad;
+            g = 4 * b + (r & 3);
+            i = (r >> 2) * 32 + (tid_lin & 31);
+        } else {
+            const int r = wl - (S / 4) * quad;
+            g = 4 * (S / 4) + r / wpg;
+            i = (r % wpg) * 32 + (tid_lin & 31);
+        }
+#else
+        (void)wl; (void)wpg; (void)S;
+        g = threadIdx.y; i = threadIdx.x;
+#endif
+    }
     const int lane = i & 31, wis = i >> 5;
     const int bar_id = 1 + g;
 

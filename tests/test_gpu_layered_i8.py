@@ -90,6 +90,14 @@ def test_other_lifting_sizes(q, O, data_dir, name, mag):
     _run_case(q, O, data_dir, name, 20, 0.04, mag, "syndrome", q.RULE_OMS, 10, True, offset=1, seed=3)
 
 
+@pytest.mark.parametrize("name", ["NR_2_1_384.qc", "NR_1_0_128.qc", "NR_2_0_256.qc"])
+def test_streamed_kernel_other_base_graphs(q, O, data_dir, name):
+    """the v5 streamed kernel (Z % 128 == 0) on BG2 and on the other lifting sizes: one, two and three warps per frame"""
+    _run_case(q, O, data_dir, name, 40, 0.03, 14, "parity", q.RULE_NMS, 10, True, seed=31)
+    _run_case(q, O, data_dir, name, 24, 0.05, 12, "syndrome", q.RULE_OMS, 8, True, offset=2, seed=32)
+    _run_case(q, O, data_dir, name, 12, 0, 0, "syndrome", q.RULE_NMS, 3, False, k8=7, random_llr=True, seed=33)
+
+
 def test_wifi_n1944(q, O, data_dir):
     # rate-1/2 N=1944 (Z=81 is not a multiple of 4 -> generic kernel)
     path = "%s/wifi_n1944_r12.qc" % data_dir

@@ -58,6 +58,21 @@ int build_qc_tables(qldpc_decoder *d)
     }
     if (int r = d->d_qc_aux.upload(aux)) return r;
     if (int r = d->d_qc_layers.upload(layers)) return r;
+    // column view for the QC flooding kernel: edges of a block column in ascending block-row order
+    std::vector<int32_t> col_ptr(c.base_cols + 1, 0);
+    std::vector<int2> col_edges;
+    for (int col = 0; col < c.base_cols; ++col) {
+        for (int r = 0, e = 0; r < c.base_rows; ++r)
+            for (int cc = 0; cc < c.base_cols; ++cc) {
+                const int s = c.base[r * c.base_cols + cc];
+                if (s < 0) continue;
+                if (cc == col) col_edges.push_back(make_int2(e, s % c.z));
+                ++e;
+            }
+        col_ptr[col + 1] = (int32_t)col_edges.size();
+    }
+    if (int r = d->d_qc_col_ptr.upload(col_ptr)) return r;
+    if (int r = d->d_qc_col_edges.upload(col_edges)) return r;
     return QLDPC_OK;
 }
 
@@ -549,6 +564,11 @@ extern "C" int qldpc_decoder_create(const qldpc_code *code, const qldpc_decoder_
     } else {
         d->kernel_family = KF_FLOODING;
         d->kernel_name = "flooding_csr";
+        // quasi-cyclic codes, float min-sum: the circulant-aware kernel (lanes on consecutive threads, no index gathers, the
+        // early-termination test fused into the check phase): 6.9 vs 6.1 Gbit/s on the N=65536 code.  SPA stays on the CSR
+        // kernel: it is bound by the double-precision tanh/atanh, and the fused test costs it one extra check phase.
+        d->flood_qc = c.z > 0 && cfg->dtype == QLDPC_DTYPE_F32 && cfg->rule != QLDPC_RULE_SPA && !std::getenv("QLDPC_FLOOD_CSR");
+        if (d->flood_qc) d->kernel_name = "flooding_qc";
         const size_t need = (size_t)(c.edges + c.n) * 4;
         d->flood_use_smem = need + 1024 <= (size_t)d->max_smem_optin;
         d->flood_smem = d->flood_use_smem ? (int)need : 0;
@@ -746,6 +766,18 @@ static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint3
         p.offset_int = d->offset_int; p.norm_eighths = d->norm_eighths;
         p.vmax = cfg.dtype == QLDPC_DTYPE_I16 ? 32767 : 127;
         p.use_smem = d->flood_use_smem;
+        if (d->flood_qc) {
+            FloodQcParams qp{};
+            qp.llr = (const float *)d_llr; qp.syn = d_syndrome; qp.allbits = allbits; qp.ok = d_ok; qp.iters = d_iters;
+            qp.posterior = (float *)d_posterior; qp.stats = d->d_stats.p;
+            qp.aux = d->d_qc_aux.p; qp.layers = d->d_qc_layers.p; qp.col_ptr = d->d_qc_col_ptr.p; qp.col_edges = d->d_qc_col_edges.p;
+            qp.c2v = (float *)d->d_scratch.p; qp.post = (float *)d->d_scratch2.p;
+            qp.F = n_frames; qp.Z = c.z; qp.nnz = c.edges / c.z; qp.N = c.n; qp.M = c.m;
+            qp.cw_words = d->cw_words; qp.syn_words = d->syn_words;
+            qp.max_iter = cfg.max_iter; qp.early_stop = cfg.early_stop; qp.syndrome_depth = cfg.syndrome_depth;
+            qp.rule = cfg.rule; qp.norm = cfg.norm_factor; qp.offset = cfg.offset; qp.use_smem = d->flood_use_smem;
+            if ((rc = launch_flooding_qc(qp, std::min(d->gen_grid, n_frames), std::min(d->flood_block, layered_flood_qc_threads()), d->flood_smem, st))) return rc;
+        } else
         if ((rc = launch_flooding(p, std::min(d->gen_grid, n_frames), d->flood_block, d->flood_smem, st))) return rc;
     }
     d->kernel_launches++;

@@ -115,6 +115,31 @@ struct FloodParams {
 };
 int launch_flooding(const FloodParams &p, int grid, int block, int smem_bytes, cudaStream_t st);
 
+// ---- flooding, quasi-cyclic codes, float (flooding_qc.cu) -----------------------------------------
+struct FloodQcParams {
+    const float *llr;
+    const uint32_t *syn;
+    uint32_t *allbits;
+    uint8_t *ok;
+    uint16_t *iters;
+    float *posterior;
+    DevStats *stats;
+    const QcEdgeAux *aux;      // nnz entries, row-major, columns ascending
+    const QcLayer *layers;     // brows
+    const int32_t *col_ptr;    // bcols + 1
+    const int2 *col_edges;     // per block column: (edge id, shift) in ascending block-row order
+    float *c2v;                // grid * nnz * Z (global scratch) when the messages do not fit in smem
+    float *post;               // grid * N
+    int F, Z, nnz, N, M;
+    int cw_words, syn_words;
+    int max_iter, early_stop, syndrome_depth;
+    int rule;
+    float norm, offset;
+    int use_smem;
+};
+int layered_flood_qc_threads();
+int launch_flooding_qc(const FloodQcParams &p, int grid, int block, int smem_bytes, cudaStream_t st);
+
 // ---- bit-level helpers ---------------------------------------------------------------------------
 // syndrome of packed frames; QC codes use word-wise rotate+XOR, others a CSR gather
 int launch_syndrome_csr(const uint32_t *bits, uint32_t *syn, int F, int N, int M, int cw_words, int syn_words,

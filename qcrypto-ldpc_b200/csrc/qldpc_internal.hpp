@@ -152,6 +152,9 @@ struct qldpc_decoder {
     qldpc::DevBuf<uint16_t> d_li8_pack_cols;
     qldpc::DevBuf<qldpc::QcEdgeAux> d_qc_aux;
     qldpc::DevBuf<qldpc::QcLayer> d_qc_layers;
+    qldpc::DevBuf<int32_t> d_qc_col_ptr;          // QC flooding: per block column, its edges in ascending block-row order
+    qldpc::DevBuf<int2> d_qc_col_edges;
+    bool flood_qc = false;
     qldpc::DevBuf<int32_t> d_row_ptr, d_col_idx, d_var_ptr, d_var_edge, d_info_pos;
     qldpc::DevBuf<qldpc::DevStats> d_stats;
     // scratch (grown on demand)

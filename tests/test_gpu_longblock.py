@@ -37,7 +37,7 @@ def test_n65536_flooding_rate_adapted_vs_oracle(q, O, data_dir, rule, norm, qber
     orr = O.RULE_SPA if rule == "spa" else O.RULE_NMS
     dec = q.Decoder(code, schedule=q.SCHED_FLOODING, rule=qr, dtype=q.DTYPE_F32, max_iter=30, early_stop=True,
                     norm_factor=norm, out_mode=q.OUT_ALL)
-    assert dec.kernel_name == "flooding_csr"
+    assert dec.kernel_name == ("flooding_csr" if rule == "spa" else "flooding_qc")
     F = 3
     x, y, syn, punct, short = _frames(q, oc, F, qber, pf, sf, seed=int(qber * 1000) + 1)
     mag = float(np.log((1 - qber) / qber))

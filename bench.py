@@ -37,10 +37,10 @@ MAX_ITER = 10
 NORM = 0.75
 # figures of the committed ncu capture of the decode kernel (profiles/r1_v5_layered_i8s_ncu_summary.txt)
 MSG_SCRATCH_BYTES_PER_FRAME = 81 * 96 * 16          # 81 16-byte message blocks per thread, 96 threads (BG1 Z=384)
-NCU_DRAM_BYTES_PER_FRAME = 189e3                    # dram__bytes_read + write per frame (message scratch share held in L2: ~half)
+NCU_DRAM_BYTES_PER_FRAME = 180.5e3                   # dram__bytes_read + write per frame (message scratch share held in L2: ~half)
 NCU_TRAFFIC_SOURCE = "profiles/r1_v5_layered_i8s_ncu_summary.txt (ncu --set full, 14800 frames, scaled per frame)"
-NCU_ALU_PIPE_PCT = 57.6
-NCU_ISSUE_ACTIVE_PCT = 60.0
+NCU_ALU_PIPE_PCT = 59.9
+NCU_ISSUE_ACTIVE_PCT = 62.4
 
 
 def parse_args():

@@ -62,6 +62,9 @@
 #ifndef QL_S_SMSP_LOCAL
 #define QL_S_SMSP_LOCAL 0            // warps of a frame group on one scheduler: 50.2 vs 51.6 Gbit/s spread over the schedulers (off)
 #endif
+#ifndef QL_S_ZEROFILL
+#define QL_S_ZEROFILL 0              // first iteration reads zero messages from pre-filled ring stages instead of one shared block: 50.0 vs 50.8 (off)
+#endif
 #ifndef QL_S_FMACLIP8
 #define QL_S_FMACLIP8 0              // belief clip (upper bound) on the FMA pipe
 #endif
@@ -628,6 +631,14 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
             const u32 *sf = p.syn + (size_t)f * p.syn_words;
             for (int r = rs; r < R; r += 8) synl[r * ZW32 + w] = __brev(__ldg(sf + r * ZW32 + w));
         }
+#if QL_S_ZEROFILL
+        {   // the first iteration of a frame reads zero messages: both ring stages are filled with biased zeros (nothing is
+            // staged into them before the second iteration)
+            uint4 *rz = reinterpret_cast<uint4 *>(ring_i);
+            const int n16 = (2 * p.stage_bytes) >> 4;
+            for (int k = 0; k < n16; k += W) rz[k] = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+        }
+#endif
         QL_BEL_ARRIVE();
         if (use_stg) {
 #if QL_S_BELMBAR
@@ -669,7 +680,8 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
                 else
 #endif
                 dispatch_row<NK, false>(la.w >> 16, cx, Li, tab_saddr + la.x, reinterpret_cast<const int4 *>(smem + la.y),
-                                        la.w & 0xff, i, m1init, QL_S_FIRSTSPEC || it ? ysrc : zero_blk, QL_S_FIRSTSPEC || it ? W : 0,
+                                        la.w & 0xff, i, m1init, (QL_S_FIRSTSPEC || QL_S_ZEROFILL || it) ? ysrc : zero_blk,
+                                        (QL_S_FIRSTSPEC || QL_S_ZEROFILL || it) ? W : 0,
                                         reinterpret_cast<uint4 *>(rg_i + la.z), W,
                                         extb_i + stage * Z, reinterpret_cast<u32 *>(reinterpret_cast<char *>(hd) + lb.y));
                 if (r == R - 1) asm volatile("fence.proxy.async.global;" ::: "memory");

@@ -61,6 +61,7 @@ int main(int argc, char **argv)
         int done = 0, turns = 0;
         const auto t0 = std::chrono::steady_clock::now();
         std::vector<Packet> a2b, b2a;
+        if (std::getenv("QLDPC_BLIND_CORRUPT")) bob.corrupt_before_done(B[0].startEpoch);   // test: provoke a CRC mismatch
         if (int rc = alice.initiate(pa, a2b)) { std::fprintf(stderr, "initiate: error %d\n", rc); return 3; }
         while (done < n_blocks && turns < 1000) {
             ++turns;
@@ -87,7 +88,11 @@ int main(int argc, char **argv)
                 bytes_ba += p.size(); ++pk_ba;
                 KeyBlock *blk = block_of(A, h.epoch);
                 if (h.subtype == SUBTYPE_LDPC_NACK) alice.on_nack(*blk, (const char *)p.data(), a2b);
-                else if (h.subtype == SUBTYPE_LDPC_DONE) { alice.on_done(*blk, (const char *)p.data()); ++done; }
+                else if (h.subtype == SUBTYPE_LDPC_DONE) {
+                    bool confirmed = false;
+                    if (int rc = alice.on_done(*blk, (const char *)p.data(), a2b, confirmed)) { std::fprintf(stderr, "on_done: error %d\n", rc); return 3; }
+                    if (confirmed) { bob.release(h.epoch); ++done; }
+                }
             }
         }
         const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -109,10 +114,10 @@ int main(int argc, char **argv)
         std::printf("{\"blocks\": %d, \"workbits\": %d, \"qber\": %.4f, \"frames_per_block\": %d, \"initial_rows\": %d, "
                     "\"turns\": %d, \"done\": %d, \"blocks_differ\": %ld, \"leak_bits\": %ld, \"corrected_errors\": %ld, "
                     "\"efficiency\": %.4f, \"packets_a2b\": %zu, \"packets_b2a\": %zu, \"bytes_a2b\": %zu, \"bytes_b2a\": %zu, "
-                    "\"wall_s\": %.6f, \"reconciled_key_bits_per_s\": %.1f, \"round_hist\": {",
+                    "\"wall_s\": %.6f, \"reconciled_key_bits_per_s\": %.1f, \"crc_mismatches\": %d, \"round_hist\": {",
                     n_blocks, workbits, qber, (workbits + fam->K() - 1) / fam->K(), fam->initial_rows(qber), turns, done,
                     diff_blocks, leak, corrected, leak / (key_bits * h2(qber)), pk_ab, pk_ba, bytes_ab, bytes_ba, wall,
-                    key_bits / wall);
+                    key_bits / wall, alice.mismatches());
         bool first = true;
         for (auto &kv : round_hist) { std::printf("%s\"%d\": %d", first ? "" : ", ", kv.first, kv.second); first = false; }
         std::printf("}}\n");

@@ -17,8 +17,10 @@
 //   sends the next DELTA parity rows of those frames
 //   (or, after the last row, the key bits themselves)
 //                              -- subtype 11 LDPC_MORE  -->    decodes those frames again with more rows
-//                              <-- subtype 12 LDPC_DONE  --    corrected bits are in the block; both sides then call
-//                                                              privAmp_sendPrivAmpMsgAndPrivAmp (cascade_biconf.c:892)
+//                              <-- subtype 12 LDPC_DONE  --    corrected bits are in the block; carries one CRC-32 per frame
+//   compares them with the CRCs of her own frames (the confirmation step the reference planned, EC/README_LDPC.md:784-788);
+//   a frame whose CRC differs is revealed (subtype 11 with reveal=1) and Bob answers with a new LDPC_DONE;
+//   when all agree both sides call privAmp_sendPrivAmpMsgAndPrivAmp (cascade_biconf.c:892)
 // Leakage: every parity bit sent counts once in pb->leakageBits (EC/subcomponents/priv_amp.c:47,166); a revealed frame
 // counts its K key bits.  Bit vectors are MSB-first 32-bit words (EC/subcomponents/helpers.h:65-68), packets start with
 // EcPktHdr_Base (EC/definitions/packets.h:65-71), host-endian, below transferd's 10 000-byte cap per frame
@@ -71,9 +73,9 @@ struct EcPktHdr_LdpcMore {              // followed by n_frames indices, then pe
     EcPktHdr_Base base;                 // or, if reveal != 0, the frame's 22*z/32 key words
     uint32_t round, n_frames, row_from, row_to, reveal;
 };
-struct EcPktHdr_LdpcDone {
+struct EcPktHdr_LdpcDone {              // followed by `frames` CRC-32 values (qldpc_crc32_frames over the K key bits of a frame)
     EcPktHdr_Base base;
-    uint32_t rounds, frames_revealed;
+    uint32_t rounds, frames_revealed, frames;
 };
 
 // the ProcessBlock fields an LDPC handler touches (EC/definitions/processblock.h:102-129)
@@ -184,6 +186,15 @@ inline void copy_frame_key(const KeyBlock &b, int f, int kwords, uint32_t *dst)
         dst[w] = v;
     }
 }
+// CRC-32 of every frame of a block (K key bits each, the last frame zero padded), on the GPU
+inline int block_crcs(const KeyBlock &b, int K, int kwords, int device, std::vector<uint32_t> &crc)
+{
+    const int nf = frames_of(b, K);
+    std::vector<uint32_t> buf((size_t)nf * kwords);
+    for (int f = 0; f < nf; ++f) copy_frame_key(b, f, kwords, buf.data() + (size_t)f * kwords);
+    crc.assign(nf, 0u);
+    return qldpc_crc32_frames(device, buf.data(), nf, kwords, kwords, crc.data());
+}
 }  // namespace detail
 
 // ---- Alice: EC initiator --------------------------------------------------------------------------------------------
@@ -273,13 +284,45 @@ public:
         return 0;
     }
 
-    // handler for SUBTYPE_LDPC_DONE: the block is reconciled (next: privacy amplification)
-    int on_done(KeyBlock &b, const char *) { st_.erase(b.startEpoch); return 0; }
+    // handler for SUBTYPE_LDPC_DONE: compare Bob's frame CRCs with her own.  All equal: the block is reconciled (`confirmed`
+    // is set; next: privacy amplification).  Otherwise the differing frames are revealed and Bob will send a new DONE.
+    int on_done(KeyBlock &b, const char *receivebuf, std::vector<Packet> &send, bool &confirmed)
+    {
+        EcPktHdr_LdpcDone in;
+        std::memcpy(&in, receivebuf, sizeof(in));
+        const uint32_t *theirs = reinterpret_cast<const uint32_t *>(receivebuf + sizeof(in));
+        std::vector<uint32_t> mine;
+        if (detail::block_crcs(b, fam_->K(), fam_->kwords(), fam_->prm.device, mine)) return ERR_LDPC_UNSUPPORTED;
+        std::vector<uint32_t> bad;
+        for (uint32_t f = 0; f < in.frames && f < mine.size(); ++f)
+            if (mine[f] != theirs[f]) bad.push_back(f);
+        confirmed = bad.empty() && in.frames == mine.size();
+        if (confirmed) { st_.erase(b.startEpoch); return 0; }
+        mismatches_ += (int)bad.size();
+        const int kw = fam_->kwords();
+        for (size_t first = 0; first < bad.size(); first += (size_t)fam_->prm.frames_per_packet) {
+            const uint32_t n = (uint32_t)std::min<size_t>((size_t)fam_->prm.frames_per_packet, bad.size() - first);
+            EcPktHdr_LdpcMore h{};
+            h.round = in.rounds + 1; h.n_frames = n; h.row_from = h.row_to = (uint32_t)fam_->max_rows(); h.reveal = 1;
+            Packet p = detail::make_packet(SUBTYPE_LDPC_MORE, b, h, (size_t)n * 4 + (size_t)n * kw * 4);
+            std::memcpy(p.data() + sizeof(h), bad.data() + first, (size_t)n * 4);
+            for (uint32_t k = 0; k < n; ++k) {
+                std::vector<uint32_t> key(kw);
+                detail::copy_frame_key(b, (int)bad[first + k], kw, key.data());
+                std::memcpy(p.data() + sizeof(h) + (size_t)n * 4 + (size_t)k * kw * 4, key.data(), (size_t)kw * 4);
+                b.leakageBits += fam_->K();
+            }
+            send.push_back(std::move(p));
+        }
+        return 0;
+    }
+    int mismatches() const { return mismatches_; }
 
 private:
     struct State { int frames = 0; std::vector<uint32_t> parity; std::vector<int> rows_sent; };
     std::shared_ptr<CodeFamily> fam_;
     std::map<uint32_t, State> st_;
+    int mismatches_ = 0;
 };
 
 // ---- Bob: EC follower -----------------------------------------------------------------------------------------------
@@ -344,6 +387,8 @@ public:
                     store_frame(b, f, hers.data(), mine.data());
                     s.done[f] = 1;
                     ++s.revealed;
+                    if (s.finished) { s.finished = false; ++s.pending; }   // a frame revealed after a CRC mismatch: answer again
+                    touched_[&b] = 1;
                 } else {
                     std::memcpy(s.parity.data() + ((size_t)f * R + in.row_from) * zw, payload + k * per, per);
                     s.rows[f] = (int)in.row_to;
@@ -351,16 +396,22 @@ public:
                 }
             }
             s.pending -= (int)in.n_frames;
+            if (s.pending < 0) s.pending = 0;
         }
         return decode_and_answer(work, send);
     }
+
+    // the block's state is dropped when Alice has confirmed it (the caller learns that from her side of the protocol)
+    void release(uint32_t epoch) { st_.erase(epoch); }
+    // test hook: flip one key bit of the block right before the next DONE is built (exercises the CRC confirmation)
+    void corrupt_before_done(uint32_t epoch) { corrupt_.push_back(epoch); }
 
     int rounds(uint32_t epoch) const { auto it = st_.find(epoch); return it == st_.end() ? 0 : it->second.round; }
 
 private:
     struct State {
         int frames = 0, received = 0, round = 0, revealed = 0, pending = 0;
-        bool queued = false;
+        bool queued = false, finished = false;
         std::vector<uint32_t> parity;
         std::vector<int> rows;
         std::vector<char> done;
@@ -445,21 +496,28 @@ private:
                 send.push_back(std::move(p));
             }
         }
-        // a block is done when every frame is (also reached through on_more's reveal path)
-        for (auto it = st_.begin(); it != st_.end();) {
+        // a block is done when every frame is (also reached through on_more's reveal path): DONE carries one CRC per frame
+        for (auto &kv : touched_) touched[kv.first] = 1;
+        touched_.clear();
+        for (auto &kv : touched) {
+            KeyBlock *b = kv.first;
+            auto it = st_.find(b->startEpoch);
+            if (it == st_.end()) continue;
             State &s = it->second;
-            bool all = s.frames > 0 && s.pending == 0;
+            bool all = s.frames > 0 && s.pending == 0 && !s.finished;
             for (char d : s.done) all = all && d;
-            if (!all) { ++it; continue; }
-            KeyBlock tmp;
-            tmp.startEpoch = it->first;
+            if (!all) continue;
+            for (auto c = corrupt_.begin(); c != corrupt_.end(); ++c)
+                if (*c == b->startEpoch) { b->mainBufPtr[0] ^= 0x00010000u; corrupt_.erase(c); break; }
+            std::vector<uint32_t> crc;
+            if (detail::block_crcs(*b, fam_->K(), fam_->kwords(), fam_->prm.device, crc)) return ERR_LDPC_UNSUPPORTED;
             EcPktHdr_LdpcDone h{};
-            h.rounds = (uint32_t)s.round; h.frames_revealed = (uint32_t)s.revealed;
-            for (auto &kv : touched)
-                if (kv.first->startEpoch == it->first) tmp.numberOfEpochs = kv.first->numberOfEpochs;
-            send.push_back(detail::make_packet(SUBTYPE_LDPC_DONE, tmp, h, 0));
-            last_rounds_[it->first] = s.round;
-            it = st_.erase(it);
+            h.rounds = (uint32_t)s.round; h.frames_revealed = (uint32_t)s.revealed; h.frames = (uint32_t)crc.size();
+            Packet p = detail::make_packet(SUBTYPE_LDPC_DONE, *b, h, crc.size() * 4);
+            std::memcpy(p.data() + sizeof(h), crc.data(), crc.size() * 4);
+            send.push_back(std::move(p));
+            last_rounds_[b->startEpoch] = s.round;
+            s.finished = true;
         }
         return 0;
     }
@@ -470,6 +528,8 @@ public:
 private:
     std::shared_ptr<CodeFamily> fam_;
     std::map<uint32_t, State> st_;
+    std::map<KeyBlock *, char> touched_;   // blocks changed by a reveal, to be answered by the next decode_and_answer
+    std::vector<uint32_t> corrupt_;
 };
 
 }  // namespace ecd2

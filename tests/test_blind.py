@@ -144,3 +144,22 @@ def test_blind_many_blocks_throughput_line(driver, data_dir, tmp_path):
     assert res["done"] == 64 and res["blocks_differ"] == 0
     assert 1.0 < res["efficiency"] < 2.5
     assert res["reconciled_key_bits_per_s"] > 1e6
+
+
+@pytest.mark.gpu
+def test_blind_crc_confirmation_catches_a_wrong_frame(driver, q, data_dir, tmp_path):
+    """the confirmation step (one CRC-32 per frame in LDPC_DONE): a bit flipped in Bob's block after decoding is caught by
+    Alice, the frame is revealed, and the keys end up identical; the extra leakage is the K bits of that frame"""
+    n_blocks, workbits, qber = 2, 40000, 0.03
+    A, B = _write_keys(tmp_path / "k.bin", n_blocks, workbits, qber, seed=77)
+    args = [driver, "%s/NR_1_1_384.qc" % data_dir, str(tmp_path / "k.bin"), str(tmp_path / "c.bin"), "1.9", "2", "20"]
+    clean = json.loads(subprocess.run(args, capture_output=True, text=True, check=True).stdout)
+    assert clean["crc_mismatches"] == 0
+    p = subprocess.run(args, capture_output=True, text=True, env=dict(os.environ, QLDPC_BLIND_CORRUPT="1"))
+    assert p.returncode == 0, (p.stderr, p.stdout)
+    res = json.loads(p.stdout)
+    assert res["crc_mismatches"] == 1 and res["blocks_differ"] == 0 and res["done"] == n_blocks
+    assert res["leak_bits"] == clean["leak_bits"] + 22 * 384
+    words = (workbits + 31) // 32
+    got = q.unpack_bits(np.frombuffer(open(tmp_path / "c.bin", "rb").read(), dtype="<u4").reshape(n_blocks, words), words * 32)
+    assert (got[:, :workbits] == A[:, :workbits]).all()

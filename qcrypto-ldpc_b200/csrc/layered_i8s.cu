@@ -65,6 +65,9 @@
 #ifndef QL_S_ZEROFILL
 #define QL_S_ZEROFILL 0              // first iteration reads zero messages from pre-filled ring stages instead of one shared block: 50.0 vs 50.8 (off)
 #endif
+#ifndef QL_S_SPLITSTAGE
+#define QL_S_SPLITSTAGE 0            // staging duty split over two warps of the group: 49.8 vs 50.9 (off)
+#endif
 #ifndef QL_S_FMACLIP8
 #define QL_S_FMACLIP8 0              // belief clip (upper bound) on the FMA pipe
 #endif
@@ -550,6 +553,10 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
 #define QL_BEL_WAIT() do { } while (0)
 #endif
     // Stage block row `rn` (messages only when `with_msgs`) for trip `trip` -- elected thread only.
+    // Two threads of different warps share the duty, so that no single warp of the group carries all of it into the row
+    // barrier: thread 0 arms the barrier with the byte count and copies the messages, thread `ext_thread` (first lane of the
+    // second warp when there is one) copies the extension bytes.  expect_tx may be posted before or after a copy completes.
+    const int ext_thread = (QL_S_SPLITSTAGE && W > 32) ? 32 : 0;
     auto stage_row = [&](int rn, bool with_msgs, u32 trip, const int8_t *frame) {
         const int4 na = *reinterpret_cast<const int4 *>(rowsc + 32 * rn);        // e_off, thr_off, g_off, nc|nv|variant
         const int es = *reinterpret_cast<const int *>(rowsc + 32 * rn + 16);     // ext_src
@@ -557,15 +564,14 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
         const u32 mb = mb_full + 8 * st;
         const u32 msg_bytes = with_msgs ? (u32)(((na.w >> 8) & 0xff) * W * 16) : 0u;
         const u32 ext_bytes = es >= 0 ? (u32)Z : 0u;
-        if (msg_bytes + ext_bytes) mbar_arrive_tx(mb, msg_bytes + ext_bytes);
-        else mbar_arrive(mb);
-        if (msg_bytes) bulk_g2s(slot_saddr + p.off_ring + st * p.stage_bytes, rg_slot + na.z, msg_bytes, mb);
-        if (ext_bytes) bulk_g2s(slot_saddr + p.off_ext + st * Z, frame + es, ext_bytes, mb);
+        if (i == 0) {
+            if (msg_bytes + ext_bytes) mbar_arrive_tx(mb, msg_bytes + ext_bytes);
+            else mbar_arrive(mb);
+            if (msg_bytes) bulk_g2s(slot_saddr + p.off_ring + st * p.stage_bytes, rg_slot + na.z, msg_bytes, mb);
+        }
+        if (i == ext_thread && ext_bytes) bulk_g2s(slot_saddr + p.off_ext + st * Z, frame + es, ext_bytes, mb);
     };
 
-    // All frame groups of the CTA run their iterations in step (one CTA-wide barrier per iteration): every warp then
-    // executes the same block-row code at about the same time, and the large unrolled code is fetched once per SM
-    // instead of once per group (without it 37 % of the issue slots were lost to instruction-cache misses).
     // Frame prefetch (when the slot has room for it, p.off_stg >= 0): the raw LLR bytes of the core columns of the slot's
     // NEXT frame are bulk-copied into a staging buffer while the current frame is decoded, so that the frame switch --
     // which every other group of the CTA waits for at the iteration barrier -- is a shared-memory transpose instead of
@@ -593,7 +599,7 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
         active = f < p.F;
         if (active) {
         const int8_t *src = p.llr + (size_t)f * p.N;
-        if (i == 0) stage_row(0, false, tt, src);   // extension bytes of the first row
+        if (i == 0 || i == ext_thread) stage_row(0, false, tt, src);   // extension bytes of the first row
         {   // pull this slot's next frame towards L2 while the current one is decoded
             const int fn = f + fstride;
             if (fn < p.F) {
@@ -660,7 +666,7 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
                 const int4 lb = *reinterpret_cast<const int4 *>(rowsc + 32 * r + 16);   // ext_src, ext_hd, syn_off, deg
                 const u32 stage = tt & 1u;
                 QL_BEL_WAIT();   // every belief update of the previous row is visible
-                if (i == 0 && r + 1 < R) stage_row(r + 1, it > 0, tt + 1, frame);
+                if ((i == 0 || i == ext_thread) && r + 1 < R) stage_row(r + 1, it > 0, tt + 1, frame);
                 uint2 m1init = make_uint2(kInf2, kInf2);   // initial (min1, sign) of the two half2 pairs
                 if (has_syn) {
                     const u32 *sr = synl + r * ZW32 + wis;
@@ -690,7 +696,7 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
             ++it;
             const bool more = it < p.max_iter;
             QL_BEL_WAIT();
-            if (i == 0 && more) stage_row(0, true, tt, frame);   // first row of the next iteration (dropped if the frame ends)
+            if ((i == 0 || i == ext_thread) && more) stage_row(0, true, tt, frame);   // first row of the next iteration (dropped if the frame ends)
             // the syndrome / hard-decision phase runs after every iteration when early stop is on,
             // otherwise once after the last iteration
             if (p.early_stop || !more) {

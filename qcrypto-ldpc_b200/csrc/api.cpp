@@ -1148,8 +1148,11 @@ extern "C" int qldpc_privacy_amplify(int32_t device, const uint32_t *key, int32_
         if ((rc = pa_upload_jump_tables())) return rc;
         tables_on = device;
     }
-    DevBuf<uint32_t> d_key, d_seed, d_out;
-    DevBuf<int32_t> d_wb, d_fb;
+    // device staging buffers are kept per host thread: an ecd2 handler calls this once per block
+    static thread_local DevBuf<uint32_t> d_key, d_seed, d_out;
+    static thread_local DevBuf<int32_t> d_wb, d_fb;
+    static thread_local int buf_device = -1;
+    if (buf_device != device) { d_key.release(); d_seed.release(); d_out.release(); d_wb.release(); d_fb.release(); buf_device = device; }
     const size_t nk = (size_t)n_blocks * key_stride_words, no = (size_t)n_blocks * std::max(1, out_stride_words);
     if ((rc = d_key.ensure(nk)) || (rc = d_seed.ensure(n_blocks)) || (rc = d_out.ensure(no)) || (rc = d_wb.ensure(n_blocks)) ||
         (rc = d_fb.ensure(n_blocks))) return rc;

@@ -143,7 +143,7 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_reference_run(frames_llr, seconds, steps=1, warmup=0, threads=0):
+def cpu_reference_run(frames_llr, seconds, steps=1, warmup=0, threads=0, early_stop=True):
     """times the CPU restatement (oracle 'port') on a bounded sample of the workload, all host threads"""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
@@ -151,22 +151,22 @@ def cpu_reference_run(frames_llr, seconds, steps=1, warmup=0, threads=0):
     rule = O.RULE_NMS
     # calibrate on a few frames, then size the sample for ~`seconds`
     t0 = time.perf_counter()
-    oc.batch_layered_fixed_i8(frames_llr[:16], None, rule=rule, n_ite=MAX_ITER, early_stop=True, norm_eighths=6, n_threads=threads)
+    oc.batch_layered_fixed_i8(frames_llr[:16], None, rule=rule, n_ite=MAX_ITER, early_stop=early_stop, norm_eighths=6, n_threads=threads)
     dt = max(time.perf_counter() - t0, 1e-4)
     n = int(max(16, min(len(frames_llr), 16 * seconds / dt)))
     sample = frames_llr[:n]
     for _ in range(warmup):
-        oc.batch_layered_fixed_i8(sample[: max(16, n // 8)], None, rule=rule, n_ite=MAX_ITER, early_stop=True, norm_eighths=6, n_threads=threads)
+        oc.batch_layered_fixed_i8(sample[: max(16, n // 8)], None, rule=rule, n_ite=MAX_ITER, early_stop=early_stop, norm_eighths=6, n_threads=threads)
     t0 = time.perf_counter()
     nt = 1
     for _ in range(steps):
-        hard, iters, ok, nt = oc.batch_layered_fixed_i8(sample, None, rule=rule, n_ite=MAX_ITER, early_stop=True,
+        hard, iters, ok, nt = oc.batch_layered_fixed_i8(sample, None, rule=rule, n_ite=MAX_ITER, early_stop=early_stop,
                                                         norm_eighths=6, n_threads=threads)
     dt = time.perf_counter() - t0
     mbps = steps * n * oc.K / dt / 1e6
     return {"value": mbps, "unit": "Mbit/s", "cores": int(nt), "kind": "port",
-            "sample": "%d frames x %d step(s) of the same workload (BG1 Z=384 int8 layered NMS 6/8, early stop, QBER 3%%), "
-                      "oracle/qldpc_oracle.c over %d pthreads" % (n, steps, nt),
+            "sample": "%d frames x %d step(s) of the same workload (BG1 Z=384 int8 layered NMS 6/8, %s, QBER 3%%), "
+                      "oracle/qldpc_oracle.c over %d pthreads" % (n, steps, "early stop" if early_stop else "10 fixed iterations", nt),
             "ms_per_step": dt / steps * 1e3, "frames": n, "ok_frac": float(ok.mean()), "mean_iters": float(iters.mean())}
 
 
@@ -201,7 +201,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     llr, oc = synth_frames_cpu(2048 if args.cpu_seconds > 5 else 256)
-    r = cpu_reference_run(llr, args.cpu_seconds, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    r = cpu_reference_run(llr, args.cpu_seconds, steps=max(1, args.steps), warmup=min(args.warmup, 1), early_stop=not args.fixed_iters)
     line = {"impl": "reference", "metric": "reconciled info Mbit/s", "value": r["value"], "unit": "Mbit/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "i8", "data": "synthetic",
@@ -375,7 +375,7 @@ def run_ours(args, rank, world, local_rank):
     cpu = None
     if not args.no_cpu:
         n_cpu = min(F, 16384)
-        cpu = cpu_reference_run(llr[:n_cpu].cpu().numpy(), args.cpu_seconds)
+        cpu = cpu_reference_run(llr[:n_cpu].cpu().numpy(), args.cpu_seconds, early_stop=not args.fixed_iters)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     line = {"metric": "reconciled info Mbit/s", "value": value, "unit": "Mbit/s", "n_gpus": world, "steps": args.steps,

@@ -191,7 +191,7 @@ def workload_config(args, world):
                         (MAX_ITER, "no early stop" if args.fixed_iters else "early termination on zero syndrome", args.frames),
             "code": CODE_FILE, "frames_per_gpu": args.frames, "global_frames": args.frames * world,
             "info_bits_per_frame": 8448, "codeword_bits": 26112, "qber": QBER, "max_iter": MAX_ITER,
-            "early_stop": not args.fixed_iters, "rule": args.rule, "parallelism": "frame-sharded x%d, no collective" % world,
+            "early_stop": not args.fixed_iters, "rule": args.rule, "parallelism": "frame-sharded x%d, no collective; ranks bound to their GPU's NUMA node" % world,
             "l2_policy": "inputs (1.71 GB of int8 LLRs per step) are larger than the 126 MB L2"}
 
 
@@ -214,6 +214,28 @@ def run_reference(args, rank, world):
 
 
 # --------------------------------------------------------------------------------------------- ours
+
+def bind_to_gpu_numa(torch, local_rank):
+    """Pin this rank (and hence its pinned host buffers, first touch) to the NUMA node of its GPU: with 8 ranks per box the
+    host side of the e2e path is otherwise bound by cross-socket traffic.  Silently does nothing where sysfs says nothing."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
 
 def synth_frames_device(torch, dec, F, K, N, seed, dev, st):
     """Synthetic sifted-key frames generated on the device with the library's own encoder / LLR kernels: Alice's
@@ -247,6 +269,7 @@ def run_ours(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa(torch, local_rank) if world > 1 else None
     dev = torch.device("cuda", local_rank)
     code = q.Code.from_qc_file(q.data_path(CODE_FILE))
     rule = q.RULE_NMS if args.rule == "nms" else q.RULE_OMS

@@ -308,7 +308,7 @@ bool plan_layered_i8s(qldpc_decoder *d)
     geo.off_mbar[1] = geo.off_syn + R * ZW32 * 4;
     geo.slot_bytes[0] = geo.off_mbar[0] + 32;
     geo.slot_bytes[1] = geo.off_mbar[1] + 32;
-    const int avail = d->max_smem_optin - geo.tab_bytes - 16;
+    const int avail = d->max_smem_optin - geo.tab_bytes - kLi8sSlotBase;
     const bool want_stg = !std::getenv("QLDPC_LI8_NOSTAGE");
     for (int k = 0; k < 2; ++k) {
         int slots = std::min(std::min(avail / geo.slot_bytes[k], layered_i8s_max_threads() / W), 15);
@@ -671,7 +671,7 @@ static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint3
         const size_t lane_u4 = (size_t)d->sm_count * std::max(geo.slots[0], geo.slots[1]) * geo.rg_u4;
         if ((rc = d->d_li8s_rg.ensure(2 * lane_u4))) return rc;
         p.rg = d->d_li8s_rg.p + (size_t)scratch_lane * lane_u4;
-        const int smem_bytes = geo.tab_bytes + 16 + p.slots * p.slot_bytes;
+        const int smem_bytes = geo.tab_bytes + kLi8sSlotBase + p.slots * p.slot_bytes;
         if (d->l2_persist_bytes > 0) {
             // keep (a share of) the message scratch resident in L2 while the LLR stream flows through it
             const size_t win = std::min<size_t>((size_t)grid * p.slots * geo.rg_u4 * 16, (size_t)d->l2_window_max);

@@ -67,6 +67,7 @@ struct LayeredI8sParams {
     int off_stg;              // staging buffer of the next frame's core LLRs (n_pack * Z bytes), -1: none
     int rg_u4;                // uint4 per frame slot in the scratch
 };
+constexpr int kLi8sSlotBase = 32;   // after the tables: 16 bytes of zero messages, the CTA's iteration mbarrier (8 bytes, padded)
 int launch_layered_i8s(const LayeredI8sParams &p, int grid, int smem_bytes, cudaStream_t st);
 int layered_i8s_max_threads();
 

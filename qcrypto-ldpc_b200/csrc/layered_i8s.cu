@@ -68,6 +68,9 @@
 #ifndef QL_S_SPLITSTAGE
 #define QL_S_SPLITSTAGE 0            // staging duty split over two warps of the group: 49.8 vs 50.9 (off)
 #endif
+#ifndef QL_S_CTAMBAR
+#define QL_S_CTAMBAR 0               // iteration alignment through an arrive (after the rows) / wait (before the next rows) mbarrier: 47.6 vs 51.4 (off)
+#endif
 #ifndef QL_S_FMACLIP8
 #define QL_S_FMACLIP8 0              // belief clip (upper bound) on the FMA pipe
 #endif
@@ -130,6 +133,10 @@ __device__ __forceinline__ void mbar_init(u32 mb, u32 count)
 __device__ __forceinline__ void mbar_arrive(u32 mb)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mb) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_drop(u32 mb)
+{
+    asm volatile("mbarrier.arrive_drop.shared::cta.b64 _, [%0];" ::"r"(mb) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_tx(u32 mb, u32 bytes)
 {
@@ -501,7 +508,7 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
     const int lane = i & 31, wis = i >> 5;
     const int bar_id = 1 + g;
 
-    char *slot = smem + p.tab_bytes + 16 + g * p.slot_bytes;
+    char *slot = smem + p.tab_bytes + kLi8sSlotBase + g * p.slot_bytes;
     const u32 slot_saddr = (u32)__cvta_generic_to_shared(slot);
     const u32 mb_full = slot_saddr + p.off_mbar, mb_bel = mb_full + 16, mb_stg = mb_full + 24;   // full[0], full[1], bel, stg
     {   // shared tables (all slots) + one block of biased zero messages; mbarriers of this group
@@ -509,7 +516,10 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
         const uint4 *src = reinterpret_cast<const uint4 *>(p.tab);
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
         for (int k = tid; k < (p.tab_bytes >> 4); k += nthreads) dst[k] = src[k];
-        if (tid == 0) dst[p.tab_bytes >> 4] = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+        if (tid == 0) {
+            dst[p.tab_bytes >> 4] = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+            mbar_init((u32)__cvta_generic_to_shared(smem + p.tab_bytes + 16), (u32)nthreads);   // iteration barrier of the CTA
+        }
         if (i == 0) {
             mbar_init(mb_full, 1);
             mbar_init(mb_full + 8, 1);
@@ -587,16 +597,31 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
     int f = blockIdx.x * p.slots + g;
     const int fstride = gridDim.x * p.slots;
     if (use_stg && i == 0 && f < p.F) stage_frame(f);
-    const int nthreads_cta = W * blockDim.y;
+    [[maybe_unused]] const int nthreads_cta = W * blockDim.y;
     bool active = false, need_load = true, conv = false;
     int it = 0;
     u32 tt = 0;
     [[maybe_unused]] u32 bt = 0;   // trips staged / waited on full[], phases waited on bel (both run on across frames)
 #pragma unroll 1
+    // QL_S_CTAMBAR (measured, off): the iteration alignment as an mbarrier every thread ARRIVES on right after its block rows
+    // and WAITS on right before the next ones, so that the phases in between (hard decisions, syndrome, output, frame switch)
+    // overlap with the waiting of the other groups.  It removes the 8 % barrier stall and loses more than that, because the
+    // groups then run those phases -- different code -- while others are in their rows (instruction-cache sharing again).
+    // A group that runs out of frames leaves with arrive_drop, after the round it has already arrived for has completed.
+    const u32 mb_cta = (u32)__cvta_generic_to_shared(smem + p.tab_bytes + 16);
+    [[maybe_unused]] u32 cpar = 0;
+    [[maybe_unused]] bool first_round = true;
     for (;;) {
       if (need_load) {
         need_load = false;
         active = f < p.F;
+#if QL_S_CTAMBAR
+        if (!active) {
+            if (!first_round) mbar_wait(mb_cta, cpar);
+            mbar_arrive_drop(mb_cta);
+            break;
+        }
+#endif
         if (active) {
         const int8_t *src = p.llr + (size_t)f * p.N;
         if (i == 0 || i == ext_thread) stage_row(0, false, tt, src);   // extension bytes of the first row
@@ -656,7 +681,12 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
         conv = false;
         }
       }
+#if QL_S_CTAMBAR
+      if (!first_round) { mbar_wait(mb_cta, cpar); cpar ^= 1u; }   // every group has finished the rows of the previous round
+      first_round = false;
+#else
       if (!bar_red_or(0, nthreads_cta, active)) break;   // also the alignment barrier of the iteration
+#endif
       if (active) {
             bool finished = false;
             const int8_t *frame = p.llr + (size_t)f * p.N;
@@ -693,6 +723,9 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
                 if (r == R - 1) asm volatile("fence.proxy.async.global;" ::: "memory");
                 QL_BEL_ARRIVE();
             }
+#if QL_S_CTAMBAR
+            mbar_arrive(mb_cta);
+#endif
             ++it;
             const bool more = it < p.max_iter;
             QL_BEL_WAIT();

@@ -137,6 +137,11 @@ int32_t qldpc_codeword_words(const qldpc_decoder *dec);  /* ceil(n/32)          
  * qldpc_decode takes HOST pointers (copies are inside the call); qldpc_decode_device takes
  * DEVICE pointers, enqueues on `cuda_stream` (a cudaStream_t, NULL = default stream) and
  * returns without synchronising.
+ * Concurrency: a decoder owns one set of device scratch buffers, so at most one qldpc_decode_device call per decoder may be
+ * in flight at a time (use one decoder per stream); the host-pointer calls are self-contained and synchronise before
+ * returning.  Side effects of the int8 layered decoders for Z % 128 == 0: decoder creation raises the device-wide
+ * cudaLimitPersistingL2CacheSize (the message scratch is kept resident in L2; QLDPC_L2_PERSIST=0 in the environment leaves
+ * the limit alone) and qldpc_decode_device sets cudaStreamAttributeAccessPolicyWindow on `cuda_stream` to that scratch.
  */
 int qldpc_decode(qldpc_decoder *dec, const void *llr, const uint32_t *syndrome, int32_t n_frames,
                  uint32_t *out_bits, uint8_t *ok, uint16_t *iters, void *posterior);

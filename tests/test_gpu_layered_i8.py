@@ -186,3 +186,12 @@ def test_host_pipeline_many_small_chunks(q, O, data_dir, monkeypatch):
     sel = rng.choice(F, 24, replace=False)
     hard, oit, ook, _ = oc.batch_layered_fixed_i8(llr[sel], None, rule=O.RULE_NMS, n_ite=10, early_stop=True, norm_eighths=6)
     assert (oit == iters[sel]).all() and (hard[:, :oc.K] == msg[sel]).all()
+
+
+@pytest.mark.parametrize("mode,qber,mag", [("parity", 0.03, 14), ("syndrome", 0.06, 11)])
+def test_bg1_z384_many_frames_per_slot_vs_oracle(q, O, data_dir, mode, qber, mag):
+    """more frames than the persistent grid has slots (148 SMs x 5): every slot switches frames several times (frame prefetch,
+    barrier parities and message scratch carried across frames) and groups of one CTA finish at different iterations;
+    bits, iteration counts and ok flags still equal the oracle's, frame by frame"""
+    iters, ok = _run_case(q, O, data_dir, "NR_1_1_384.qc", 2600, qber, mag, mode, q.RULE_NMS, 10, True, out_all=False, seed=91)
+    assert len(set(iters.tolist())) >= 2          # a mix of iteration counts inside the batch

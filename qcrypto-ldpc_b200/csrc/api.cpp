@@ -778,7 +778,14 @@ static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint3
             qp.rule = cfg.rule; qp.norm = cfg.norm_factor; qp.offset = cfg.offset; qp.use_smem = d->flood_use_smem;
             if ((rc = launch_flooding_qc(qp, std::min(d->gen_grid, n_frames), std::min(d->flood_block, layered_flood_qc_threads()), d->flood_smem, st))) return rc;
         } else
-        if ((rc = launch_flooding(p, std::min(d->gen_grid, n_frames), d->flood_block, d->flood_smem, st))) return rc;
+        {
+            int smem_bytes = d->flood_smem;
+            if (!d->flood_use_smem && cfg.dtype == QLDPC_DTYPE_F32 && cfg.rule == QLDPC_RULE_SPA && !std::getenv("QLDPC_NO_TANH_CACHE")) {
+                p.tanh_cache = 1;
+                smem_bytes = 8 * d->flood_block * 4;
+            }
+            if ((rc = launch_flooding(p, std::min(d->gen_grid, n_frames), d->flood_block, smem_bytes, st))) return rc;
+        }
     }
     d->kernel_launches++;
     if (!direct) {

@@ -40,8 +40,11 @@ __device__ __forceinline__ int norm8(int v, int k)
 }
 
 // ---- float check-node update (one thread owns the whole check)
+// tcache: when not null, kTanhCache slots of shared memory per thread ([slot][thread]): the tanh of the first pass is kept
+// for the second one (the double-precision tanh is the most expensive operation of the SPA update); the sign travels with it.
+constexpr int kTanhCache = 8;
 __device__ __forceinline__ void check_update_f32(const FloodParams &p, const float *post, float *c2v, int e0, int e1,
-                                                 int synbit)
+                                                 int synbit, float *tcache, int tstride)
 {
     int sign = synbit;
     if (p.rule == QLDPC_RULE_SPA) {
@@ -49,16 +52,26 @@ __device__ __forceinline__ void check_update_f32(const FloodParams &p, const flo
         for (int e = e0; e < e1; ++e) {
             const float x = post[p.col_idx[e]] - c2v[e];
             const float t = (float)tanh((double)(fabsf(x) * 0.5f));
+            if (tcache && e - e0 < kTanhCache) tcache[(e - e0) * tstride] = signbit(x) ? -t : t;   // t >= 0; -0.0f keeps the sign
             product *= (t != 0.0f) ? t : 1e-12f;
             sign ^= signbit(x) ? 1 : 0;
         }
         for (int e = e0; e < e1; ++e) {
-            const float x = post[p.col_idx[e]] - c2v[e];
-            const float t = (float)tanh((double)(fabsf(x) * 0.5f));
+            float t;
+            int sx;
+            if (tcache && e - e0 < kTanhCache) {
+                const float ts = tcache[(e - e0) * tstride];
+                t = fabsf(ts);
+                sx = signbit(ts) ? 1 : 0;
+            } else {
+                const float x = post[p.col_idx[e]] - c2v[e];
+                t = (float)tanh((double)(fabsf(x) * 0.5f));
+                sx = signbit(x) ? 1 : 0;
+            }
             float r = product / ((t != 0.0f) ? t : 1e-12f);
             r = (r < 1.0f) ? r : 1.0f - 1.1920929e-07f;
             const float mag = 2.0f * (float)atanh((double)r);
-            c2v[e] = sgn_apply(mag, sign ^ (signbit(x) ? 1 : 0));
+            c2v[e] = sgn_apply(mag, sign ^ sx);
         }
     } else {
         float min1 = 3.402823466e+38f, min2 = 3.402823466e+38f;
@@ -126,6 +139,8 @@ __global__ void __launch_bounds__(1024, 1) flooding_kernel(const FloodParams p)
         post = reinterpret_cast<T *>(p.post) + (size_t)blockIdx.x * p.N;
     }
     const int tid = threadIdx.x, nt = blockDim.x;
+    // SPA with the messages in global scratch: the (otherwise unused) shared memory caches tanh values between the passes
+    float *tcache = (!p.use_smem && p.tanh_cache) ? reinterpret_cast<float *>(smem) + tid : nullptr;
 
     for (int f = blockIdx.x; f < p.F; f += gridDim.x) {
         const IN *llr = reinterpret_cast<const IN *>(p.llr) + (size_t)f * p.N;
@@ -160,7 +175,7 @@ __global__ void __launch_bounds__(1024, 1) flooding_kernel(const FloodParams p)
             // check phase
             for (int m = tid; m < p.M; m += nt) {
                 const int synbit = syn ? (int)((syn[m >> 5] >> (31 - (m & 31))) & 1u) : 0;
-                if constexpr (std::is_floating_point<T>::value) check_update_f32(p, (const float *)post, (float *)c2v, p.row_ptr[m], p.row_ptr[m + 1], synbit);
+                if constexpr (std::is_floating_point<T>::value) check_update_f32(p, (const float *)post, (float *)c2v, p.row_ptr[m], p.row_ptr[m + 1], synbit, tcache, nt);
                 else check_update_int(p, (const int *)post, (int *)c2v, p.row_ptr[m], p.row_ptr[m + 1], synbit);
             }
             __syncthreads();

@@ -113,6 +113,7 @@ struct FloodParams {
     float norm, offset;
     int offset_int, norm_eighths, vmax;
     int use_smem;             // messages + posteriors in shared memory
+    int tanh_cache;           // !use_smem, float SPA: 8 * block floats of shared memory cache tanh between the two passes
 };
 int launch_flooding(const FloodParams &p, int grid, int block, int smem_bytes, cudaStream_t st);
 

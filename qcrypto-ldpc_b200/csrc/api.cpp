@@ -829,6 +829,13 @@ static ChunkPlan pick_chunk(const qldpc_decoder_full *d, size_t frame_bytes, siz
     chunk = std::max<long long>(cp.wave, (chunk + cp.wave / 2) / cp.wave * cp.wave);
     cp.max = (int)std::min<long long>(chunk, n_frames);
     cp.first = std::min(cp.max, 2 * cp.wave);
+    if (const char *e = std::getenv("QLDPC_CHUNK_PLAN")) {   // experiments: "first,max" in waves
+        int a = 2, b = 17;
+        if (std::sscanf(e, "%d,%d", &a, &b) == 2 && a >= 1 && b >= a) {
+            cp.max = (int)std::min<long long>((long long)b * cp.wave, n_frames);
+            cp.first = std::min(cp.max, a * cp.wave);
+        }
+    }
     return cp;
 }
 

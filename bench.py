@@ -170,6 +170,19 @@ def cpu_reference_run(frames_llr, seconds, steps=1, warmup=0, threads=0, early_s
             "ms_per_step": dt / steps * 1e3, "frames": n, "ok_frac": float(ok.mean()), "mean_iters": float(iters.mean())}
 
 
+def host_description():
+    model = "unknown"
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name"):
+                    model = ln.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    return {"cpu": model, "nproc": os.cpu_count()}
+
+
 def synth_frames_cpu(n, seed=1234):
     """small CPU-side sample of the synthetic workload for the reference arm (numpy + oracle encoder)"""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -206,7 +219,7 @@ def run_reference(args, rank, world):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "i8", "data": "synthetic",
             "config": workload_config(args, world),
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": dict({k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}, host=host_description()),
             "e2e": {"value": r["value"], "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "the reference's own LDPC arithmetic (AFF3CT v2.3.5, MATLAB) cannot be built here; this arm times the "
                     "CPU restatement of it (oracle/, kind=port) on the host cores; each step is a bounded sample"}
@@ -400,6 +413,10 @@ def run_ours(args, rank, world, local_rank):
         n_cpu = min(F, 16384)
         cpu = cpu_reference_run(llr[:n_cpu].cpu().numpy(), args.cpu_seconds, early_stop=not args.fixed_iters)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        # the same decoder on ONE host thread beside the all-cores figure, and what the host is
+        one = cpu_reference_run(llr[:n_cpu].cpu().numpy(), min(3.0, args.cpu_seconds), threads=1, early_stop=not args.fixed_iters)
+        cpu["single_thread"] = {"value": one["value"], "unit": "Mbit/s", "frames": one["frames"]}
+        cpu["host"] = host_description()
 
     line = {"metric": "reconciled info Mbit/s", "value": value, "unit": "Mbit/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",

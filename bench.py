@@ -35,12 +35,14 @@ QBER = 0.03
 LLR_NOISY, LLR_KNOWN = 14.0, 31.0      # ln((1-q)/q)=3.476 at scale 2^2 -> 14; known parity saturates the 6-bit range
 MAX_ITER = 10
 NORM = 0.75
-# figures of the committed ncu capture of the decode kernel (profiles/r1_v5_layered_i8s_ncu_summary.txt)
+# figures of the committed ncu capture of the decode kernel (profiles/r1_v6_layered_i8s_ncu_summary.txt)
 MSG_SCRATCH_BYTES_PER_FRAME = 81 * 96 * 16          # 81 16-byte message blocks per thread, 96 threads (BG1 Z=384)
-NCU_DRAM_BYTES_PER_FRAME = 180.5e3                   # dram__bytes_read + write per frame (message scratch share held in L2: ~half)
-NCU_TRAFFIC_SOURCE = "profiles/r1_v5_layered_i8s_ncu_summary.txt (ncu --set full, 14800 frames, scaled per frame)"
-NCU_ALU_PIPE_PCT = 59.9
-NCU_ISSUE_ACTIVE_PCT = 62.4
+NCU_DRAM_BYTES_PER_FRAME = 178.2e3                   # dram__bytes_read + write per frame (message scratch share held in L2: ~half)
+NCU_TRAFFIC_SOURCE = "profiles/r1_v6_layered_i8s_ncu_summary.txt (ncu --set full, 14800 frames, scaled per frame)"
+NCU_ALU_PIPE_PCT = 54.8
+SMEM_PEAK_GBPS = 37060.0                              # shared-memory loads, all SMs (profiles/r1_onchip_peaks.json)
+L2_PEAK_GBPS = 17600.0                                # L2 reads over a 64 MB buffer (same file)
+NCU_ISSUE_ACTIVE_PCT = 63.9
 
 
 def parse_args():
@@ -406,7 +408,11 @@ def run_ours(args, rank, world, local_rank):
                            "edge_updates_per_s": mean_iters * code.edges * F / (launch_ms * 1e-3),
                            "message_scratch_l2_bytes_per_frame": msg_l2_bytes_per_frame,
                            "message_scratch_l2_GBps": msg_l2_bytes_per_frame * F / (launch_ms * 1e-3) / 1e9,
-                           "alu_pipe_pct_ncu": NCU_ALU_PIPE_PCT, "issue_active_pct_ncu": NCU_ISSUE_ACTIVE_PCT}}
+                           "alu_pipe_pct_ncu": NCU_ALU_PIPE_PCT, "issue_active_pct_ncu": NCU_ISSUE_ACTIVE_PCT,
+                           # measured ceilings (tools_onchip_peaks.cu, profiles/r1_onchip_peaks.md)
+                           "smem_peak_GBps_measured": SMEM_PEAK_GBPS, "l2_read_peak_GBps_measured": L2_PEAK_GBPS,
+                           "edge_update_frac_of_smem_peak": edge_bytes_per_frame * F / (launch_ms * 1e-3) / 1e9 / SMEM_PEAK_GBPS,
+                           "message_scratch_frac_of_l2_peak": msg_l2_bytes_per_frame * F / (launch_ms * 1e-3) / 1e9 / L2_PEAK_GBPS}}
 
     cpu = None
     if not args.no_cpu:

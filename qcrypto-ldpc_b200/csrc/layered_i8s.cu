@@ -71,6 +71,12 @@
 #ifndef QL_S_CTAMBAR
 #define QL_S_CTAMBAR 0               // iteration alignment through an arrive (after the rows) / wait (before the next rows) mbarrier: 47.6 vs 51.4 (off)
 #endif
+#ifndef QL_S_FMASEL
+#define QL_S_FMASEL 1                // new message = sigma * (c2 + [|t| == min1] * (c1 - c2)) + 128 as two FMAs and one LOP3 (was two LOP3 and an add)
+#endif
+#ifndef QL_S_M2FMA
+#define QL_S_M2FMA 1                 // second minimum as min(m2, |m1| + |t| - |min1'|): one HMNMX2 becomes two adds (bit 0: lanes A, bit 1: lanes B)
+#endif
 #ifndef QL_S_FMACLIP8
 #define QL_S_FMACLIP8 0              // belief clip (upper bound) on the FMA pipe
 #endif
@@ -100,6 +106,8 @@ __device__ __forceinline__ u32 hadd_relu(u32 a, u32 b) { return bits(__hfma2_rel
 // relu(b - a)
 __device__ __forceinline__ u32 hrsub_relu(u32 a, u32 b) { return bits(__hfma2_relu(h2(a), h2(kMinusOne2), h2(b))); }
 __device__ __forceinline__ u32 heq_mask(u32 a, u32 b) { return __heq2_mask(h2(a), h2(b)); }
+__device__ __forceinline__ u32 heq_one(u32 a, u32 b) { return bits(__heq2(h2(a), h2(b))); }      // 1.0h where equal, else 0
+__device__ __forceinline__ u32 hfma(u32 a, u32 b, u32 c) { return bits(__hfma2(h2(a), h2(b), h2(c))); }
 __device__ __forceinline__ u32 prmt(u32 a, u32 b, u32 sel)
 {
     u32 d;
@@ -111,6 +119,19 @@ __device__ __forceinline__ u32 min_xorsign_abs(u32 a, u32 b)
     u32 d;
     asm("min.xorsign.abs.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
     return d;
+}
+// one edge into the running (min1 with sign product, min2) pair
+template <bool ADDFORM>
+__device__ __forceinline__ void two_min(u32 &m1, u32 &m2, u32 t)
+{
+    if (ADDFORM) {
+        const u32 s = hadd(habs(m1), habs(t));     // exact: both below 2048 ulp
+        m1 = min_xorsign_abs(m1, t);
+        m2 = hmin(m2, hsub(s, habs(m1)));          // |m1| + |t| - min(|m1|, |t|) = max(|m1|, |t|)
+    } else {
+        m2 = hmax(habs(m1), hmin(habs(t), m2));
+        m1 = min_xorsign_abs(m1, t);
+    }
 }
 __device__ __forceinline__ void bar_sync(int id, int nthreads)
 {
@@ -310,10 +331,8 @@ __device__ __forceinline__ void process_row(const Cx &cx, char *Li, u32 erow, co
             if (j < KU) { uA[j] = ua; uB[j] = ub; } else { xk[j] = X; }
             if constexpr (MODE == 0) { tA[j] = ta; tB[j] = tb; }
             if constexpr (MODE <= 1) { sw[j] = en.selW; ad[j] = a; }
-            m2A = hmax(habs(m1A), hmin(habs(ta), m2A));               // second minimum (:61)
-            m2B = hmax(habs(m1B), hmin(habs(tb), m2B));
-            m1A = min_xorsign_abs(m1A, ta);                           // first minimum and sign product (:60,:63)
-            m1B = min_xorsign_abs(m1B, tb);
+            two_min<(QL_S_M2FMA & 1) != 0>(m1A, m2A, ta);               // first minimum and sign product (:60,:63), second minimum (:61)
+            two_min<(QL_S_M2FMA & 2) != 0>(m1B, m2B, tb);
         }
     }
     u32 ueA = 0, ueB = 0, teA = 0, teB = 0;
@@ -323,10 +342,8 @@ __device__ __forceinline__ void process_row(const Cx &cx, char *Li, u32 erow, co
         ueB = hsub((b2 | (b3 << 16)) ^ k128, k128);
         teA = clip_msg(cx, ueA);
         teB = clip_msg(cx, ueB);
-        m2A = hmax(habs(m1A), hmin(habs(teA), m2A));
-        m2B = hmax(habs(m1B), hmin(habs(teB), m2B));
-        m1A = min_xorsign_abs(m1A, teA);
-        m1B = min_xorsign_abs(m1B, teB);
+        two_min<(QL_S_M2FMA & 1) != 0>(m1A, m2A, teA);
+        two_min<(QL_S_M2FMA & 2) != 0>(m1B, m2B, teB);
     }
     const u32 parA = m1A & kSignMask, parB = m1B & kSignMask;
     const u32 min1A = habs(m1A), min1B = habs(m1B);
@@ -340,13 +357,24 @@ __device__ __forceinline__ void process_row(const Cx &cx, char *Li, u32 erow, co
         c1A = norm_eighths2<NK>(m2A, cx.norm_eighths); c1B = norm_eighths2<NK>(m2B, cx.norm_eighths);
         c2A = norm_eighths2<NK>(min1A, cx.norm_eighths); c2B = norm_eighths2<NK>(min1B, cx.norm_eighths);
     }
+#if QL_S_FMASEL
+    // magnitude c2 + [|t| == min1] * (c1 - c2), sign sigma = (row parity ^ sign(t)) as +-1.0h: all exact on subnormal integers
+    const u32 dcA = hsub(c1A, c2A), dcB = hsub(c1B, c2B);
+    const u32 sgA = parA ^ kOne2, sgB = parB ^ kOne2;
+#else
     c1A ^= parA; c2A ^= parA; c1B ^= parB; c2B ^= parB;               // parity folded into both candidates
+#endif
 
     if constexpr (EXT) {   // only the sign of channel + new message is observable: ballot it into the hd vector
+#if QL_S_FMASEL
+        const u32 aA = hfma((teA & kSignMask) ^ sgA, hfma(heq_one(habs(teA), min1A), dcA, c2A), ueA);
+        const u32 aB = hfma((teB & kSignMask) ^ sgB, hfma(heq_one(habs(teB), min1B), dcB, c2B), ueB);
+#else
         const u32 eA = heq_mask(habs(teA), min1A), eB = heq_mask(habs(teB), min1B);
         const u32 rA = ((eA & c1A) | (~eA & c2A)) ^ (teA & kSignMask);
         const u32 rB = ((eB & c1B) | (~eB & c2B)) ^ (teB & kSignMask);
         const u32 aA = hadd(ueA, rA), aB = hadd(ueB, rB);
+#endif
         const u32 b0 = __ballot_sync(0xffffffffu, (int)(aA << 16) < 0);   // lane i
         const u32 b1 = __ballot_sync(0xffffffffu, (int)aA < 0);           // lane i + W
         const u32 b2 = __ballot_sync(0xffffffffu, (int)(aB << 16) < 0);   // lane i + 2W
@@ -389,11 +417,16 @@ __device__ __forceinline__ void process_row(const Cx &cx, char *Li, u32 erow, co
                 ta = clip_msg(cx, ua);
                 tb = clip_msg(cx, ub);
             }
-            const u32 eA = heq_mask(habs(ta), min1A), eB = heq_mask(habs(tb), min1B);
             // |t| == min1 ? c1 : c2, then the edge's own sign (:73-75)
+#if QL_S_FMASEL
+            const u32 bA = hfma((ta & kSignMask) ^ sgA, hfma(heq_one(habs(ta), min1A), dcA, c2A), k128);   // biased new message
+            const u32 bB = hfma((tb & kSignMask) ^ sgB, hfma(heq_one(habs(tb), min1B), dcB, c2B), k128);
+#else
+            const u32 eA = heq_mask(habs(ta), min1A), eB = heq_mask(habs(tb), min1B);
             const u32 rA = ((eA & c1A) | (~eA & c2A)) ^ (ta & kSignMask);
             const u32 rB = ((eB & c1B) | (~eB & c2B)) ^ (tb & kSignMask);
             const u32 bA = hadd(rA, k128), bB = hadd(rB, k128);       // biased new message
+#endif
             const u32 lA = clip_belief(ua, bA);                       // clip(L - R_old + R_new) biased (:88-91)
             const u32 lB = clip_belief(ub, bB);
             vset(Yn, j & 3, prmt(bA, bB, 0x6420u));

@@ -159,6 +159,46 @@ def test_full_batch_roundtrip_property(q, O, data_dir):
     assert (oit == iters[sel]).all() and ook.all()
 
 
+def test_baseline_full_size_65536_frames_roundtrip(q, O, data_dir):
+    """BASELINE config 2 at its full size (65 536 frames of BG1 Z=384 in ONE call through the host-pointer entry point):
+    encode -> BSC(3 %) -> decode gives back every one of Alice's 553 648 128 bits; syndrome linearity over the whole batch."""
+    path = "%s/NR_1_1_384.qc" % data_dir
+    oc = O.Code.from_qc(path)
+    code = q.Code.from_qc_file(path)
+    dec = q.Decoder(code, schedule=q.SCHED_LAYERED, rule=q.RULE_NMS, dtype=q.DTYPE_I8, max_iter=10, early_stop=True,
+                    norm_factor=0.75, out_mode=q.OUT_INFO)
+    F, C = 65536, 4096
+    rng = np.random.default_rng(2024)
+    kw = (oc.K + 31) // 32
+    msg_p = np.empty((F, kw), np.uint32)
+    noisy_p = np.empty((F, (oc.N + 31) // 32), np.uint32)
+    for c in range(0, F, C):   # inputs are built chunk-wise on the host (numpy), the decode below is one call
+        m = rng.integers(0, 2, (C, oc.K), dtype=np.uint8)
+        msg_p[c:c + C] = q.pack_bits(m)
+        cw = dec.encode_nr(msg_p[c:c + C])
+        e = np.zeros((C, oc.N), np.uint8)
+        e[:, :oc.K] = rng.random((C, oc.K), dtype=np.float32) < 0.03
+        noisy_p[c:c + C] = cw ^ q.pack_bits(e)
+    known = np.zeros(oc.N, np.uint8)
+    known[oc.K:] = 1
+    dec.reset_stats()
+    out, ok, iters = dec.decode_bits(noisy_p, 14.0, 31.0, known_mask=q.pack_bits(known))
+    assert ok.all()
+    assert (out == msg_p).all()
+    st = dec.stats()
+    assert st["frames"] == F and st["failures"] == 0 and st["iter_sum"] == int(iters.sum())
+    assert 1 <= iters.min() and iters.max() <= 4           # QBER 3 %: converges in 1-3 iterations (SURVEY.md 8d)
+    # linearity of the syndrome over the full batch: H(a ^ b) = H(a) ^ H(b), with b = a cyclic shift of the batch
+    sa = dec.syndrome(noisy_p)
+    sb = np.roll(sa, 1, axis=0)
+    assert (dec.syndrome(noisy_p ^ np.roll(noisy_p, 1, axis=0)) == (sa ^ sb)).all()
+    # sampled oracle agreement on iteration counts at this size
+    sel = rng.choice(F, 8, replace=False)
+    llr = dec.make_llr(noisy_p[sel], 14.0, 31.0, known_mask=q.pack_bits(known))
+    _, oit, ook, _ = oc.batch_layered_fixed_i8(llr, None, rule=O.RULE_NMS, n_ite=10, early_stop=True, norm_eighths=6)
+    assert (oit == iters[sel]).all() and ook.all()
+
+
 def test_host_pipeline_many_small_chunks(q, O, data_dir, monkeypatch):
     """the host-pointer entry points cut the batch into chunks that ping-pong over two streams; kernels of the two
     streams overlap in time, so nothing they write may be shared (regression: streamed-message scratch)"""

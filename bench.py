@@ -35,14 +35,14 @@ QBER = 0.03
 LLR_NOISY, LLR_KNOWN = 14.0, 31.0      # ln((1-q)/q)=3.476 at scale 2^2 -> 14; known parity saturates the 6-bit range
 MAX_ITER = 10
 NORM = 0.75
-# figures of the committed ncu capture of the decode kernel (profiles/r1_v6_layered_i8s_ncu_summary.txt)
+# figures of the committed ncu capture of the decode kernel (profiles/r1_v7_layered_i8s_ncu_summary.txt)
 MSG_SCRATCH_BYTES_PER_FRAME = 81 * 96 * 16          # 81 16-byte message blocks per thread, 96 threads (BG1 Z=384)
-NCU_DRAM_BYTES_PER_FRAME = 178.2e3                   # dram__bytes_read + write per frame (message scratch share held in L2: ~half)
-NCU_TRAFFIC_SOURCE = "profiles/r1_v6_layered_i8s_ncu_summary.txt (ncu --set full, 14800 frames, scaled per frame)"
+NCU_DRAM_BYTES_PER_FRAME = 183.9e3                   # dram__bytes_read + write per frame (message scratch share held in L2: ~half)
+NCU_TRAFFIC_SOURCE = "profiles/r1_v7_layered_i8s_ncu_summary.txt (ncu --set full, 14800 frames, scaled per frame)"
 NCU_ALU_PIPE_PCT = 54.8
 SMEM_PEAK_GBPS = 37060.0                              # shared-memory loads, all SMs (profiles/r1_onchip_peaks.json)
 L2_PEAK_GBPS = 17600.0                                # L2 reads over a 64 MB buffer (same file)
-NCU_ISSUE_ACTIVE_PCT = 63.9
+NCU_ISSUE_ACTIVE_PCT = 64.4
 
 
 def parse_args():
@@ -434,7 +434,7 @@ def run_ours(args, rank, world, local_rank):
         line["e2e"] = {"value": F * world * K / (e2e_ms * 1e-3) / 1e6, "unit": "Mbit/s", "h2d_bytes_per_step": e2e["h2d"] * world,
                        "d2h_bytes_per_step": e2e["d2h"] * world, "ms_per_step": e2e_ms, "steps": e2e["steps"],
                        "api": "qldpc_decode_bits (host pointers: pinned packed key bits in, packed bits/ok/iters out; "
-                              "LLR synthesis on the device; 2-stream chunked pipeline)"}
+                              "LLR synthesis on the device beside the decoder of the other lane; 2-stream chunked pipeline)"}
         line["e2e_llr_api"] = {"value": F * world * K / (e2e_llr_ms * 1e-3) / 1e6, "unit": "Mbit/s",
                                "h2d_bytes_per_step": e2e["h2d_llr"] * world, "d2h_bytes_per_step": e2e["d2h"] * world,
                                "ms_per_step": e2e_llr_ms, "api": "qldpc_decode (host pointers, pinned int8 LLRs in)"}

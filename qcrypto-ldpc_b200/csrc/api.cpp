@@ -1,5 +1,8 @@
 // C ABI of libqldpc_b200 (see include/qldpc.h for the reference interface each entry point replaces).
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <vector>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -669,8 +672,16 @@ static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint3
         p.rg_u4 = geo.rg_u4;
         const int grid = std::min(d->sm_count, (n_frames + p.slots - 1) / p.slots);
         const size_t lane_u4 = (size_t)d->sm_count * std::max(geo.slots[0], geo.slots[1]) * geo.rg_u4;
-        if ((rc = d->d_li8s_rg.ensure(2 * lane_u4))) return rc;
+        if ((rc = d->d_li8s_rg.ensure(2 * lane_u4 + 2))) return rc;
         p.rg = d->d_li8s_rg.p + (size_t)scratch_lane * lane_u4;
+        // frame queue: with early termination the frames of a slot take 1..max_iter iterations each, and a fixed
+        // f, f + grid*slots, ... assignment leaves the slots that drew the easy frames idle at the end of the launch
+        static const bool static_frames = std::getenv("QLDPC_LI8_STATIC") != nullptr;
+        p.frame_ctr = nullptr;
+        if (!static_frames && n_frames > grid * p.slots) {
+            p.frame_ctr = reinterpret_cast<unsigned int *>(d->d_li8s_rg.p + 2 * lane_u4 + scratch_lane);
+            QLDPC_CUDA(cudaMemsetAsync(p.frame_ctr, 0, sizeof(unsigned int), st));
+        }
         const int smem_bytes = geo.tab_bytes + kLi8sSlotBase + p.slots * p.slot_bytes;
         if (d->l2_persist_bytes > 0) {
             // keep (a share of) the message scratch resident in L2 while the LLR stream flows through it
@@ -1020,27 +1031,59 @@ extern "C" int qldpc_decode_bits(qldpc_decoder *dec, const uint32_t *bits, const
         if ((rc = ln.iters.ensure(chunk))) return rc;
         if (syndrome && (rc = ln.syn.ensure((size_t)chunk * d->syn_words))) return rc;
     }
+    // QLDPC_TIMELINE=1 (diagnostics): per chunk, when its H2D copy, LLR synthesis, decode and D2H copy ended, on stderr
+    static const bool timeline = std::getenv("QLDPC_TIMELINE") != nullptr;
+    std::vector<cudaEvent_t> tl;
+    auto mark = [&](cudaStream_t st) {
+        if (!timeline) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        tl.push_back(e);
+    };
+    const auto host_t0 = std::chrono::steady_clock::now();
+    mark(l0.st);
     int idx = 0;
     for (int f0 = 0, nf = 0; f0 < n_frames; f0 += nf, ++idx) {
         Lane &ln = d->lanes.lane[shared_scratch ? 0 : (idx & 1)];
         nf = std::min(plan.at(idx), n_frames - f0);
+        mark(ln.st);
         QLDPC_CUDA(cudaMemcpyAsync(ln.bits.p, bits + (size_t)f0 * d->cw_words, (size_t)nf * d->cw_words * 4,
                                    cudaMemcpyHostToDevice, ln.st));
+        mark(ln.st);
         if (syndrome)
             QLDPC_CUDA(cudaMemcpyAsync(ln.syn.p, syndrome + (size_t)f0 * d->syn_words, (size_t)nf * d->syn_words * 4,
                                        cudaMemcpyHostToDevice, ln.st));
         if ((rc = qldpc_make_llr_device(dec, ln.bits.p, dk, dp, llr_noisy, llr_known, nf, ln.in.p, ln.st))) break;
+        mark(ln.st);
         if ((rc = decode_device_impl(dec, ln.in.p, syndrome ? ln.syn.p : nullptr, nf, ln.out.p, ln.ok.p, ln.iters.p, nullptr,
                                      ln.st, shared_scratch ? 0 : (idx & 1)))) break;
+        mark(ln.st);
         QLDPC_CUDA(cudaMemcpyAsync(out_bits + (size_t)f0 * d->out_words, ln.out.p, (size_t)nf * d->out_words * 4,
                                    cudaMemcpyDeviceToHost, ln.st));
         if (ok) QLDPC_CUDA(cudaMemcpyAsync(ok + f0, ln.ok.p, nf, cudaMemcpyDeviceToHost, ln.st));
         if (iters) QLDPC_CUDA(cudaMemcpyAsync(iters + f0, ln.iters.p, (size_t)nf * 2, cudaMemcpyDeviceToHost, ln.st));
+        mark(ln.st);
     }
+    const double host_issue_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
     for (auto &ln : d->lanes.lane) {
         cudaError_t e = cudaStreamSynchronize(ln.st);
         if (e != cudaSuccess && rc == QLDPC_OK) rc = CudaCheck::fail(e, "cudaStreamSynchronize");
     }
+    if (timeline && rc == QLDPC_OK && tl.size() == (size_t)(1 + 5 * idx)) {
+        const double host_total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+        std::fprintf(stderr, "[qldpc timeline] %d frames, %d chunks, host issue %.3f ms, host total %.3f ms\n", n_frames, idx,
+                     host_issue_ms, host_total_ms);
+        for (int k = 0, f0 = 0; k < idx; ++k) {
+            float t[5];
+            for (int j = 0; j < 5; ++j) cudaEventElapsedTime(&t[j], tl[0], tl[1 + 5 * k + j]);
+            const int nfk = std::min(plan.at(k), n_frames - f0);
+            std::fprintf(stderr, "[qldpc timeline] chunk %2d lane %d frames %6d: start %7.3f h2d %7.3f llr %7.3f decode %7.3f d2h %7.3f ms\n",
+                         k, k & 1, nfk, t[0], t[1], t[2], t[3], t[4]);
+            f0 += nfk;
+        }
+    }
+    for (auto e : tl) cudaEventDestroy(e);
     return rc;
 }
 

@@ -70,35 +70,62 @@ __global__ void make_llr_kernel(const uint32_t *__restrict__ bits, const uint32_
     }
 }
 
-// int8 fast path of the same synthesis: one thread per 16 consecutive positions, one 128-bit store.  128 threads and at
-// most 32 registers per CTA so that a CTA fits beside the persistent decode CTA of the other pipeline lane on every SM
-// (the decoder leaves 4096 registers per SM): LLR synthesis of chunk i+1 then overlaps the decode of chunk i.
+// int8 fast path of the same synthesis: one thread per 16 consecutive positions, one 128-bit store.
 __device__ __forceinline__ uint32_t spread_nibble(uint32_t nib)   // bit 3..0 of nib -> 0x00/0xFF in bytes 0..3
 {
     return (((nib * 0x08040201u) >> 3) & 0x01010101u) * 0xffu;
 }
-__global__ void __launch_bounds__(128) make_llr_i8x16_kernel(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ known,
-                                                             const uint32_t *__restrict__ punct, int noisy, int known_mag, int F,
-                                                             int groups, int cw_words, uint4 *__restrict__ out)
+// 16 positions per item -> one 16-byte store.  In the host pipeline the kernel runs BESIDE a decode CTA of the other lane,
+// which leaves 1024 registers on each of the four SM sub-partitions (layered_i8s.cu, QL_S_MAXNREG): one CTA of four warps
+// at 32 registers per SM.  With so few warps the latency is hidden by loads in flight, not by occupancy: a CTA lives for
+// kLlrRep rounds of kLlrUnroll independent loads per thread.  (A one-warp CTA with more registers, QL_LLR_BLOCK=32, does
+// not get placed beside a decoder that uses 128 registers either: measured.)
+#ifndef QL_LLR_BLOCK
+#define QL_LLR_BLOCK 128
+#endif
+constexpr int kLlrBlock = QL_LLR_BLOCK, kLlrUnroll = QL_LLR_BLOCK == 32 ? 8 : 4, kLlrRep = QL_LLR_BLOCK == 32 ? 8 : 4;
+__global__ void __launch_bounds__(kLlrBlock, QL_LLR_BLOCK == 32 ? 32 : 16)
+make_llr_i8x16_kernel(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ known, const uint32_t *__restrict__ punct,
+                      int noisy, int known_mag, int F, int groups, int cw_words, uint4 *__restrict__ out)
 {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)F * groups) return;
-    const int f = (int)(t / groups), g = (int)(t - (long long)f * groups);
-    const int sh = (g & 1) ? 0 : 16;                        // MSB-first words: positions 32w .. 32w+15 are bits 31 .. 16
-    const uint32_t b = (__ldg(bits + (size_t)f * cw_words + (g >> 1)) >> sh) & 0xffffu;
-    const uint32_t k = known ? (__ldg(known + (g >> 1)) >> sh) & 0xffffu : 0u;
-    const uint32_t p = punct ? (__ldg(punct + (g >> 1)) >> sh) & 0xffffu : 0u;
+    const long long total = (long long)F * groups;
     const uint32_t posN = (uint32_t)(noisy & 0xff) * 0x01010101u, negN = (uint32_t)(-noisy & 0xff) * 0x01010101u;
     const uint32_t posK = (uint32_t)(known_mag & 0xff) * 0x01010101u, negK = (uint32_t)(-known_mag & 0xff) * 0x01010101u;
-    uint32_t w[4];
+    long long t0 = (long long)blockIdx.x * (kLlrBlock * kLlrUnroll * kLlrRep) + threadIdx.x;
+#pragma unroll 1
+    for (int rep = 0; rep < kLlrRep; ++rep, t0 += kLlrBlock * kLlrUnroll) {
+        uint32_t b[kLlrUnroll];
+        int g[kLlrUnroll];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const uint32_t S = spread_nibble((b >> (12 - 4 * q)) & 0xfu);
-        const uint32_t K = spread_nibble((k >> (12 - 4 * q)) & 0xfu), P = spread_nibble((p >> (12 - 4 * q)) & 0xfu);
-        const uint32_t rN = (posN & ~S) | (negN & S), rK = (posK & ~S) | (negK & S);
-        w[q] = ((rN & ~K) | (rK & K)) & ~P;
+        for (int u = 0; u < kLlrUnroll; ++u) {
+            const long long t = t0 + kLlrBlock * u;
+            b[u] = 0;
+            g[u] = 0;
+            if (t < total) {
+                const int f = (int)(t / groups);
+                g[u] = (int)(t - (long long)f * groups);
+                b[u] = __ldg(bits + (size_t)f * cw_words + (g[u] >> 1));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kLlrUnroll; ++u) {
+            const long long t = t0 + kLlrBlock * u;
+            if (t >= total) break;
+            const int sh = (g[u] & 1) ? 0 : 16;                 // MSB-first words: positions 32w .. 32w+15 are bits 31 .. 16
+            const uint32_t bb = (b[u] >> sh) & 0xffffu;
+            const uint32_t k = known ? (__ldg(known + (g[u] >> 1)) >> sh) & 0xffffu : 0u;
+            const uint32_t p = punct ? (__ldg(punct + (g[u] >> 1)) >> sh) & 0xffffu : 0u;
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t S = spread_nibble((bb >> (12 - 4 * q)) & 0xfu);
+                const uint32_t K = spread_nibble((k >> (12 - 4 * q)) & 0xfu), P = spread_nibble((p >> (12 - 4 * q)) & 0xfu);
+                const uint32_t rN = (posN & ~S) | (negN & S), rK = (posK & ~S) | (negK & S);
+                w[q] = ((rN & ~K) | (rK & K)) & ~P;
+            }
+            out[t] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
     }
-    out[t] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 // 5G-NR double-diagonal encoder (ML/nrldpc_encode.m:12-40), one CTA per frame, bits unpacked in
@@ -206,7 +233,7 @@ int launch_make_llr(const uint32_t *bits, const uint32_t *known, const uint32_t 
     case QLDPC_DTYPE_I8:
         if (N % 16 == 0 && (reinterpret_cast<uintptr_t>(llr_out) & 15) == 0) {
             const int groups = N / 16;
-            make_llr_i8x16_kernel<<<grid_for((long long)F * groups, 128), 128, 0, st>>>(
+            make_llr_i8x16_kernel<<<grid_for((long long)F * groups, kLlrBlock * kLlrUnroll * kLlrRep), kLlrBlock, 0, st>>>(
                 bits, known, punct, (int)(int8_t)lrintf(noisy), (int)(int8_t)lrintf(known_mag), F, groups, cw_words,
                 (uint4 *)llr_out);
             break;

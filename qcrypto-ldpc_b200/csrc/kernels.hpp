@@ -66,6 +66,8 @@ struct LayeredI8sParams {
     int slot_bytes, off_ring, stage_bytes, off_ext, off_hd, off_syn, off_mbar;
     int off_stg;              // staging buffer of the next frame's core LLRs (n_pack * Z bytes), -1: none
     int rg_u4;                // uint4 per frame slot in the scratch
+    unsigned int *frame_ctr;  // zeroed before the launch: frames beyond the first grid * slots are handed out through it
+                              // (null: frame f of a slot is followed by f + grid * slots)
 };
 constexpr int kLi8sSlotBase = 32;   // after the tables: 16 bytes of zero messages, the CTA's iteration mbarrier (8 bytes, padded)
 int launch_layered_i8s(const LayeredI8sParams &p, int grid, int smem_bytes, cudaStream_t st);

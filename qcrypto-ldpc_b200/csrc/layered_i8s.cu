@@ -29,6 +29,13 @@
 #ifndef QL_S_MAXTHREADS
 #define QL_S_MAXTHREADS 480          // 5 frames x 96 threads = 15 warps -> 128 registers per thread (18 warps: 96)
 #endif
+#ifndef QL_S_MAXNREG
+// 120, not the 128 that 15 warps would allow: the warps sit 4/4/4/3 on the four SM sub-partitions, and at 128 registers the
+// three full ones have none left, so no other CTA can start on the SM.  At 120 each keeps 1024 registers free = one
+// 32-register warp, and the LLR synthesis of the next chunk (bitops.cu, 4 warps x 32 registers) runs beside the decoder
+// in the host pipeline: device-resident 52.4 vs 52.6 Gbit/s, through the host call 48.0 vs 46.6.  0: cap from the thread count.
+#define QL_S_MAXNREG 120
+#endif
 #ifndef QL_S_FMACLIP
 #define QL_S_FMACLIP 1               // message clip as relu forms on the FMA pipe
 #endif
@@ -510,7 +517,11 @@ __device__ __forceinline__ void transpose4x4(const u32 (&in)[4], u32 (&out)[4])
 // proxy): every thread issues fence.proxy.async.global after its last store of an iteration, and the first row of
 // the next iteration is staged only after all threads of the group have passed that fence.
 template <int NK, int WT>
+#if QL_S_MAXNREG > 0
+__global__ void __maxnreg__(QL_S_MAXNREG) layered_i8s_kernel(const LayeredI8sParams p)
+#else
 __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const LayeredI8sParams p)
+#endif
 {
     extern __shared__ __align__(16) char smem[];
     const int W = WT ? WT : p.W;
@@ -556,7 +567,9 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
         if (i == 0) {
             mbar_init(mb_full, 1);
             mbar_init(mb_full + 8, 1);
+#if QL_S_BELMBAR
             mbar_init(mb_bel, (u32)W);
+#endif
             mbar_init(mb_stg, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -629,6 +642,11 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
 
     int f = blockIdx.x * p.slots + g;
     const int fstride = gridDim.x * p.slots;
+    // the slot's next frame: f + fstride, or (frame queue) drawn from the launch's counter by thread 0 while the current
+    // frame is loaded and handed to the group through the word of the (unused) belief mbarrier
+    const bool dynq = !QL_S_BELMBAR && p.frame_ctr != nullptr;
+    volatile int *nf_slot = reinterpret_cast<volatile int *>(slot + p.off_mbar + 16);
+    int fnext = f + fstride;
     if (use_stg && i == 0 && f < p.F) stage_frame(f);
     [[maybe_unused]] const int nthreads_cta = W * blockDim.y;
     bool active = false, need_load = true, conv = false;
@@ -658,13 +676,8 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
         if (active) {
         const int8_t *src = p.llr + (size_t)f * p.N;
         if (i == 0 || i == ext_thread) stage_row(0, false, tt, src);   // extension bytes of the first row
-        {   // pull this slot's next frame towards L2 while the current one is decoded
-            const int fn = f + fstride;
-            if (fn < p.F) {
-                const char *nx = reinterpret_cast<const char *>(p.llr + (size_t)fn * p.N);
-                for (int o = i * 128; o < p.N; o += W * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
-            }
-        }
+        int fdraw = 0;
+        if (dynq && i == 0) fdraw = fstride + (int)atomicAdd(p.frame_ctr, 1u);
         // ---- load: int8 LLRs of the core columns -> interleaved biased belief words
         // 4 aligned 32-bit loads (one per quarter of the column) -> 4x4 byte transpose -> one 128-bit store
         if (use_stg) {
@@ -703,12 +716,18 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
             for (int k = 0; k < n16; k += W) rz[k] = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
         }
 #endif
+        if (dynq && i == 0) *nf_slot = fdraw;
         QL_BEL_ARRIVE();
+        fnext = dynq ? *nf_slot : f + fstride;
         if (use_stg) {
 #if QL_S_BELMBAR
             bar_sync(bar_id, W);   // every thread has read the staging buffer
 #endif
-            if (i == 0 && f + fstride < p.F) stage_frame(f + fstride);
+            if (i == 0 && fnext < p.F) stage_frame(fnext);
+        }
+        if (fnext < p.F) {   // pull the rest of the slot's next frame towards L2 while the current one is decoded
+            const char *nx = reinterpret_cast<const char *>(p.llr + (size_t)fnext * p.N);
+            for (int o = i * 128; o < p.N; o += W * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
         }
         it = 0;
         conv = false;
@@ -842,7 +861,7 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
             ++tt;
         }
         bar_sync(bar_id, W);   // hd / beliefs / ring are reused by the next frame of this slot
-        f += fstride;
+        f = fnext;
         need_load = true;
         }
       }

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(512) l2_read(const uint4 *buf, size_t n_vec, i
 }
 
 // 8 independent chains per thread.  One op code per chain slot: chains u = 0..7 run op OPS[u % NOPS].
-enum Op { LOP3 = 0, PRMT, HFMA2, HMNMX2, IADD3, IMAD, HSET2, FFMA, HADD2 };
+enum Op { LOP3 = 0, PRMT, HFMA2, HMNMX2, IADD3, IMAD, HSET2, FFMA, HADD2, VIMNMX16, VIADDMNMX16, VIMNMX3_16, VIMNMX32 };
 template <int OP>
 __device__ __forceinline__ void one(uint32_t &r, uint32_t k1, uint32_t k2)
 {
@@ -85,7 +85,12 @@ __device__ __forceinline__ void one(uint32_t &r, uint32_t k1, uint32_t k2)
     else if (OP == IMAD) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r) : "r"(k1), "r"(k2));
     else if (OP == HSET2) asm volatile("set.eq.f16x2.f16x2 %0, %0, %1;" : "+r"(r) : "r"(k1));
     else if (OP == FFMA) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(*(float *)&r) : "f"(__uint_as_float(k1)), "f"(__uint_as_float(k2)));
-    else asm volatile("add.rn.f16x2 %0, %0, %1;" : "+r"(r) : "r"(k1));
+    else if (OP == HADD2) asm volatile("add.rn.f16x2 %0, %0, %1;" : "+r"(r) : "r"(k1));
+    // DPX: packed signed 16-bit min / add-min-relu / three-input min, and the 32-bit scalar form
+    else if (OP == VIMNMX16) r = __vmins2(r, k1 ^ r);
+    else if (OP == VIADDMNMX16) r = __viaddmin_s16x2_relu(r, k1, k2);
+    else if (OP == VIMNMX3_16) r = __vimin3_s16x2(r, k1, k2 ^ r);
+    else r = (uint32_t)__vimin3_s32((int)r, (int)k1, (int)(k2 ^ r));
 }
 template <int A, int B, int C>
 __global__ void __launch_bounds__(kThreads) issue_rate(int iters, uint32_t *sink, uint32_t seed)
@@ -166,6 +171,8 @@ int main()
         MIX(LOP3, HFMA2, LOP3), MIX(LOP3, HFMA2, HFMA2), MIX(LOP3, HFMA2, IADD3), MIX(LOP3, HFMA2, FFMA), MIX(LOP3, FFMA, FFMA),
         MIX(HFMA2, FFMA, FFMA), MIX(HFMA2, IMAD, HFMA2), MIX(HMNMX2, HFMA2, HMNMX2), MIX(HSET2, LOP3, HSET2), MIX(HSET2, HFMA2, HSET2),
         MIX(HMNMX2, LOP3, HMNMX2), MIX(LOP3, IADD3, IADD3), MIX(HFMA2, IADD3, IADD3), MIX(LOP3, IMAD, LOP3),
+        MIX(VIMNMX16, VIMNMX16, VIMNMX16), MIX(VIADDMNMX16, VIADDMNMX16, VIADDMNMX16), MIX(VIMNMX3_16, VIMNMX3_16, VIMNMX3_16),
+        MIX(VIMNMX32, VIMNMX32, VIMNMX32), MIX(VIADDMNMX16, HFMA2, VIADDMNMX16), MIX(VIADDMNMX16, LOP3, VIADDMNMX16),
 #undef MIX
     };
     CK(cudaGetLastError());

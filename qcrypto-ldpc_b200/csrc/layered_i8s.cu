@@ -2,7 +2,7 @@
 // (BG1/BG2 lifting sizes 128, 256, 384).  Same arithmetic as layered_i8.cu -- ML/BPSK_nrldpc_sim_FP.m:35-94
 // generalised by syndrome input, early stop and the shift-normalised rule; bit-exact with
 // oracle/qldpc_oracle.c:ora_decode_layered_fixed -- but a different placement of the state, chosen so that
-// FIVE frames (BG1 Z=384) are in flight per SM, 15 warps at 128 registers:
+// FIVE frames (BG1 Z=384) are in flight per SM, 15 warps at 120 registers (see QL_S_MAXNREG):
 //   shared memory, per frame slot:
 //     beliefs of the CORE block columns only (columns that are not weight-1/shift-0 extension columns),
 //       word i of a column = lanes {i, i+W, i+2W, i+3W} as biased bytes (L+128), W = Z/4;
@@ -16,7 +16,10 @@
 // Per edge and thread (4 check lanes = 2 half2 pairs) the instruction budget is ~43:
 //   the wrap decision (lane i+r >= W) selects between two precomputed 16-byte table entries (address select + one
 //   128-bit shared load, no SEL chain); clips and the k/8 normalisation run on the FMA pipe (relu / multiply forms)
-//   so that the half-rate ALU pipe only carries PRMT / min-max / logic.
+//   and so does the selection of the new message (two FMAs), so that the half-rate ALU pipe only carries PRMT / min-max /
+//   logic; ALU and fp16-FMA pipe are both half rate, the target is an even split (profiles/r1_onchip_peaks.md).
+// Frames: the first grid*slots are assigned statically, after that a slot draws its next frame from a per-launch counter
+// (frame queue): with early termination frames take 1..max_iter iterations and a fixed assignment leaves slots idle at the end.
 // All frame groups of a CTA start every iteration together, so that the 255 KB of unrolled row code are fetched once
 // per SM (see the comment at the iteration barrier).
 // Early termination: hard decisions are balloted into Z-bit vectors; the syndrome is evaluated word-wise
@@ -27,7 +30,7 @@
 #include "kernels.hpp"
 
 #ifndef QL_S_MAXTHREADS
-#define QL_S_MAXTHREADS 480          // 5 frames x 96 threads = 15 warps -> 128 registers per thread (18 warps: 96)
+#define QL_S_MAXTHREADS 480          // 5 frames x 96 threads = 15 warps (18 warps: 5 on one sub-partition -> 96 registers, spills)
 #endif
 #ifndef QL_S_MAXNREG
 // 120, not the 128 that 15 warps would allow: the warps sit 4/4/4/3 on the four SM sub-partitions, and at 128 registers the

@@ -290,7 +290,7 @@ def run_ours(args, rank, world, local_rank):
     rule = q.RULE_NMS if args.rule == "nms" else q.RULE_OMS
     dec = q.Decoder(code, schedule=q.SCHED_LAYERED, rule=rule, dtype=q.DTYPE_I8, max_iter=MAX_ITER,
                     early_stop=not args.fixed_iters, norm_factor=NORM, offset=2.0, out_mode=q.OUT_INFO, device=local_rank)
-    assert dec.kernel_name == "layered_i8_zpack4"
+    assert dec.kernel_name == "layered_i8s_zpack4", dec.kernel_name   # the streamed kernel (layered_i8s.cu)
     F, N, K = args.frames, code.n, code.k
     st = torch.cuda.current_stream().cuda_stream
 

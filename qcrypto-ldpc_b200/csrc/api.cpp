@@ -550,7 +550,7 @@ extern "C" int qldpc_decoder_create(const qldpc_code *code, const qldpc_decoder_
                 cudaGetLastError();
             }
             d->kernel_family = KF_LAYERED_I8S;
-            d->kernel_name = "layered_i8_zpack4";
+            d->kernel_name = "layered_i8s_zpack4";
         } else if (fast) {
             d->kernel_family = KF_LAYERED_I8;
             d->kernel_name = "layered_i8_zpack4";

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _run_case(q, O, data_dir, name, F, qber, mag, mode, rule, n_ite, early, offset=2, k8=6, out_all=True, seed=1,
-              expect_kernel="layered_i8_zpack4", random_llr=False):
+              expect_kernel=None, random_llr=False):
     path = "%s/%s" % (data_dir, name)
     oc = O.Code.from_qc(path)
     if random_llr:   # stress: arbitrary int8 LLRs incl. -128 / 127 saturation, random syndrome
@@ -21,7 +21,11 @@ def _run_case(q, O, data_dir, name, F, qber, mag, mode, rule, n_ite, early, offs
     code = q.Code.from_qc_file(path)
     dec = q.Decoder(code, schedule=q.SCHED_LAYERED, rule=rule, dtype=q.DTYPE_I8, max_iter=n_ite, early_stop=early,
                     norm_factor=k8 / 8.0, offset=float(offset), out_mode=q.OUT_ALL if out_all else q.OUT_INFO)
-    assert dec.kernel_name == expect_kernel
+    import os
+    if expect_kernel is None:   # streamed kernel (layered_i8s.cu) for Z % 128 == 0, else the shared-memory-resident one
+        streamed = oc.Z % 128 == 0 and not os.environ.get("QLDPC_LI8_MODE")
+        expect_kernel = "layered_i8s_zpack4" if streamed else "layered_i8_zpack4"
+    assert dec.kernel_name == expect_kernel, dec.kernel_name
     syn_packed = None if syn is None else q.pack_bits(syn)
     out, ok, iters, _ = dec.decode(llr.astype(np.int8), syn_packed)
     nbits = oc.N if out_all else oc.K

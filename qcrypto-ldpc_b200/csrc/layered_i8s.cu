@@ -87,6 +87,9 @@
 #ifndef QL_S_M2FMA
 #define QL_S_M2FMA 1                 // second minimum as min(m2, |m1| + |t| - |min1'|): one HMNMX2 becomes two adds (bit 0: lanes A, bit 1: lanes B)
 #endif
+#ifndef QL_S_UNIFORM_G
+#define QL_S_UNIFORM_G 1
+#endif
 #ifndef QL_S_FMACLIP8
 #define QL_S_FMACLIP8 0              // belief clip (upper bound) on the FMA pipe
 #endif
@@ -552,6 +555,17 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
         g = threadIdx.y; i = threadIdx.x;
 #endif
     }
+#if QL_S_UNIFORM_G
+    // the group index is the same for all lanes of a warp (W is a multiple of 32): taking it through a warp reduction puts it
+    // and everything derived from it (slot base, barrier id, mbarrier addresses) on the uniform datapath, out of the way of the
+    // 120 vector registers, instead of being recomputed from %tid.y in every block row
+    if (W % 32 == 0) g = (int)__reduce_max_sync(0xffffffffu, (unsigned)g);
+#if QL_S_UNIFORM_G > 1
+    // same for the warp's index inside its group: i = 32 * (uniform) + lane lets per-thread addresses split into a uniform base
+    // and a lane offset
+    if (W % 32 == 0) i = 32 * (int)__reduce_max_sync(0xffffffffu, (unsigned)(i >> 5)) + (i & 31);
+#endif
+#endif
     const int lane = i & 31, wis = i >> 5;
     const int bar_id = 1 + g;
 

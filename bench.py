@@ -37,12 +37,12 @@ MAX_ITER = 10
 NORM = 0.75
 # figures of the committed ncu capture of the decode kernel (profiles/r1_v7_layered_i8s_ncu_summary.txt)
 MSG_SCRATCH_BYTES_PER_FRAME = 81 * 96 * 16          # 81 16-byte message blocks per thread, 96 threads (BG1 Z=384)
-NCU_DRAM_BYTES_PER_FRAME = 183.9e3                   # dram__bytes_read + write per frame (message scratch share held in L2: ~half)
+NCU_DRAM_BYTES_PER_FRAME = 186.2e3                   # dram__bytes_read + write per frame (message scratch share held in L2: ~half)
 NCU_TRAFFIC_SOURCE = "profiles/r1_v7_layered_i8s_ncu_summary.txt (ncu --set full, 14800 frames, scaled per frame)"
-NCU_ALU_PIPE_PCT = 54.8
+NCU_ALU_PIPE_PCT = 55.7
 SMEM_PEAK_GBPS = 37060.0                              # shared-memory loads, all SMs (profiles/r1_onchip_peaks.json)
 L2_PEAK_GBPS = 17600.0                                # L2 reads over a 64 MB buffer (same file)
-NCU_ISSUE_ACTIVE_PCT = 64.4
+NCU_ISSUE_ACTIVE_PCT = 65.0
 
 
 def parse_args():

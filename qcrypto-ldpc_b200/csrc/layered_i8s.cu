@@ -90,6 +90,9 @@
 #ifndef QL_S_UNIFORM_G
 #define QL_S_UNIFORM_G 1
 #endif
+#ifndef QL_S_HOTCHAIN
+#define QL_S_HOTCHAIN 0
+#endif
 #ifndef QL_S_FMACLIP8
 #define QL_S_FMACLIP8 0              // belief clip (upper bound) on the FMA pipe
 #endif
@@ -457,6 +460,19 @@ __device__ __forceinline__ void dispatch_row(int variant, const Cx &cx, char *Li
 #define QL_ROW(DCV, EXACTV, EXTV, BIGV) \
     process_row<NK, DCV, EXACTV, EXTV, (BIGV ? QL_S_BIGMODE : (DCV > QL_S_KEEPT ? 1 : 0)), FIRST>(cx, Li, erow, thr4, nc, i, m1init, ysrc, ystride, gdst, \
                                                                                 W, extb, hd_ext)
+#if QL_S_HOTCHAIN
+    // the four shapes that make up 36 of BG1's 46 block rows (3..6 core edges + the extension edge) are tested with plain
+    // compare-and-branch before the jump table (an indexed constant load + indirect branch per row); the copy of `variant`
+    // is opaque so that the compiler does not fold the chain back into the switch
+    {
+        int v2 = variant;
+        asm volatile("" : "+r"(v2));
+        if (v2 == 7) { QL_ROW(4, true, true, false); return; }
+        if (v2 == 9) { QL_ROW(5, true, true, false); return; }
+        if (v2 == 5) { QL_ROW(3, true, true, false); return; }
+        if (v2 == 11) { QL_ROW(6, true, true, false); return; }
+    }
+#endif
     switch (variant) {
 #ifndef QL_S_NOSMALL
     case 0: QL_ROW(1, true, false, false); break;
@@ -464,13 +480,21 @@ __device__ __forceinline__ void dispatch_row(int variant, const Cx &cx, char *Li
     case 2: QL_ROW(2, true, false, false); break;
     case 3: QL_ROW(2, true, true, false); break;
     case 4: QL_ROW(3, true, false, false); break;
+#if !QL_S_HOTCHAIN
     case 5: QL_ROW(3, true, true, false); break;
+#endif
     case 6: QL_ROW(4, true, false, false); break;
+#if !QL_S_HOTCHAIN
     case 7: QL_ROW(4, true, true, false); break;
+#endif
     case 8: QL_ROW(5, true, false, false); break;
+#if !QL_S_HOTCHAIN
     case 9: QL_ROW(5, true, true, false); break;
+#endif
     case 10: QL_ROW(6, true, false, false); break;
+#if !QL_S_HOTCHAIN
     case 11: QL_ROW(6, true, true, false); break;
+#endif
     case 12: QL_ROW(7, true, false, false); break;
     case 13: QL_ROW(7, true, true, false); break;
     case 14: QL_ROW(8, true, false, false); break;

@@ -90,6 +90,9 @@
 #ifndef QL_S_UNIFORM_G
 #define QL_S_UNIFORM_G 1
 #endif
+#ifndef QL_S_ROTSTAGE
+#define QL_S_ROTSTAGE 0
+#endif
 #ifndef QL_S_HOTCHAIN
 #define QL_S_HOTCHAIN 0
 #endif
@@ -669,6 +672,22 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
         if (i == ext_thread && ext_bytes) bulk_g2s(slot_saddr + p.off_ext + st * Z, frame + es, ext_bytes, mb);
     };
 
+#if QL_S_ROTSTAGE
+    auto stage_row_any = [&](int rn, bool with_msgs, u32 trip, const int8_t *frame) {   // the caller elected ONE thread
+        const int4 na = *reinterpret_cast<const int4 *>(rowsc + 32 * rn);
+        const int es = *reinterpret_cast<const int *>(rowsc + 32 * rn + 16);
+        const u32 st = trip & 1u;
+        const u32 mb = mb_full + 8 * st;
+        const u32 msg_bytes = with_msgs ? (u32)(((na.w >> 8) & 0xff) * W * 16) : 0u;
+        const u32 ext_bytes = es >= 0 ? (u32)Z : 0u;
+        if (msg_bytes + ext_bytes) mbar_arrive_tx(mb, msg_bytes + ext_bytes);
+        else mbar_arrive(mb);
+        if (msg_bytes) bulk_g2s(slot_saddr + p.off_ring + st * p.stage_bytes, rg_slot + na.z, msg_bytes, mb);
+        if (ext_bytes) bulk_g2s(slot_saddr + p.off_ext + st * Z, frame + es, ext_bytes, mb);
+    };
+    int rot = 0;
+#endif
+
     // Frame prefetch (when the slot has room for it, p.off_stg >= 0): the raw LLR bytes of the core columns of the slot's
     // NEXT frame are bulk-copied into a staging buffer while the current frame is decoded, so that the frame switch --
     // which every other group of the CTA waits for at the iteration barrier -- is a shared-memory transpose instead of
@@ -789,7 +808,14 @@ __global__ void __launch_bounds__(QL_S_MAXTHREADS, 1) layered_i8s_kernel(const L
                 const int4 lb = *reinterpret_cast<const int4 *>(rowsc + 32 * r + 16);   // ext_src, ext_hd, syn_off, deg
                 const u32 stage = tt & 1u;
                 QL_BEL_WAIT();   // every belief update of the previous row is visible
+#if QL_S_ROTSTAGE
+                // the staging duty (30 instructions with one active lane) rotates over the warps of the group, so that no warp
+                // is the slow one at every row barrier
+                if (lane == 0 && wis == rot && r + 1 < R) stage_row_any(r + 1, it > 0, tt + 1, frame);
+                rot = (rot + 1 == W / 32) ? 0 : rot + 1;
+#else
                 if ((i == 0 || i == ext_thread) && r + 1 < R) stage_row(r + 1, it > 0, tt + 1, frame);
+#endif
                 uint2 m1init = make_uint2(kInf2, kInf2);   // initial (min1, sign) of the two half2 pairs
                 if (has_syn) {
                     const u32 *sr = synl + r * ZW32 + wis;

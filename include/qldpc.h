@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define QLDPC_VERSION 100
+#define QLDPC_VERSION 200
 
 /* error codes */
 enum {
@@ -69,6 +69,16 @@ enum { QLDPC_SCHED_FLOODING = 0, QLDPC_SCHED_LAYERED = 1 };
 enum { QLDPC_RULE_SPA = 0, QLDPC_RULE_NMS = 1, QLDPC_RULE_OMS = 2 };
 enum { QLDPC_DTYPE_F32 = 0, QLDPC_DTYPE_I16 = 1, QLDPC_DTYPE_I8 = 2 };
 enum { QLDPC_OUT_INFO = 0, QLDPC_OUT_ALL = 1 };
+
+#define QLDPC_MAX_DEVICES 8
+/* decoder flags */
+#define QLDPC_FLAG_L2_PERSIST     1u  /* int8 layered decoder for Z % 128 == 0: keep the check-to-variable message scratch
+                                         resident in L2.  OPT-IN because it has side effects outside the decoder: creation raises
+                                         the device-wide cudaLimitPersistingL2CacheSize and the decode calls set
+                                         cudaStreamAttributeAccessPolicyWindow on the stream they run on.                */
+#define QLDPC_FLAG_LI8_RESIDENT   2u  /* diagnostics: int8 layered decoding on the previous-generation kernel (layered_i8.cu)  */
+#define QLDPC_FLAG_LI8_STREAM     4u  /*   with its messages resident in shared memory / streamed through an L2 scratch   */
+#define QLDPC_FLAG_NO_FUSED_BITS  8u  /* diagnostics: qldpc_decode_bits runs LLR synthesis and decoding as two kernels      */
 
 typedef struct qldpc_code qldpc_code;
 typedef struct qldpc_decoder qldpc_decoder;
@@ -113,7 +123,15 @@ typedef struct qldpc_decoder_config {
     int32_t app_max;         /* integer dtypes, layered: beliefs clipped to [-(app_max+1), app_max];
                                 0 = default (127 for i8 = maxqL, BPSK_nrldpc_sim_FP.m:5; 8191 for i16) */
     int32_t out_mode;        /* QLDPC_OUT_INFO: k info bits per frame; QLDPC_OUT_ALL: n bits   */
-    int32_t device;          /* CUDA device ordinal                                            */
+    int32_t device;          /* CUDA device ordinal (used when n_devices <= 1)                 */
+    /* Frames are independent (AFF3CT n_frames semantics; ML/BPSK_nrldpc_sim_RM_FP.m:27 `parfor`): with n_devices > 1 the
+     * HOST-pointer entry points (qldpc_decode, qldpc_decode_bits, qldpc_syndrome, qldpc_make_llr, qldpc_encode_nr) cut the
+     * batch into contiguous frame ranges, one per device, each driven by its own host thread and stream pair; statistics
+     * are summed on the host (qldpc_get_stats).  No collective, no peer access.  The *_device entry points take pointers
+     * of ONE device and return QLDPC_ERR_UNSUPPORTED on such a decoder. */
+    int32_t n_devices;       /* 0 or 1: `device` only; 2..QLDPC_MAX_DEVICES: devices[0..n_devices)             */
+    int32_t devices[QLDPC_MAX_DEVICES];
+    uint32_t flags;          /* QLDPC_FLAG_* */
 } qldpc_decoder_config;
 
 void qldpc_decoder_config_default(qldpc_decoder_config *cfg);
@@ -139,9 +157,7 @@ int32_t qldpc_codeword_words(const qldpc_decoder *dec);  /* ceil(n/32)          
  * returns without synchronising.
  * Concurrency: a decoder owns one set of device scratch buffers, so at most one qldpc_decode_device call per decoder may be
  * in flight at a time (use one decoder per stream); the host-pointer calls are self-contained and synchronise before
- * returning.  Side effects of the int8 layered decoders for Z % 128 == 0: decoder creation raises the device-wide
- * cudaLimitPersistingL2CacheSize (the message scratch is kept resident in L2; QLDPC_L2_PERSIST=0 in the environment leaves
- * the limit alone) and qldpc_decode_device sets cudaStreamAttributeAccessPolicyWindow on `cuda_stream` to that scratch.
+ * returning.  The library changes no device-wide state unless QLDPC_FLAG_L2_PERSIST is set in the configuration.
  */
 int qldpc_decode(qldpc_decoder *dec, const void *llr, const uint32_t *syndrome, int32_t n_frames,
                  uint32_t *out_bits, uint8_t *ok, uint16_t *iters, void *posterior);
@@ -171,6 +187,10 @@ int qldpc_make_llr_device(qldpc_decoder *dec, const uint32_t *d_bits, const uint
  * Fused LLR synthesis + decode for callers that hold sifted-key bits (what an ecd2 LDPC handler has in
  * pb->mainBufPtr, MSB-first words): only n/8 bytes per frame cross the bus instead of n LLR values.
  * Arguments as in qldpc_make_llr followed by qldpc_decode; results are identical to calling the two.
+ * On the int8 layered decoder for Z % 128 == 0 the synthesis happens INSIDE the decoder kernel (the frame's bits are
+ * bulk-copied to shared memory, +-magnitude bytes are formed there): no LLR array exists in device memory.
+ * Integer dtypes: llr_noisy / llr_known are rounded to the nearest integer and must lie in [0, 127] (int8) or
+ * [0, 32767] (int16), else QLDPC_ERR_ARG.
  */
 int qldpc_decode_bits(qldpc_decoder *dec, const uint32_t *bits, const uint32_t *known_mask, const uint32_t *punct_mask,
                       float llr_noisy, float llr_known, const uint32_t *syndrome, int32_t n_frames,

@@ -24,6 +24,8 @@ RULE_SPA, RULE_NMS, RULE_OMS = 0, 1, 2
 DTYPE_F32, DTYPE_I16, DTYPE_I8 = 0, 1, 2
 OUT_INFO, OUT_ALL = 0, 1
 ITER_HIST_BINS = 64
+MAX_DEVICES = 8
+FLAG_L2_PERSIST, FLAG_LI8_RESIDENT, FLAG_LI8_STREAM, FLAG_NO_FUSED_BITS = 1, 2, 4, 8
 
 _NP_DTYPE = {DTYPE_F32: np.float32, DTYPE_I16: np.int16, DTYPE_I8: np.int8}
 
@@ -57,7 +59,7 @@ class DecoderConfig(C.Structure):
     _fields_ = [("schedule", C.c_int32), ("rule", C.c_int32), ("dtype", C.c_int32), ("max_iter", C.c_int32),
                 ("early_stop", C.c_int32), ("syndrome_depth", C.c_int32), ("norm_factor", C.c_float),
                 ("offset", C.c_float), ("msg_max", C.c_int32), ("app_max", C.c_int32), ("out_mode", C.c_int32),
-                ("device", C.c_int32)]
+                ("device", C.c_int32), ("n_devices", C.c_int32), ("devices", C.c_int32 * MAX_DEVICES), ("flags", C.c_uint32)]
 
 
 class Stats(C.Structure):
@@ -187,13 +189,21 @@ class Decoder:
     """Batched decoder bound to one CUDA device (qldpc_decoder_create)."""
 
     def __init__(self, code, schedule=SCHED_FLOODING, rule=RULE_SPA, dtype=DTYPE_F32, max_iter=100, early_stop=True,
-                 syndrome_depth=1, norm_factor=1.0, offset=0.0, msg_max=0, app_max=0, out_mode=OUT_INFO, device=0):
+                 syndrome_depth=1, norm_factor=1.0, offset=0.0, msg_max=0, app_max=0, out_mode=OUT_INFO, device=0,
+                 devices=None, flags=0):
+        """devices: list of CUDA ordinals -> one multi-device decoder whose host-buffer calls shard the frames over them
+        (qldpc_decoder_config.devices); flags: FLAG_* bits"""
         cfg = DecoderConfig()
         lib().qldpc_decoder_config_default(C.byref(cfg))
         cfg.schedule, cfg.rule, cfg.dtype, cfg.max_iter = schedule, rule, dtype, max_iter
         cfg.early_stop, cfg.syndrome_depth = int(early_stop), syndrome_depth
         cfg.norm_factor, cfg.offset, cfg.msg_max, cfg.app_max = norm_factor, offset, msg_max, app_max
         cfg.out_mode, cfg.device = out_mode, device
+        cfg.flags = flags
+        if devices is not None:
+            cfg.n_devices = len(devices)
+            for k, dv in enumerate(devices):
+                cfg.devices[k] = dv
         self.cfg = cfg
         self.code = code
         self.h = C.c_void_p()

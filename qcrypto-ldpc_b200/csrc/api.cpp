@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
 
 #include "kernels.hpp"
 
@@ -83,10 +84,9 @@ int build_qc_tables(qldpc_decoder *d)
 // the kernel's assumptions (the caller then uses the generic kernel).
 bool plan_layered_i8(qldpc_decoder *d, LayeredI8Params &p, bool upload)
 {
-    // QLDPC_LI8_MODE=resident|stream overrides the automatic choice (kernel experiments)
-    const char *mode_env = std::getenv("QLDPC_LI8_MODE");
-    const bool force_stream = mode_env && std::strcmp(mode_env, "stream") == 0;
-    const bool force_resident = mode_env && std::strcmp(mode_env, "resident") == 0;
+    // QLDPC_FLAG_LI8_RESIDENT / _STREAM override the automatic choice of the message placement (parity tests of both)
+    const bool force_stream = (d->cfg.flags & QLDPC_FLAG_LI8_STREAM) != 0;
+    const bool force_resident = (d->cfg.flags & QLDPC_FLAG_LI8_RESIDENT) != 0;
     const HostCode &c = d->code;
     if (c.z <= 0 || c.z % 4 != 0 || c.max_chk_degree > 20 || d->cfg.max_iter < 1) return false;
     const int W = c.z / 4, ZW32 = (c.z + 31) / 32;
@@ -187,8 +187,7 @@ bool plan_layered_i8(qldpc_decoder *d, LayeredI8Params &p, bool upload)
     bool stream = slots_str > slots_res;
     if (force_stream && slots_str >= 1) stream = true;
     if (force_resident && slots_res >= 1) stream = false;
-    int slots = stream ? slots_str : slots_res;
-    if (const char *cap = std::getenv("QLDPC_LI8_SLOTS")) slots = std::min(slots, std::max(1, std::atoi(cap)));   // experiments
+    const int slots = stream ? slots_str : slots_res;
     if (slots < 1) return false;
     if (stream) {   // no register rows in streamed mode: every row's messages go through the ring
         regdc = 0;
@@ -225,8 +224,7 @@ bool plan_layered_i8(qldpc_decoder *d, LayeredI8Params &p, bool upload)
 // does not fit its assumptions (the caller then tries the older layered_i8 kernel).
 bool plan_layered_i8s(qldpc_decoder *d)
 {
-    if (const char *mode_env = std::getenv("QLDPC_LI8_MODE"))
-        if (std::strcmp(mode_env, "resident") == 0 || std::strcmp(mode_env, "stream") == 0) return false;
+    if (d->cfg.flags & (QLDPC_FLAG_LI8_RESIDENT | QLDPC_FLAG_LI8_STREAM)) return false;
     const HostCode &c = d->code;
     if (c.z <= 0 || c.z % 128 != 0 || d->cfg.max_iter < 1) return false;
     const int Z = c.z, W = Z / 4, ZW32 = Z / 32;
@@ -312,14 +310,12 @@ bool plan_layered_i8s(qldpc_decoder *d)
     geo.slot_bytes[0] = geo.off_mbar[0] + 32;
     geo.slot_bytes[1] = geo.off_mbar[1] + 32;
     const int avail = d->max_smem_optin - geo.tab_bytes - kLi8sSlotBase;
-    const bool want_stg = !std::getenv("QLDPC_LI8_NOSTAGE");
     for (int k = 0; k < 2; ++k) {
-        int slots = std::min(std::min(avail / geo.slot_bytes[k], layered_i8s_max_threads() / W), 15);
-        if (const char *cap = std::getenv("QLDPC_LI8_SLOTS")) slots = std::min(slots, std::max(1, std::atoi(cap)));   // experiments
+        const int slots = std::min(std::min(avail / geo.slot_bytes[k], layered_i8s_max_threads() / W), 15);
         geo.slots[k] = slots;
         // frame-prefetch staging buffer, if it fits without giving up a frame slot
         const int with_stg = geo.slot_bytes[k] + L_bytes;
-        if (want_stg && slots >= 1 && avail / with_stg >= slots) {
+        if (slots >= 1 && avail / with_stg >= slots) {
             geo.off_stg[k] = geo.slot_bytes[k];
             geo.slot_bytes[k] = with_stg;
         }
@@ -451,8 +447,13 @@ extern "C" void qldpc_decoder_config_default(qldpc_decoder_config *cfg)
 }
 
 struct qldpc_decoder_full : qldpc_decoder {
+    // n_devices > 1: this object only holds one complete single-device decoder per device; the host-pointer entry
+    // points shard the frames over them, one host thread each
+    std::vector<qldpc_decoder *> children;
     qldpc_decoder_lanes lanes;
     DevBuf<uint8_t> d_llr_tmp;          // LLRs synthesised by qldpc_decode_bits_device
+    DevBuf<uint8_t> d_mag;              // bit input of the streamed int8 kernel: 2 x n magnitudes (host pipeline / device call)
+    DevBuf<int8_t> d_ext;               // ... and the slots' extension-column LLRs, 2 lanes x SMs x slots x n bytes
     DevBuf<int32_t> d_base;
     DevBuf<uint32_t> d_mask_known, d_mask_punct, d_tmp_bits;
     size_t scratch_msg_bytes = 0, scratch_app_bytes = 0;
@@ -462,6 +463,38 @@ struct qldpc_decoder_full : qldpc_decoder {
 };
 
 static qldpc_decoder_full *full(qldpc_decoder *d) { return static_cast<qldpc_decoder_full *>(d); }
+
+// Frame sharding of a multi-device decoder: child g takes frames [g*F/G, (g+1)*F/G), each call on its own host thread
+// (every child owns its device, streams and staging buffers, so the calls share nothing).  `fn(child, first, count)`.
+template <typename Fn>
+static int shard_frames(qldpc_decoder_full *d, int n_frames, Fn fn)
+{
+    const int G = (int)d->children.size();
+    std::vector<int> rc(G, QLDPC_OK);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; ++g) {
+        const int f0 = (int)((long long)n_frames * g / G), f1 = (int)((long long)n_frames * (g + 1) / G);
+        if (f1 > f0) th.emplace_back([&, g, f0, f1] { rc[g] = fn(d->children[g], f0, f1 - f0); });
+    }
+    for (auto &t : th) t.join();
+    for (int g = 0; g < G; ++g)
+        if (rc[g]) return rc[g];
+    return QLDPC_OK;
+}
+
+// the kernels of the int8 layered family write the information bits themselves when they are whole leading block columns
+static bool li8_direct_out(const qldpc_decoder *d)
+{
+    return d->cfg.out_mode == QLDPC_OUT_ALL || (d->info_is_prefix && d->code.z > 0 && d->code.k % d->code.z == 0);
+}
+
+// integer LLR magnitudes of the bit-input entry points: rounded to the nearest integer, inside the dtype's range
+static bool llr_mags_ok(int dtype, float noisy, float known)
+{
+    if (dtype == QLDPC_DTYPE_F32) return true;
+    const float hi = dtype == QLDPC_DTYPE_I8 ? 127.0f : 32767.0f;
+    return noisy >= 0.0f && known >= 0.0f && lrintf(noisy) <= hi && lrintf(known) <= hi;
+}
 
 extern "C" int qldpc_decoder_create(const qldpc_code *code, const qldpc_decoder_config *cfg, qldpc_decoder **out)
 {
@@ -474,19 +507,50 @@ extern "C" int qldpc_decoder_create(const qldpc_code *code, const qldpc_decoder_
     const bool is_int = cfg->dtype != QLDPC_DTYPE_F32;
     if (is_int && cfg->rule == QLDPC_RULE_SPA) return QLDPC_ERR_UNSUPPORTED;   // SPA is float only (as in AFF3CT)
     if (cfg->schedule == QLDPC_SCHED_LAYERED && code->h.z <= 0) return QLDPC_ERR_UNSUPPORTED;
+    if (cfg->n_devices < 0 || cfg->n_devices > QLDPC_MAX_DEVICES) return QLDPC_ERR_ARG;
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return QLDPC_ERR_NO_DEVICE; }
-    if (cfg->device < 0 || cfg->device >= ndev) return QLDPC_ERR_ARG;
-    QLDPC_CUDA(cudaSetDevice(cfg->device));
+    if (cfg->n_devices > 1) {   // one complete decoder per device; this object shards the host-pointer calls over them
+        for (int g = 0; g < cfg->n_devices; ++g) {
+            if (cfg->devices[g] < 0 || cfg->devices[g] >= ndev) return QLDPC_ERR_ARG;
+            for (int h = 0; h < g; ++h)
+                if (cfg->devices[h] == cfg->devices[g]) return QLDPC_ERR_ARG;
+        }
+        qldpc_decoder_full *par = new (std::nothrow) qldpc_decoder_full();
+        if (!par) return QLDPC_ERR_NOMEM;
+        for (int g = 0; g < cfg->n_devices; ++g) {
+            qldpc_decoder_config cc = *cfg;
+            cc.n_devices = 0;
+            cc.device = cfg->devices[g];
+            qldpc_decoder *child = nullptr;
+            const int rc = qldpc_decoder_create(code, &cc, &child);
+            if (rc) { qldpc_decoder_free(par); return rc; }
+            par->children.push_back(child);
+        }
+        const qldpc_decoder *c0 = par->children[0];
+        par->code = c0->code;
+        par->cfg = *cfg;
+        par->kernel_family = c0->kernel_family;
+        par->kernel_name = c0->kernel_name;
+        par->out_words = c0->out_words; par->syn_words = c0->syn_words; par->cw_words = c0->cw_words; par->out_bits = c0->out_bits;
+        par->info_is_prefix = c0->info_is_prefix;
+        *out = par;
+        return QLDPC_OK;
+    }
+    const int device = cfg->n_devices == 1 ? cfg->devices[0] : cfg->device;
+    if (device < 0 || device >= ndev) return QLDPC_ERR_ARG;
+    QLDPC_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
-    QLDPC_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    QLDPC_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return QLDPC_ERR_NO_DEVICE;   // kernels are built for sm_100a only
 
     qldpc_decoder_full *d = new (std::nothrow) qldpc_decoder_full();
     if (!d) return QLDPC_ERR_NOMEM;
     d->code = code->h;
     d->cfg = *cfg;
+    d->cfg.device = device;
+    d->cfg.n_devices = 0;
     if (d->cfg.syndrome_depth < 1) d->cfg.syndrome_depth = 1;
     d->sm_count = prop.multiProcessorCount;
     d->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
@@ -538,10 +602,10 @@ extern "C" int qldpc_decoder_create(const qldpc_code *code, const qldpc_decoder_
         const bool fast_s = i8_ok && plan_layered_i8s(d);
         const bool fast = !fast_s && i8_ok && plan_layered_i8(d, p, true);
         if (fast_s) {
-            {   // L2 set-aside for the message scratch: the streamed LLRs would otherwise evict it (ncu: DRAM traffic halves).
-                // This is a device-wide limit of the CUDA context; QLDPC_L2_PERSIST=<MiB> overrides, 0 leaves it alone.
-                size_t want = (size_t)d->sm_count * d->li8s_geo.slots[0] * d->li8s_geo.rg_u4 * 16;
-                if (const char *e = std::getenv("QLDPC_L2_PERSIST")) want = (size_t)std::max(0, std::atoi(e)) << 20;
+            if (cfg->flags & QLDPC_FLAG_L2_PERSIST) {
+                // L2 set-aside for the message scratch: the streamed LLRs would otherwise evict it (ncu: DRAM traffic halves).
+                // This is a device-wide limit of the CUDA context, hence opt-in.
+                const size_t want = (size_t)d->sm_count * d->li8s_geo.slots[0] * d->li8s_geo.rg_u4 * 16;
                 const size_t lim = std::min<size_t>(want, (size_t)prop.persistingL2CacheMaxSize);
                 if (lim > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, lim) == cudaSuccess) {
                     d->l2_persist_bytes = lim;
@@ -570,7 +634,7 @@ extern "C" int qldpc_decoder_create(const qldpc_code *code, const qldpc_decoder_
         // quasi-cyclic codes, float min-sum: the circulant-aware kernel (lanes on consecutive threads, no index gathers, the
         // early-termination test fused into the check phase): 6.9 vs 6.1 Gbit/s on the N=65536 code.  SPA stays on the CSR
         // kernel: it is bound by the double-precision tanh/atanh, and the fused test costs it one extra check phase.
-        d->flood_qc = c.z > 0 && cfg->dtype == QLDPC_DTYPE_F32 && cfg->rule != QLDPC_RULE_SPA && !std::getenv("QLDPC_FLOOD_CSR");
+        d->flood_qc = c.z > 0 && cfg->dtype == QLDPC_DTYPE_F32 && cfg->rule != QLDPC_RULE_SPA;
         if (d->flood_qc) d->kernel_name = "flooding_qc";
         const size_t need = (size_t)(c.edges + c.n) * 4;
         d->flood_use_smem = need + 1024 <= (size_t)d->max_smem_optin;
@@ -594,6 +658,11 @@ extern "C" void qldpc_decoder_free(qldpc_decoder *dec)
 {
     if (!dec) return;
     qldpc_decoder_full *d = full(dec);
+    if (!d->children.empty() || d->cfg.n_devices > 1) {
+        for (qldpc_decoder *c : d->children) qldpc_decoder_free(c);
+        delete d;
+        return;
+    }
     cudaSetDevice(d->cfg.device);
     cudaDeviceSynchronize();
     for (auto &ln : d->lanes.lane)
@@ -616,16 +685,27 @@ static int ensure_scratch(qldpc_decoder_full *d)
     return QLDPC_OK;
 }
 
+// Bit input of the streamed int8 kernel (LLR synthesis inside the decoder): needs the frame-prefetch staging buffer of the
+// slot geometry in use and 16-byte aligned bits (bulk copies); n % 128 == 0 holds for every code the kernel takes.
+static bool fused_bits_ok(const qldpc_decoder_full *d, const uint32_t *d_bits, bool with_syndrome)
+{
+    return d->kernel_family == KF_LAYERED_I8S && !(d->cfg.flags & QLDPC_FLAG_NO_FUSED_BITS) &&
+           d->li8s_geo.off_stg[with_syndrome ? 1 : 0] >= 0 && (reinterpret_cast<uintptr_t>(d_bits) & 15) == 0;
+}
+
 // scratch_lane: which copy of the streamed-message scratch to use. Launches that may overlap in time (the two
 // streams of the host-pointer pipelines) MUST use different copies; the public device entry point uses copy 0,
 // so a decoder supports one qldpc_decode_device call in flight at a time.
+// d_bits / d_mag (both or neither): bit input of the streamed int8 kernel instead of d_llr (see fused_bits_ok).
 static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint32_t *d_syndrome, int32_t n_frames,
                               uint32_t *d_out_bits, uint8_t *d_ok, uint16_t *d_iters, void *d_posterior,
-                              void *cuda_stream, int scratch_lane)
+                              void *cuda_stream, int scratch_lane, const uint32_t *d_bits = nullptr,
+                              const uint8_t *d_mag = nullptr)
 {
-    if (!dec || !d_llr || !d_out_bits || n_frames < 0) return QLDPC_ERR_ARG;
+    if (!dec || (!d_llr && !d_bits) || !d_out_bits || n_frames < 0) return QLDPC_ERR_ARG;
     if (n_frames == 0) return QLDPC_OK;
     qldpc_decoder_full *d = full(dec);
+    if (!d->children.empty()) return QLDPC_ERR_UNSUPPORTED;   // device pointers belong to one device
     const HostCode &c = d->code;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     QLDPC_CUDA(cudaSetDevice(d->cfg.device));
@@ -634,16 +714,25 @@ static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint3
 
     int family = d->kernel_family;
     if ((family == KF_LAYERED_I8 || family == KF_LAYERED_I8S) && d_posterior) family = KF_LAYERED_GENERIC;
-    if (family == KF_LAYERED_I8S && (reinterpret_cast<uintptr_t>(d_llr) & 15) != 0) family = KF_LAYERED_GENERIC;   // cp.async staging
+    if (family == KF_LAYERED_I8S && (reinterpret_cast<uintptr_t>(d_llr) & 15) != 0) family = KF_LAYERED_GENERIC;   // bulk-copy staging
+    if (d_bits && family != KF_LAYERED_I8S) return QLDPC_ERR_ARG;
 
     if (family == KF_LAYERED_I8S) {
         const Li8sGeo &geo = d->li8s_geo;
         const int k = d_syndrome ? 1 : 0;
         LayeredI8sParams p{};
-        const bool direct = cfg.out_mode == QLDPC_OUT_ALL || d->info_is_prefix;
+        const bool direct = li8_direct_out(d);
         if (!direct)
             if ((rc = d->d_allbits.ensure((size_t)n_frames * d->cw_words))) return rc;
         p.llr = (const int8_t *)d_llr;
+        if (d_bits) {
+            const size_t lane_ext = (size_t)d->sm_count * std::max(geo.slots[0], geo.slots[1]) * c.n;
+            if ((rc = d->d_ext.ensure(2 * lane_ext))) return rc;
+            p.llr = nullptr;
+            p.bits = d_bits;
+            p.mag = d_mag;
+            p.ext_scratch = d->d_ext.p + (size_t)scratch_lane * lane_ext;
+        }
         p.syn = d_syndrome;
         p.out = direct ? d_out_bits : d->d_allbits.p;
         p.ok = d_ok; p.iters = d_iters; p.stats = d->d_stats.p;
@@ -652,7 +741,7 @@ static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint3
         p.Z = c.z; p.W = c.z / 4; p.ZW32 = c.z / 32;
         p.brows = c.base_rows; p.bcols = c.base_cols; p.N = c.n;
         p.n_pack = geo.n_pack;
-        p.out_cols = (direct && cfg.out_mode == QLDPC_OUT_INFO) ? c.base_cols - c.base_rows : c.base_cols;
+        p.out_cols = (direct && cfg.out_mode == QLDPC_OUT_INFO) ? c.k / c.z : c.base_cols;
         p.out_words = p.out_cols * p.ZW32;
         p.syn_words = d->syn_words;
         p.max_iter = cfg.max_iter; p.early_stop = cfg.early_stop;
@@ -676,9 +765,8 @@ static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint3
         p.rg = d->d_li8s_rg.p + (size_t)scratch_lane * lane_u4;
         // frame queue: with early termination the frames of a slot take 1..max_iter iterations each, and a fixed
         // f, f + grid*slots, ... assignment leaves the slots that drew the easy frames idle at the end of the launch
-        static const bool static_frames = std::getenv("QLDPC_LI8_STATIC") != nullptr;
         p.frame_ctr = nullptr;
-        if (!static_frames && n_frames > grid * p.slots) {
+        if (n_frames > grid * p.slots) {
             p.frame_ctr = reinterpret_cast<unsigned int *>(d->d_li8s_rg.p + 2 * lane_u4 + scratch_lane);
             QLDPC_CUDA(cudaMemsetAsync(p.frame_ctr, 0, sizeof(unsigned int), st));
         }
@@ -708,7 +796,7 @@ static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint3
     if (family == KF_LAYERED_I8) {
         LayeredI8Params p{};
         if (!plan_layered_i8(d, p, false)) return QLDPC_ERR_UNSUPPORTED;
-        const bool direct = cfg.out_mode == QLDPC_OUT_ALL || d->info_is_prefix;
+        const bool direct = li8_direct_out(d);
         if (!direct)
             if ((rc = d->d_allbits.ensure((size_t)n_frames * d->cw_words))) return rc;
         p.llr = (const int8_t *)d_llr;
@@ -717,7 +805,7 @@ static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint3
         p.ok = d_ok; p.iters = d_iters; p.stats = d->d_stats.p;
         p.edges = d->d_li8_edges.p; p.layers = d->d_li8_layers.p; p.aux = d->d_qc_aux.p; p.pack_cols = d->d_li8_pack_cols.p;
         p.F = n_frames;
-        p.out_cols = (direct && cfg.out_mode == QLDPC_OUT_INFO) ? c.base_cols - c.base_rows : c.base_cols;
+        p.out_cols = (direct && cfg.out_mode == QLDPC_OUT_INFO) ? c.k / c.z : c.base_cols;
         p.out_words = (p.out_cols * c.z + 31) / 32;
         p.syn_words = d->syn_words;
         p.max_iter = cfg.max_iter; p.early_stop = cfg.early_stop;
@@ -791,7 +879,7 @@ static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint3
         } else
         {
             int smem_bytes = d->flood_smem;
-            if (!d->flood_use_smem && cfg.dtype == QLDPC_DTYPE_F32 && cfg.rule == QLDPC_RULE_SPA && !std::getenv("QLDPC_NO_TANH_CACHE")) {
+            if (!d->flood_use_smem && cfg.dtype == QLDPC_DTYPE_F32 && cfg.rule == QLDPC_RULE_SPA) {
                 p.tanh_cache = 1;
                 smem_bytes = 8 * d->flood_block * 4;
             }
@@ -814,18 +902,13 @@ extern "C" int qldpc_decode_device(qldpc_decoder *dec, const void *d_llr, const 
     return decode_device_impl(dec, d_llr, d_syndrome, n_frames, d_out_bits, d_ok, d_iters, d_posterior, cuda_stream, 0);
 }
 
-// Chunk size of the host-pointer entry points: whole waves of the persistent grid (no ragged last wave), about
-// `target_bytes` of device input per chunk; QLDPC_CHUNK_FRAMES overrides (experiments).
 // Chunk schedule of the host-pointer entry points.  Chunks are whole waves of the persistent grid; they start small
 // (two waves: the first kernel starts after a 5 MB copy) and double up to about `target_bytes` of device input, so that
 // a large batch needs few launches (every launch ends with a partly idle wave) without paying for it in pipeline fill.
-// QLDPC_CHUNK_FRAMES forces one uniform size (experiments).
 struct ChunkPlan {
     int wave = 1, first = 1, max = 1;
-    bool uniform = false;
     int at(int idx) const
     {
-        if (uniform) return max;
         long long c = first;
         for (int k = 0; k < idx && c < max; ++k) c *= 2;
         return (int)std::min<long long>(c, max);
@@ -836,17 +919,9 @@ static ChunkPlan pick_chunk(const qldpc_decoder_full *d, size_t frame_bytes, siz
     ChunkPlan cp;
     cp.wave = d->sm_count * std::max(1, d->li8_slots);
     long long chunk = (long long)std::max<size_t>(1, target_bytes / frame_bytes);
-    if (const char *e = std::getenv("QLDPC_CHUNK_FRAMES")) { chunk = std::max(1, std::atoi(e)); cp.uniform = true; }
     chunk = std::max<long long>(cp.wave, (chunk + cp.wave / 2) / cp.wave * cp.wave);
     cp.max = (int)std::min<long long>(chunk, n_frames);
     cp.first = std::min(cp.max, 2 * cp.wave);
-    if (const char *e = std::getenv("QLDPC_CHUNK_PLAN")) {   // experiments: "first,max" in waves
-        int a = 2, b = 17;
-        if (std::sscanf(e, "%d,%d", &a, &b) == 2 && a >= 1 && b >= a) {
-            cp.max = (int)std::min<long long>((long long)b * cp.wave, n_frames);
-            cp.first = std::min(cp.max, a * cp.wave);
-        }
-    }
     return cp;
 }
 
@@ -859,15 +934,21 @@ extern "C" int qldpc_decode(qldpc_decoder *dec, const void *llr, const uint32_t 
     if (n_frames == 0) return QLDPC_OK;
     qldpc_decoder_full *d = full(dec);
     const HostCode &c = d->code;
-    QLDPC_CUDA(cudaSetDevice(d->cfg.device));
     const size_t esz = dtype_size(d->cfg.dtype);
     const size_t frame_in = (size_t)c.n * esz;
-    // chunk: ~64 MiB of LLRs, at least one wave of the persistent grid
+    if (!d->children.empty())
+        return shard_frames(d, n_frames, [&](qldpc_decoder *ch, int f0, int nf) {
+            return qldpc_decode(ch, (const char *)llr + (size_t)f0 * frame_in, syndrome ? syndrome + (size_t)f0 * d->syn_words : nullptr,
+                                nf, out_bits + (size_t)f0 * d->out_words, ok ? ok + f0 : nullptr, iters ? iters + f0 : nullptr,
+                                posterior ? (char *)posterior + (size_t)f0 * c.n * 4 : nullptr);
+        });
+    QLDPC_CUDA(cudaSetDevice(d->cfg.device));
+    // chunk: ~320 MiB of LLRs, at least one wave of the persistent grid
     const ChunkPlan plan = pick_chunk(d, frame_in, 320u << 20, n_frames);
     const int chunk = plan.max;
     // the scratch of the gather path is shared: those configurations run on one lane only
     const bool shared_scratch = !((d->kernel_family == KF_LAYERED_I8 || d->kernel_family == KF_LAYERED_I8S) && !posterior &&
-                                  (d->cfg.out_mode == QLDPC_OUT_ALL || d->info_is_prefix));
+                                  li8_direct_out(d));
     int rc = QLDPC_OK;
     for (auto &ln : d->lanes.lane) {
         if ((rc = ln.in.ensure((size_t)chunk * frame_in))) return rc;
@@ -911,9 +992,15 @@ extern "C" int qldpc_syndrome_device(qldpc_decoder *dec, const uint32_t *d_bits,
 {
     if (!dec || !d_bits || !d_syndrome || n_frames < 0) return QLDPC_ERR_ARG;
     qldpc_decoder_full *d = full(dec);
+    if (!d->children.empty()) return QLDPC_ERR_UNSUPPORTED;
     QLDPC_CUDA(cudaSetDevice(d->cfg.device));
-    const int rc = launch_syndrome_csr(d_bits, d_syndrome, n_frames, d->code.n, d->code.m, d->cw_words, d->syn_words,
-                                       d->d_row_ptr.p, d->d_col_idx.p, (cudaStream_t)cuda_stream);
+    const HostCode &c = d->code;
+    // quasi-cyclic codes with whole words per circulant: rotate + XOR of packed words; everything else: CSR bit gather
+    const int rc = (c.z > 0 && c.z % 32 == 0)
+                       ? launch_syndrome_qc(d_bits, d_syndrome, n_frames, c.base_rows, c.z, d->cw_words, d->syn_words,
+                                            d->d_qc_layers.p, d->d_qc_aux.p, (cudaStream_t)cuda_stream)
+                       : launch_syndrome_csr(d_bits, d_syndrome, n_frames, c.n, c.m, d->cw_words, d->syn_words, d->d_row_ptr.p,
+                                             d->d_col_idx.p, (cudaStream_t)cuda_stream);
     if (!rc && n_frames) d->kernel_launches++;
     return rc;
 }
@@ -923,6 +1010,10 @@ extern "C" int qldpc_syndrome(qldpc_decoder *dec, const uint32_t *bits, int32_t 
     if (!dec || !bits || !syndrome || n_frames < 0) return QLDPC_ERR_ARG;
     if (n_frames == 0) return QLDPC_OK;
     qldpc_decoder_full *d = full(dec);
+    if (!d->children.empty())
+        return shard_frames(d, n_frames, [&](qldpc_decoder *ch, int f0, int nf) {
+            return qldpc_syndrome(ch, bits + (size_t)f0 * d->cw_words, nf, syndrome + (size_t)f0 * d->syn_words);
+        });
     QLDPC_CUDA(cudaSetDevice(d->cfg.device));
     Lane &ln = d->lanes.lane[0];
     int rc;
@@ -941,6 +1032,8 @@ extern "C" int qldpc_make_llr_device(qldpc_decoder *dec, const uint32_t *d_bits,
 {
     if (!dec || !d_bits || !d_llr_out || n_frames < 0) return QLDPC_ERR_ARG;
     qldpc_decoder_full *d = full(dec);
+    if (!d->children.empty()) return QLDPC_ERR_UNSUPPORTED;
+    if (!llr_mags_ok(d->cfg.dtype, llr_noisy, llr_known)) return QLDPC_ERR_ARG;
     QLDPC_CUDA(cudaSetDevice(d->cfg.device));
     const int rc = launch_make_llr(d_bits, d_known_mask, d_punct_mask, llr_noisy, llr_known, n_frames, d->code.n,
                                    d->cw_words, d->cfg.dtype, d_llr_out, (cudaStream_t)cuda_stream);
@@ -954,9 +1047,15 @@ extern "C" int qldpc_make_llr(qldpc_decoder *dec, const uint32_t *bits, const ui
     if (!dec || !bits || !llr_out || n_frames < 0) return QLDPC_ERR_ARG;
     if (n_frames == 0) return QLDPC_OK;
     qldpc_decoder_full *d = full(dec);
+    const size_t esz = dtype_size(d->cfg.dtype);
+    if (!d->children.empty())
+        return shard_frames(d, n_frames, [&](qldpc_decoder *ch, int f0, int nf) {
+            return qldpc_make_llr(ch, bits + (size_t)f0 * d->cw_words, known_mask, punct_mask, llr_noisy, llr_known, nf,
+                                  (char *)llr_out + (size_t)f0 * d->code.n * esz);
+        });
+    if (!llr_mags_ok(d->cfg.dtype, llr_noisy, llr_known)) return QLDPC_ERR_ARG;
     QLDPC_CUDA(cudaSetDevice(d->cfg.device));
     Lane &ln = d->lanes.lane[0];
-    const size_t esz = dtype_size(d->cfg.dtype);
     int rc;
     if ((rc = d->d_tmp_bits.ensure((size_t)n_frames * d->cw_words))) return rc;
     if ((rc = ln.in.ensure((size_t)n_frames * d->code.n * esz))) return rc;
@@ -986,15 +1085,27 @@ extern "C" int qldpc_decode_bits_device(qldpc_decoder *dec, const uint32_t *d_bi
     if (!dec || !d_bits || !d_out_bits || n_frames < 0) return QLDPC_ERR_ARG;
     if (n_frames == 0) return QLDPC_OK;
     qldpc_decoder_full *d = full(dec);
+    if (!d->children.empty()) return QLDPC_ERR_UNSUPPORTED;
+    if (!llr_mags_ok(d->cfg.dtype, llr_noisy, llr_known)) return QLDPC_ERR_ARG;
     QLDPC_CUDA(cudaSetDevice(d->cfg.device));
     int rc;
+    if (fused_bits_ok(d, d_bits, d_syndrome != nullptr)) {   // LLR synthesis inside the decoder kernel: no LLR array at all
+        const int n = d->code.n;
+        if ((rc = d->d_mag.ensure(2 * (size_t)n))) return rc;
+        uint8_t *mag = d->d_mag.p + n;                       // second copy: the first belongs to the host-pointer pipeline
+        if ((rc = launch_make_mag_i8(d_known_mask, d_punct_mask, (int)lrintf(llr_noisy), (int)lrintf(llr_known), n, mag,
+                                     (cudaStream_t)cuda_stream))) return rc;
+        d->kernel_launches++;
+        return decode_device_impl(dec, nullptr, d_syndrome, n_frames, d_out_bits, d_ok, d_iters, nullptr, cuda_stream, 0, d_bits, mag);
+    }
     if ((rc = d->d_llr_tmp.ensure((size_t)n_frames * d->code.n * dtype_size(d->cfg.dtype)))) return rc;
     if ((rc = qldpc_make_llr_device(dec, d_bits, d_known_mask, d_punct_mask, llr_noisy, llr_known, n_frames, d->d_llr_tmp.p,
                                     cuda_stream))) return rc;
     return qldpc_decode_device(dec, d->d_llr_tmp.p, d_syndrome, n_frames, d_out_bits, d_ok, d_iters, nullptr, cuda_stream);
 }
 
-// Host-pointer version: packed bits in, packed bits out, chunks ping-pong over two streams.
+// Host-pointer version: packed bits in, packed bits out, chunks ping-pong over two streams.  With the streamed int8
+// kernel the chunks carry bits only (n/8 bytes per frame) and the kernel synthesises its LLRs itself.
 extern "C" int qldpc_decode_bits(qldpc_decoder *dec, const uint32_t *bits, const uint32_t *known_mask,
                                  const uint32_t *punct_mask, float llr_noisy, float llr_known, const uint32_t *syndrome,
                                  int32_t n_frames, uint32_t *out_bits, uint8_t *ok, uint16_t *iters)
@@ -1003,12 +1114,19 @@ extern "C" int qldpc_decode_bits(qldpc_decoder *dec, const uint32_t *bits, const
     if (n_frames == 0) return QLDPC_OK;
     qldpc_decoder_full *d = full(dec);
     const HostCode &c = d->code;
+    if (!d->children.empty())
+        return shard_frames(d, n_frames, [&](qldpc_decoder *ch, int f0, int nf) {
+            return qldpc_decode_bits(ch, bits + (size_t)f0 * d->cw_words, known_mask, punct_mask, llr_noisy, llr_known,
+                                     syndrome ? syndrome + (size_t)f0 * d->syn_words : nullptr, nf,
+                                     out_bits + (size_t)f0 * d->out_words, ok ? ok + f0 : nullptr, iters ? iters + f0 : nullptr);
+        });
+    if (!llr_mags_ok(d->cfg.dtype, llr_noisy, llr_known)) return QLDPC_ERR_ARG;
     QLDPC_CUDA(cudaSetDevice(d->cfg.device));
     const size_t esz = dtype_size(d->cfg.dtype);
     const size_t frame_llr = (size_t)c.n * esz;
     const ChunkPlan plan = pick_chunk(d, frame_llr, 320u << 20, n_frames);
     const int chunk = plan.max;
-    const bool shared_scratch = !((d->kernel_family == KF_LAYERED_I8 || d->kernel_family == KF_LAYERED_I8S) && (d->cfg.out_mode == QLDPC_OUT_ALL || d->info_is_prefix));
+    const bool shared_scratch = !((d->kernel_family == KF_LAYERED_I8 || d->kernel_family == KF_LAYERED_I8S) && li8_direct_out(d));
     int rc = QLDPC_OK;
     Lane &l0 = d->lanes.lane[0];
     const uint32_t *dk = nullptr, *dp = nullptr;
@@ -1022,9 +1140,18 @@ extern "C" int qldpc_decode_bits(qldpc_decoder *dec, const uint32_t *bits, const
         QLDPC_CUDA(cudaMemcpyAsync(d->d_mask_punct.p, punct_mask, (size_t)d->cw_words * 4, cudaMemcpyHostToDevice, l0.st));
         dp = d->d_mask_punct.p;
     }
-    QLDPC_CUDA(cudaStreamSynchronize(l0.st));   // masks are read by both lanes
+    // lane buffers are 16-byte aligned (cudaMalloc), chunks are whole frames of n/8 bytes with n % 128 == 0
+    const bool fused = fused_bits_ok(d, nullptr, syndrome != nullptr);
+    uint8_t *mag = nullptr;
+    if (fused) {
+        if ((rc = d->d_mag.ensure(2 * (size_t)c.n))) return rc;
+        mag = d->d_mag.p;
+        if ((rc = launch_make_mag_i8(dk, dp, (int)lrintf(llr_noisy), (int)lrintf(llr_known), c.n, mag, l0.st))) return rc;
+        d->kernel_launches++;
+    }
+    QLDPC_CUDA(cudaStreamSynchronize(l0.st));   // masks / magnitudes are read by both lanes
     for (auto &ln : d->lanes.lane) {
-        if ((rc = ln.in.ensure((size_t)chunk * frame_llr))) return rc;
+        if (!fused && (rc = ln.in.ensure((size_t)chunk * frame_llr))) return rc;
         if ((rc = ln.bits.ensure((size_t)chunk * d->cw_words))) return rc;
         if ((rc = ln.out.ensure((size_t)chunk * d->out_words))) return rc;
         if ((rc = ln.ok.ensure(chunk))) return rc;
@@ -1054,10 +1181,11 @@ extern "C" int qldpc_decode_bits(qldpc_decoder *dec, const uint32_t *bits, const
         if (syndrome)
             QLDPC_CUDA(cudaMemcpyAsync(ln.syn.p, syndrome + (size_t)f0 * d->syn_words, (size_t)nf * d->syn_words * 4,
                                        cudaMemcpyHostToDevice, ln.st));
-        if ((rc = qldpc_make_llr_device(dec, ln.bits.p, dk, dp, llr_noisy, llr_known, nf, ln.in.p, ln.st))) break;
+        if (!fused && (rc = qldpc_make_llr_device(dec, ln.bits.p, dk, dp, llr_noisy, llr_known, nf, ln.in.p, ln.st))) break;
         mark(ln.st);
-        if ((rc = decode_device_impl(dec, ln.in.p, syndrome ? ln.syn.p : nullptr, nf, ln.out.p, ln.ok.p, ln.iters.p, nullptr,
-                                     ln.st, shared_scratch ? 0 : (idx & 1)))) break;
+        if ((rc = decode_device_impl(dec, fused ? nullptr : ln.in.p, syndrome ? ln.syn.p : nullptr, nf, ln.out.p, ln.ok.p,
+                                     ln.iters.p, nullptr, ln.st, shared_scratch ? 0 : (idx & 1), fused ? ln.bits.p : nullptr,
+                                     mag))) break;
         mark(ln.st);
         QLDPC_CUDA(cudaMemcpyAsync(out_bits + (size_t)f0 * d->out_words, ln.out.p, (size_t)nf * d->out_words * 4,
                                    cudaMemcpyDeviceToHost, ln.st));
@@ -1092,6 +1220,7 @@ extern "C" int qldpc_encode_nr_device(qldpc_decoder *dec, const uint32_t *d_msg,
 {
     if (!dec || !d_msg || !d_cword || n_frames < 0) return QLDPC_ERR_ARG;
     qldpc_decoder_full *d = full(dec);
+    if (!d->children.empty()) return QLDPC_ERR_UNSUPPORTED;
     if (!d->code.has_nr_core()) return QLDPC_ERR_UNSUPPORTED;
     QLDPC_CUDA(cudaSetDevice(d->cfg.device));
     const HostCode &c = d->code;
@@ -1108,9 +1237,13 @@ extern "C" int qldpc_encode_nr(qldpc_decoder *dec, const uint32_t *msg, int32_t 
     if (n_frames == 0) return QLDPC_OK;
     qldpc_decoder_full *d = full(dec);
     if (!d->code.has_nr_core()) return QLDPC_ERR_UNSUPPORTED;
-    QLDPC_CUDA(cudaSetDevice(d->cfg.device));
     const HostCode &c = d->code;
     const int msg_words = ((c.base_cols - c.base_rows) * c.z + 31) / 32;
+    if (!d->children.empty())
+        return shard_frames(d, n_frames, [&](qldpc_decoder *ch, int f0, int nf) {
+            return qldpc_encode_nr(ch, msg + (size_t)f0 * msg_words, nf, cword + (size_t)f0 * d->cw_words);
+        });
+    QLDPC_CUDA(cudaSetDevice(d->cfg.device));
     Lane &ln = d->lanes.lane[0];
     int rc;
     if ((rc = d->d_tmp_bits.ensure((size_t)n_frames * msg_words))) return rc;
@@ -1128,6 +1261,17 @@ extern "C" int qldpc_get_stats(qldpc_decoder *dec, qldpc_stats *out)
 {
     if (!dec || !out) return QLDPC_ERR_ARG;
     qldpc_decoder_full *d = full(dec);
+    if (!d->children.empty()) {   // the only reduction of the multi-device path: on the host
+        std::memset(out, 0, sizeof(*out));
+        for (qldpc_decoder *ch : d->children) {
+            qldpc_stats s;
+            if (int rc = qldpc_get_stats(ch, &s)) return rc;
+            out->frames += s.frames; out->failures += s.failures; out->iter_sum += s.iter_sum;
+            out->kernel_launches += s.kernel_launches;
+            for (int i = 0; i < QLDPC_ITER_HIST_BINS; ++i) out->iter_hist[i] += s.iter_hist[i];
+        }
+        return QLDPC_OK;
+    }
     QLDPC_CUDA(cudaSetDevice(d->cfg.device));
     QLDPC_CUDA(cudaDeviceSynchronize());
     DevStats h;
@@ -1144,6 +1288,11 @@ extern "C" int qldpc_reset_stats(qldpc_decoder *dec)
 {
     if (!dec) return QLDPC_ERR_ARG;
     qldpc_decoder_full *d = full(dec);
+    if (!d->children.empty()) {
+        for (qldpc_decoder *ch : d->children)
+            if (int rc = qldpc_reset_stats(ch)) return rc;
+        return QLDPC_OK;
+    }
     QLDPC_CUDA(cudaSetDevice(d->cfg.device));
     QLDPC_CUDA(cudaDeviceSynchronize());
     QLDPC_CUDA(cudaMemset(d->d_stats.p, 0, sizeof(DevStats)));

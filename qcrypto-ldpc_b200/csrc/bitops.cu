@@ -29,6 +29,31 @@ __global__ void syndrome_csr_kernel(const uint32_t *__restrict__ bits, uint32_t 
     syn[t] = out;
 }
 
+// The same for quasi-cyclic codes with Z % 32 == 0: a check word is the XOR of one rotated 32-bit window per edge
+// (two loads + funnel shift) instead of 32 x degree single-bit gathers.  One thread per output word.
+__global__ void syndrome_qc_kernel(const uint32_t *__restrict__ bits, uint32_t *__restrict__ syn, int F, int brows, int ZW32,
+                                   int cw_words, int syn_words, const QcLayer *__restrict__ layers,
+                                   const QcEdgeAux *__restrict__ aux)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)F * syn_words) return;
+    const int f = (int)(t / syn_words), ow = (int)(t - (long long)f * syn_words);
+    const int r = ow / ZW32, w = ow - r * ZW32;
+    if (r >= brows) return;
+    const uint32_t *b = bits + (size_t)f * cw_words;
+    const QcLayer ly = layers[r];
+    uint32_t acc = 0;
+    for (int e = 0; e < ly.degree; ++e) {
+        const QcEdgeAux a = aux[ly.edge_begin + e];
+        // check lane 32w + j reads variable lane (32w + j + shift) mod Z (ML/mul_sh.m:9); MSB-first words: a left funnel shift
+        int w0 = w + (a.shift >> 5);
+        if (w0 >= ZW32) w0 -= ZW32;
+        const int w1 = w0 + 1 == ZW32 ? 0 : w0 + 1;
+        acc ^= __funnelshift_l(__ldg(b + a.hdw + w1), __ldg(b + a.hdw + w0), a.shift & 31);
+    }
+    syn[t] = acc;
+}
+
 __global__ void gather_bits_kernel(const uint32_t *__restrict__ allbits, uint32_t *__restrict__ out, int F, int cw_words,
                                    int out_words, int K, const int32_t *__restrict__ info_pos)
 {
@@ -76,15 +101,12 @@ __device__ __forceinline__ uint32_t spread_nibble(uint32_t nib)   // bit 3..0 of
     return (((nib * 0x08040201u) >> 3) & 0x01010101u) * 0xffu;
 }
 // 16 positions per item -> one 16-byte store.  In the host pipeline the kernel runs BESIDE a decode CTA of the other lane,
-// which leaves 1024 registers on each of the four SM sub-partitions (layered_i8s.cu, QL_S_MAXNREG): one CTA of four warps
+// which leaves 1024 registers on each of the four SM sub-partitions (layered_i8s.cu, kMaxRegs): one CTA of four warps
 // at 32 registers per SM.  With so few warps the latency is hidden by loads in flight, not by occupancy: a CTA lives for
-// kLlrRep rounds of kLlrUnroll independent loads per thread.  (A one-warp CTA with more registers, QL_LLR_BLOCK=32, does
-// not get placed beside a decoder that uses 128 registers either: measured.)
-#ifndef QL_LLR_BLOCK
-#define QL_LLR_BLOCK 128
-#endif
-constexpr int kLlrBlock = QL_LLR_BLOCK, kLlrUnroll = QL_LLR_BLOCK == 32 ? 8 : 4, kLlrRep = QL_LLR_BLOCK == 32 ? 8 : 4;
-__global__ void __launch_bounds__(kLlrBlock, QL_LLR_BLOCK == 32 ? 32 : 16)
+// kLlrRep rounds of kLlrUnroll independent loads per thread.  (A one-warp CTA with more registers does not get placed
+// beside a decoder that uses 128 registers either: measured.)
+constexpr int kLlrBlock = 128, kLlrUnroll = 4, kLlrRep = 4;
+__global__ void __launch_bounds__(kLlrBlock, 16)
 make_llr_i8x16_kernel(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ known, const uint32_t *__restrict__ punct,
                       int noisy, int known_mag, int F, int groups, int cw_words, uint4 *__restrict__ out)
 {
@@ -192,9 +214,39 @@ __global__ void encode_nr_kernel(const uint32_t *__restrict__ msg, uint32_t *__r
     }
 }
 
+// Per-position LLR magnitudes (one byte each, shared by all frames) for the decoders that synthesise their LLRs from key
+// bits themselves (layered_i8s.cu, bit input): noisy / known / punctured as in make_llr_kernel.
+__global__ void make_mag_i8_kernel(const uint32_t *__restrict__ known, const uint32_t *__restrict__ punct, int noisy,
+                                   int known_mag, int N, uint8_t *__restrict__ mag)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int m = noisy;
+    if (known && get_bit(known, i)) m = known_mag;
+    if (punct && get_bit(punct, i)) m = 0;
+    mag[i] = (uint8_t)m;
+}
+
 inline int grid_for(long long items, int block) { return (int)((items + block - 1) / block); }
 
 }  // namespace
+
+int launch_make_mag_i8(const uint32_t *known, const uint32_t *punct, int noisy, int known_mag, int N, uint8_t *mag, cudaStream_t st)
+{
+    make_mag_i8_kernel<<<grid_for(N, 256), 256, 0, st>>>(known, punct, noisy, known_mag, N, mag);
+    QLDPC_CUDA(cudaGetLastError());
+    return QLDPC_OK;
+}
+
+int launch_syndrome_qc(const uint32_t *bits, uint32_t *syn, int F, int brows, int Z, int cw_words, int syn_words,
+                       const QcLayer *layers, const QcEdgeAux *aux, cudaStream_t st)
+{
+    if (F <= 0) return QLDPC_OK;
+    syndrome_qc_kernel<<<grid_for((long long)F * syn_words, 128), 128, 0, st>>>(bits, syn, F, brows, Z / 32, cw_words, syn_words,
+                                                                                 layers, aux);
+    QLDPC_CUDA(cudaGetLastError());
+    return QLDPC_OK;
+}
 
 int launch_syndrome_csr(const uint32_t *bits, uint32_t *syn, int F, int N, int M, int cw_words, int syn_words,
                         const int32_t *row_ptr, const int32_t *col_idx, cudaStream_t st)

@@ -45,7 +45,11 @@ int layered_i8_max_threads_stream();
 
 // ---- layered int8, QC, Z % 128 == 0, streamed kernel (layered_i8s.cu) ----------------------------
 struct LayeredI8sParams {
-    const int8_t *llr;        // F * N, 16-byte aligned
+    const int8_t *llr;        // F * N, 16-byte aligned (null with bit input)
+    // bit input (qldpc_decode_bits): packed sifted-key bits instead of LLRs; the kernel synthesises +-mag[position] itself
+    const uint32_t *bits;     // F * N/32 words, MSB-first, 16-byte aligned; null: LLR input
+    const uint8_t *mag;       // N magnitudes 0..127 (shared by all frames), 4-byte aligned
+    int8_t *ext_scratch;      // grid * slots * N bytes: the slots' synthesised extension-column LLRs
     const uint32_t *syn;      // F * syn_words (MSB-first) or null
     uint32_t *out;            // F * out_words (MSB-first)
     uint8_t *ok;
@@ -145,7 +149,10 @@ int layered_flood_qc_threads();
 int launch_flooding_qc(const FloodQcParams &p, int grid, int block, int smem_bytes, cudaStream_t st);
 
 // ---- bit-level helpers ---------------------------------------------------------------------------
-// syndrome of packed frames; QC codes use word-wise rotate+XOR, others a CSR gather
+// syndrome of packed frames: QC codes with Z % 32 == 0 use word-wise rotate + XOR (launch_syndrome_qc), others a CSR gather
+int launch_syndrome_qc(const uint32_t *bits, uint32_t *syn, int F, int brows, int Z, int cw_words, int syn_words,
+                       const QcLayer *layers, const QcEdgeAux *aux, cudaStream_t st);
+int launch_make_mag_i8(const uint32_t *known, const uint32_t *punct, int noisy, int known_mag, int N, uint8_t *mag, cudaStream_t st);
 int launch_syndrome_csr(const uint32_t *bits, uint32_t *syn, int F, int N, int M, int cw_words, int syn_words,
                         const int32_t *row_ptr, const int32_t *col_idx, cudaStream_t st);
 int launch_gather_bits(const uint32_t *allbits, uint32_t *out, int F, int cw_words, int out_words, int K,

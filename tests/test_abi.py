@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(q):
     for name in declared:
         assert hasattr(L, name), "libqldpc_b200.so does not export " + name
     assert sorted(q.ABI_SYMBOLS) == declared
-    assert L.qldpc_version() == 100
+    assert L.qldpc_version() == 200
 
 
 def test_signatures_are_plain_c(q):

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _run_case(q, O, data_dir, name, F, qber, mag, mode, rule, n_ite, early, offset=2, k8=6, out_all=True, seed=1,
-              expect_kernel=None, random_llr=False):
+              expect_kernel=None, random_llr=False, flags=0):
     path = "%s/%s" % (data_dir, name)
     oc = O.Code.from_qc(path)
     if random_llr:   # stress: arbitrary int8 LLRs incl. -128 / 127 saturation, random syndrome
@@ -20,10 +20,9 @@ def _run_case(q, O, data_dir, name, F, qber, mag, mode, rule, n_ite, early, offs
         llr, syn, _ = make_frames(O, oc, F, qber, mag, 31, mode, seed)
     code = q.Code.from_qc_file(path)
     dec = q.Decoder(code, schedule=q.SCHED_LAYERED, rule=rule, dtype=q.DTYPE_I8, max_iter=n_ite, early_stop=early,
-                    norm_factor=k8 / 8.0, offset=float(offset), out_mode=q.OUT_ALL if out_all else q.OUT_INFO)
-    import os
+                    norm_factor=k8 / 8.0, offset=float(offset), out_mode=q.OUT_ALL if out_all else q.OUT_INFO, flags=flags)
     if expect_kernel is None:   # streamed kernel (layered_i8s.cu) for Z % 128 == 0, else the shared-memory-resident one
-        streamed = oc.Z % 128 == 0 and not os.environ.get("QLDPC_LI8_MODE")
+        streamed = oc.Z % 128 == 0 and not (flags & (q.FLAG_LI8_RESIDENT | q.FLAG_LI8_STREAM))
         expect_kernel = "layered_i8s_zpack4" if streamed else "layered_i8_zpack4"
     assert dec.kernel_name == expect_kernel, dec.kernel_name
     syn_packed = None if syn is None else q.pack_bits(syn)
@@ -55,13 +54,13 @@ def test_bg1_z384_qber3(q, O, data_dir, mode, rule, k8, offset):
 
 
 @pytest.mark.parametrize("mode", ["resident", "stream"])
-def test_bg1_z384_both_message_placements(q, O, data_dir, mode, monkeypatch):
-    """the kernel keeps check-to-variable messages either resident in shared memory (+ register rows, 2 frames/SM)
-    or streamed through an L2-resident scratch (4 frames/SM); both must be bit-exact"""
-    monkeypatch.setenv("QLDPC_LI8_MODE", mode)
-    _run_case(q, O, data_dir, "NR_1_1_384.qc", 40, 0.05, 12, "syndrome", q.RULE_NMS, 10, True, k8=6, seed=21)
-    _run_case(q, O, data_dir, "NR_1_1_384.qc", 24, 0.03, 14, "parity", q.RULE_OMS, 3, False, offset=2, seed=22)
-    _run_case(q, O, data_dir, "NR_2_3_112.qc", 24, 0.03, 14, "parity", q.RULE_NMS, 10, True, seed=23)
+def test_bg1_z384_both_message_placements(q, O, data_dir, mode):
+    """the previous-generation kernel keeps check-to-variable messages either resident in shared memory (+ register rows,
+    2 frames/SM) or streamed through an L2-resident scratch (4 frames/SM); both must be bit-exact"""
+    fl = q.FLAG_LI8_RESIDENT if mode == "resident" else q.FLAG_LI8_STREAM
+    _run_case(q, O, data_dir, "NR_1_1_384.qc", 40, 0.05, 12, "syndrome", q.RULE_NMS, 10, True, k8=6, seed=21, flags=fl)
+    _run_case(q, O, data_dir, "NR_1_1_384.qc", 24, 0.03, 14, "parity", q.RULE_OMS, 3, False, offset=2, seed=22, flags=fl)
+    _run_case(q, O, data_dir, "NR_2_3_112.qc", 24, 0.03, 14, "parity", q.RULE_NMS, 10, True, seed=23, flags=fl)
 
 
 def test_bg1_z384_fixed_iterations_matlab_constants(q, O, data_dir):
@@ -203,10 +202,10 @@ def test_baseline_full_size_65536_frames_roundtrip(q, O, data_dir):
     assert (oit == iters[sel]).all() and ook.all()
 
 
-def test_host_pipeline_many_small_chunks(q, O, data_dir, monkeypatch):
-    """the host-pointer entry points cut the batch into chunks that ping-pong over two streams; kernels of the two
-    streams overlap in time, so nothing they write may be shared (regression: streamed-message scratch)"""
-    monkeypatch.setenv("QLDPC_CHUNK_FRAMES", "592")
+def test_host_pipeline_chunks_on_two_streams(q, O, data_dir):
+    """the host-pointer entry points cut the batch into chunks (2, 4, 8 ... waves of the persistent grid) that ping-pong over
+    two streams; kernels of the two streams overlap in time, so nothing they write may be shared (regression:
+    streamed-message scratch, and with bit input the slots' extension-column scratch)"""
     path = "%s/NR_1_1_384.qc" % data_dir
     oc = O.Code.from_qc(path)
     code = q.Code.from_qc_file(path)
@@ -239,3 +238,81 @@ def test_bg1_z384_many_frames_per_slot_vs_oracle(q, O, data_dir, mode, qber, mag
     bits, iteration counts and ok flags still equal the oracle's, frame by frame"""
     iters, ok = _run_case(q, O, data_dir, "NR_1_1_384.qc", 2600, qber, mag, mode, q.RULE_NMS, 10, True, out_all=False, seed=91)
     assert len(set(iters.tolist())) >= 2          # a mix of iteration counts inside the batch
+
+
+@pytest.mark.parametrize("mode", ["parity", "syndrome"])
+@pytest.mark.parametrize("name", ["NR_1_1_384.qc", "NR_2_0_256.qc", "NR_1_0_128.qc"])
+def test_bit_input_fused_synthesis_equals_two_kernel_path(q, O, data_dir, name, mode):
+    """qldpc_decode_bits on the streamed kernel synthesises the LLRs INSIDE the decoder (bit input); bits, flags and
+    iteration counts must equal the two-kernel path (QLDPC_FLAG_NO_FUSED_BITS: make_llr + decode) and the oracle on the
+    same LLRs -- with known, punctured and noisy positions mixed inside core AND extension columns, more frames than slots"""
+    path = "%s/%s" % (data_dir, name)
+    oc = O.Code.from_qc(path)
+    code = q.Code.from_qc_file(path)
+    F = 2100
+    rng = np.random.default_rng(77)
+    x = rng.integers(0, 2, (F, oc.N)).astype(np.uint8)
+    kw = dict(schedule=q.SCHED_LAYERED, rule=q.RULE_NMS, dtype=q.DTYPE_I8, max_iter=10, early_stop=True, norm_factor=0.75,
+              out_mode=q.OUT_ALL)
+    fused, plain = q.Decoder(code, **kw), q.Decoder(code, flags=q.FLAG_NO_FUSED_BITS, **kw)
+    assert fused.kernel_name == plain.kernel_name == "layered_i8s_zpack4"
+    known = np.zeros(oc.N, np.uint8)
+    punct = np.zeros(oc.N, np.uint8)
+    if mode == "parity":
+        cw = q.unpack_bits(fused.encode_nr(q.pack_bits(x[:, :oc.K])), oc.N)
+        known[oc.K:] = 1
+        known[rng.choice(oc.K, oc.K // 50, replace=False)] = 1        # some revealed information bits (blind reconciliation)
+        punct[oc.N - 3 * oc.Z // 2:] = 1                               # punctured tail, not a whole number of block columns
+        known[punct == 1] = 0
+        syn = None
+    else:
+        cw = x
+        punct[rng.choice(oc.N, oc.N // 40, replace=False)] = 1
+        syn = fused.syndrome(q.pack_bits(cw))
+    noise = (rng.random((F, oc.N)) < 0.03).astype(np.uint8) & (1 - known)
+    noisy_p = q.pack_bits(cw ^ noise)
+    km, pm = q.pack_bits(known), q.pack_bits(punct)
+    a = fused.decode_bits(noisy_p, 13.0, 31.0, known_mask=km, punct_mask=pm, syndrome=syn)
+    b = plain.decode_bits(noisy_p, 13.0, 31.0, known_mask=km, punct_mask=pm, syndrome=syn)
+    for u, v in zip(a, b):
+        assert (u == v).all()
+    assert fused.stats()["kernel_launches"] < plain.stats()["kernel_launches"]      # no LLR synthesis launches
+    sel = rng.choice(F, 40, replace=False)
+    llr = plain.make_llr(noisy_p[sel], 13.0, 31.0, known_mask=km, punct_mask=pm)
+    hard, oit, ook, _ = oc.batch_layered_fixed_i8(llr, None if syn is None else q.unpack_bits(syn[sel], oc.M), rule=O.RULE_NMS,
+                                                  n_ite=10, early_stop=True, norm_eighths=6)
+    assert (q.unpack_bits(a[0][sel], oc.N) == hard).all() and (a[2][sel] == oit).all() and (a[1][sel] == ook).all()
+    fused.close()
+    plain.close()
+
+
+def test_shortened_prefix_info_bits_on_the_int8_kernels(q, O, data_dir):
+    """information positions [0, k') with k' smaller than the systematic part (a shortened code) -- k' a whole
+    number of block columns is written directly, any other k' goes through the gather; frames must not be mis-strided"""
+    path = "%s/NR_1_1_384.qc" % data_dir
+    oc = O.Code.from_qc(path)
+    llr, syn, truth = make_frames(O, oc, 900, 0.03, 14, 31, "parity", 5)
+    for kk in (20 * oc.Z, 20 * oc.Z + 100, 37):
+        code = q.Code.from_qc_file(path)
+        code.set_info_bits_pos(np.arange(kk))
+        dec = q.Decoder(code, schedule=q.SCHED_LAYERED, rule=q.RULE_NMS, dtype=q.DTYPE_I8, max_iter=10, early_stop=True,
+                        norm_factor=0.75, out_mode=q.OUT_INFO)
+        assert dec.out_words == (kk + 31) // 32
+        out, ok, iters, _ = dec.decode(llr.astype(np.int8))
+        assert ok.all() and (q.unpack_bits(out, kk) == truth[:, :kk]).all()
+        dec.close()
+
+
+def test_llr_magnitudes_outside_the_dtype_range_are_rejected(q, data_dir):
+    """llr_known = 200 on the int8 tier used to wrap to -56 and flip every confirmed bit"""
+    code = q.Code.from_qc_file("%s/NR_1_1_384.qc" % data_dir)
+    dec = q.Decoder(code, schedule=q.SCHED_LAYERED, rule=q.RULE_NMS, dtype=q.DTYPE_I8, max_iter=2, norm_factor=0.75)
+    bits = np.zeros((4, dec.cw_words), np.uint32)
+    for noisy, known in ((14.0, 200.0), (-1.0, 31.0), (128.0, 31.0)):
+        with pytest.raises(q.QldpcError) as e:
+            dec.make_llr(bits, noisy, known)
+        assert e.value.code == 1
+        with pytest.raises(q.QldpcError):
+            dec.decode_bits(bits, noisy, known)
+    assert (dec.make_llr(bits, 127.0, 127.0) == 127).all()
+    dec.close()

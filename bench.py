@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fused-bits", action="store_true", help="qldpc_decode_bits as two kernels (LLR synthesis + decode)")
     ap.add_argument("--no-l2-persist", action="store_true", help="do not set QLDPC_FLAG_L2_PERSIST")
+    ap.add_argument("--no-zero-copy", action="store_true", help="qldpc_decode_bits stages pinned buffers through device copies")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
 
@@ -292,7 +293,8 @@ def run_ours(args, rank, world, local_rank):
     rule = q.RULE_NMS if args.rule == "nms" else q.RULE_OMS
     dec = q.Decoder(code, schedule=q.SCHED_LAYERED, rule=rule, dtype=q.DTYPE_I8, max_iter=MAX_ITER,
                     early_stop=not args.fixed_iters, norm_factor=NORM, offset=2.0, out_mode=q.OUT_INFO, device=local_rank,
-                    flags=(0 if args.no_l2_persist else q.FLAG_L2_PERSIST) | (q.FLAG_NO_FUSED_BITS if args.no_fused_bits else 0))
+                    flags=(0 if args.no_l2_persist else q.FLAG_L2_PERSIST) | (q.FLAG_NO_FUSED_BITS if args.no_fused_bits else 0) |
+                    (q.FLAG_NO_ZERO_COPY if args.no_zero_copy else 0))
     assert dec.kernel_name == "layered_i8s_zpack4", dec.kernel_name   # the streamed kernel (layered_i8s.cu)
     F, N, K = args.frames, code.n, code.k
     st = torch.cuda.current_stream().cuda_stream

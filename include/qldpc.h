@@ -79,6 +79,7 @@ enum { QLDPC_OUT_INFO = 0, QLDPC_OUT_ALL = 1 };
 #define QLDPC_FLAG_LI8_RESIDENT   2u  /* diagnostics: int8 layered decoding on the previous-generation kernel (layered_i8.cu)  */
 #define QLDPC_FLAG_LI8_STREAM     4u  /*   with its messages resident in shared memory / streamed through an L2 scratch   */
 #define QLDPC_FLAG_NO_FUSED_BITS  8u  /* diagnostics: qldpc_decode_bits runs LLR synthesis and decoding as two kernels      */
+#define QLDPC_FLAG_NO_ZERO_COPY  16u  /* diagnostics: qldpc_decode_bits stages pinned host buffers through device copies too */
 
 typedef struct qldpc_code qldpc_code;
 typedef struct qldpc_decoder qldpc_decoder;
@@ -188,7 +189,10 @@ int qldpc_make_llr_device(qldpc_decoder *dec, const uint32_t *d_bits, const uint
  * pb->mainBufPtr, MSB-first words): only n/8 bytes per frame cross the bus instead of n LLR values.
  * Arguments as in qldpc_make_llr followed by qldpc_decode; results are identical to calling the two.
  * On the int8 layered decoder for Z % 128 == 0 the synthesis happens INSIDE the decoder kernel (the frame's bits are
- * bulk-copied to shared memory, +-magnitude bytes are formed there): no LLR array exists in device memory.
+ * bulk-copied to shared memory, +-magnitude bytes are formed there): no LLR array exists in device memory.  If, in
+ * addition, bits / syndrome / out_bits / ok / iters are PINNED host memory (cudaHostAlloc, cudaHostRegister), the kernel
+ * reads and writes them in place over PCIe (zero copy): one launch per call, no staging buffers.  Pageable buffers
+ * are staged through a two-stream chunked copy pipeline.
  * Integer dtypes: llr_noisy / llr_known are rounded to the nearest integer and must lie in [0, 127] (int8) or
  * [0, 32767] (int16), else QLDPC_ERR_ARG.
  */

@@ -313,6 +313,12 @@ bool plan_layered_i8s(qldpc_decoder *d)
     for (int k = 0; k < 2; ++k) {
         const int slots = std::min(std::min(avail / geo.slot_bytes[k], layered_i8s_max_threads() / W), 15);
         geo.slots[k] = slots;
+        // bit-input layout: packed bits staged instead of core LLRs, magnitude table behind the slots
+        geo.bits_off_stg[k] = geo.slot_bytes[k];
+        geo.bits_slot_bytes[k] = geo.slot_bytes[k] + round_up(c.n / 8, 16);
+        geo.bits_off_magtab[k] = geo.tab_bytes + kLi8sSlotBase + slots * geo.bits_slot_bytes[k];
+        geo.bits_smem[k] = geo.bits_off_magtab[k] + round_up(c.n, 16);
+        geo.bits_ok[k] = slots >= 1 && c.n % 128 == 0 && geo.bits_smem[k] <= d->max_smem_optin;
         // frame-prefetch staging buffer, if it fits without giving up a frame slot
         const int with_stg = geo.slot_bytes[k] + L_bytes;
         if (slots >= 1 && avail / with_stg >= slots) {
@@ -685,12 +691,22 @@ static int ensure_scratch(qldpc_decoder_full *d)
     return QLDPC_OK;
 }
 
-// Bit input of the streamed int8 kernel (LLR synthesis inside the decoder): needs the frame-prefetch staging buffer of the
-// slot geometry in use and 16-byte aligned bits (bulk copies); n % 128 == 0 holds for every code the kernel takes.
+// Bit input of the streamed int8 kernel (LLR synthesis inside the decoder): needs room for its shared-memory layout (packed
+// bits staged per slot, one magnitude table per CTA) and 16-byte aligned bits (bulk copies).
 static bool fused_bits_ok(const qldpc_decoder_full *d, const uint32_t *d_bits, bool with_syndrome)
 {
     return d->kernel_family == KF_LAYERED_I8S && !(d->cfg.flags & QLDPC_FLAG_NO_FUSED_BITS) &&
-           d->li8s_geo.off_stg[with_syndrome ? 1 : 0] >= 0 && (reinterpret_cast<uintptr_t>(d_bits) & 15) == 0;
+           d->li8s_geo.bits_ok[with_syndrome ? 1 : 0] && (reinterpret_cast<uintptr_t>(d_bits) & 15) == 0;
+}
+
+// Device-side alias of a pinned host buffer (cudaHostAlloc / cudaHostRegister under unified addressing), or null when
+// the pointer is pageable host memory / not known to the driver.
+static void *pinned_alias(const void *p)
+{
+    if (!p) return nullptr;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
 }
 
 // scratch_lane: which copy of the streamed-message scratch to use. Launches that may overlap in time (the two
@@ -758,6 +774,11 @@ static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint3
         p.tab_bytes = geo.tab_bytes; p.off_rows = geo.off_rows; p.off_pcols = geo.off_pcols;
         p.slot_bytes = geo.slot_bytes[k]; p.off_ring = geo.off_ring; p.stage_bytes = geo.stage_bytes;
         p.off_ext = geo.off_ext; p.off_hd = geo.off_hd; p.off_syn = geo.off_syn; p.off_mbar = geo.off_mbar[k]; p.off_stg = geo.off_stg[k];
+        int smem_bytes = geo.tab_bytes + kLi8sSlotBase + p.slots * p.slot_bytes;
+        if (d_bits) {
+            p.slot_bytes = geo.bits_slot_bytes[k]; p.off_stg = geo.bits_off_stg[k]; p.off_magtab = geo.bits_off_magtab[k];
+            smem_bytes = geo.bits_smem[k];
+        }
         p.rg_u4 = geo.rg_u4;
         const int grid = std::min(d->sm_count, (n_frames + p.slots - 1) / p.slots);
         const size_t lane_u4 = (size_t)d->sm_count * std::max(geo.slots[0], geo.slots[1]) * geo.rg_u4;
@@ -770,7 +791,6 @@ static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint3
             p.frame_ctr = reinterpret_cast<unsigned int *>(d->d_li8s_rg.p + 2 * lane_u4 + scratch_lane);
             QLDPC_CUDA(cudaMemsetAsync(p.frame_ctr, 0, sizeof(unsigned int), st));
         }
-        const int smem_bytes = geo.tab_bytes + kLi8sSlotBase + p.slots * p.slot_bytes;
         if (d->l2_persist_bytes > 0) {
             // keep (a share of) the message scratch resident in L2 while the LLR stream flows through it
             const size_t win = std::min<size_t>((size_t)grid * p.slots * geo.rg_u4 * 16, (size_t)d->l2_window_max);
@@ -1150,6 +1170,21 @@ extern "C" int qldpc_decode_bits(qldpc_decoder *dec, const uint32_t *bits, const
         d->kernel_launches++;
     }
     QLDPC_CUDA(cudaStreamSynchronize(l0.st));   // masks / magnitudes are read by both lanes
+    // Zero-copy: with bit input a frame costs n/8 bytes in and k/8 + 3 bytes out.  When the caller's frame buffers are
+    // pinned host memory the decoder kernel fetches the bits (its per-slot bulk copy of the NEXT frame, one frame ahead of
+    // the decode) and stores its results through PCIe itself: ONE launch for the whole batch, no staging copies, no chunk
+    // pipeline whose every launch ends with a partly idle wave.  Pageable buffers take the chunked copy pipeline below.
+    if (fused && !(d->cfg.flags & QLDPC_FLAG_NO_ZERO_COPY)) {
+        const uint32_t *zb = (const uint32_t *)pinned_alias(bits), *zs = (const uint32_t *)pinned_alias(syndrome);
+        uint32_t *zo = (uint32_t *)pinned_alias(out_bits);
+        uint8_t *zk = (uint8_t *)pinned_alias(ok);
+        uint16_t *zi = (uint16_t *)pinned_alias(iters);
+        if (zb && zo && (!syndrome || zs) && (!ok || zk) && (!iters || zi) && (reinterpret_cast<uintptr_t>(zb) & 15) == 0) {
+            if ((rc = decode_device_impl(dec, nullptr, zs, n_frames, zo, zk, zi, nullptr, l0.st, 0, zb, mag))) return rc;
+            QLDPC_CUDA(cudaStreamSynchronize(l0.st));
+            return QLDPC_OK;
+        }
+    }
     for (auto &ln : d->lanes.lane) {
         if (!fused && (rc = ln.in.ensure((size_t)chunk * frame_llr))) return rc;
         if ((rc = ln.bits.ensure((size_t)chunk * d->cw_words))) return rc;

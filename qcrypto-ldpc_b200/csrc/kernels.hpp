@@ -48,7 +48,7 @@ struct LayeredI8sParams {
     const int8_t *llr;        // F * N, 16-byte aligned (null with bit input)
     // bit input (qldpc_decode_bits): packed sifted-key bits instead of LLRs; the kernel synthesises +-mag[position] itself
     const uint32_t *bits;     // F * N/32 words, MSB-first, 16-byte aligned; null: LLR input
-    const uint8_t *mag;       // N magnitudes 0..127 (shared by all frames), 4-byte aligned
+    const uint8_t *mag;       // N magnitudes 0..127 (shared by all frames), 16-byte aligned; copied to shared memory (off_magtab)
     int8_t *ext_scratch;      // grid * slots * N bytes: the slots' synthesised extension-column LLRs
     const uint32_t *syn;      // F * syn_words (MSB-first) or null
     uint32_t *out;            // F * out_words (MSB-first)
@@ -68,7 +68,8 @@ struct LayeredI8sParams {
     int slots;
     int tab_bytes, off_rows, off_pcols;
     int slot_bytes, off_ring, stage_bytes, off_ext, off_hd, off_syn, off_mbar;
-    int off_stg;              // staging buffer of the next frame's core LLRs (n_pack * Z bytes), -1: none
+    int off_stg;              // staging buffer of the next frame's core LLRs (n_pack * Z bytes; bit input: N/8 bytes), -1: none
+    int off_magtab;           // bit input: byte offset of the CTA's magnitude table (N bytes) in dynamic shared memory
     int rg_u4;                // uint4 per frame slot in the scratch
     unsigned int *frame_ctr;  // zeroed before the launch: frames beyond the first grid * slots are handed out through it
                               // (null: frame f of a slot is followed by f + grid * slots)

@@ -438,6 +438,11 @@ __global__ void __maxnreg__(kMaxRegs) layered_i8s_kernel(const LayeredI8sParams 
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
         for (int k = tid; k < (p.tab_bytes >> 4); k += nthreads_cta) dst[k] = src[k];
         if (tid == 0) dst[p.tab_bytes >> 4] = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+        if (p.bits != nullptr) {   // bit input: the per-position magnitudes, one table for all slots of the CTA
+            const uint4 *ms = reinterpret_cast<const uint4 *>(p.mag);
+            uint4 *md = reinterpret_cast<uint4 *>(smem + p.off_magtab);
+            for (int k = tid; k < (p.N >> 4); k += nthreads_cta) md[k] = __ldg(ms + k);
+        }
         if (i == 0) {
             mbar_init(mb_full, 1);
             mbar_init(mb_full + 8, 1);
@@ -533,26 +538,27 @@ __global__ void __maxnreg__(kMaxRegs) layered_i8s_kernel(const LayeredI8sParams 
             mbar_wait(mb_stg, sp);
             sp ^= 1u;
             const u32 *bw = reinterpret_cast<const u32 *>(slot + p.off_stg);   // the frame's packed bits, MSB first
+            const char *magtab = smem + p.off_magtab;
             const u32 nsh = 28u - 4u * (u32)(lj & 7);
 #pragma unroll kLoadUnroll
             for (int c = lc; c < p.n_pack; c += 4) {   // core columns -> interleaved biased belief words
                 const int off = pcols[c].llr_off;
-                const u32 *mq = reinterpret_cast<const u32 *>(p.mag + off) + lj;
+                const u32 *mq = reinterpret_cast<const u32 *>(magtab + off) + lj;
                 const u32 *bq = bw + (off >> 5) + (lj >> 3);
                 u32 in[4], out[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) in[k] = synth_biased4((bq[k * wq] >> nsh) & 0xfu, __ldg(mq + k * wq4));
+                for (int k = 0; k < 4; ++k) in[k] = synth_biased4((bq[k * wq] >> nsh) & 0xfu, mq[k * wq4]);
                 transpose4x4(in, out);
                 *reinterpret_cast<uint4 *>(Lw + c * W + 4 * lj) = make_uint4(out[0], out[1], out[2], out[3]);
             }
             // extension columns -> raw int8 LLRs in the slot's scratch (word i of a column = lanes 4i .. 4i+3), from where
             // the row staging bulk-copies them exactly as it does from a frame of LLRs
             const u32 esh = 28u - 4u * (u32)(i & 7);
-#pragma unroll 2
+#pragma unroll 4
             for (int r = 0; r < R; ++r) {
                 const int es = *reinterpret_cast<const int *>(rowsc + 32 * r + 16);
                 if (es < 0) continue;
-                const u32 b = synth_biased4((bw[(es >> 5) + (i >> 3)] >> esh) & 0xfu, __ldg(reinterpret_cast<const u32 *>(p.mag + es) + i));
+                const u32 b = synth_biased4((bw[(es >> 5) + (i >> 3)] >> esh) & 0xfu, reinterpret_cast<const u32 *>(magtab + es)[i]);
                 reinterpret_cast<u32 *>(ext_slot + es)[i] = b ^ 0x80808080u;
             }
             asm volatile("fence.proxy.async.global;" ::: "memory");   // the bulk copies of the rows read what was just stored

@@ -77,6 +77,10 @@ struct Li8sGeo {         // launch geometry of the streamed kernel; index 0: no 
     int tab_bytes = 0, off_rows = 0, off_pcols = 0, n_pack = 0;
     int rg_u4 = 0, stage_bytes = 0, off_ring = 0, off_ext = 0, off_hd = 0, off_syn = 0;
     int slot_bytes[2] = {0, 0}, slots[2] = {0, 0}, off_mbar[2] = {0, 0}, off_stg[2] = {-1, -1};
+    // bit input (LLR synthesis inside the kernel): the staging buffer holds N/8 bytes of packed bits instead of the core
+    // LLRs, and one N-byte magnitude table per CTA follows the slots; bits_ok: that layout fits with the same slot count
+    int bits_slot_bytes[2] = {0, 0}, bits_off_stg[2] = {-1, -1}, bits_off_magtab[2] = {0, 0}, bits_smem[2] = {0, 0};
+    bool bits_ok[2] = {false, false};
 };
 // generic QC tables (syndrome phase of the int8 kernel, generic layered kernel)
 struct QcEdgeAux {       // 8 bytes

@@ -87,7 +87,9 @@ int main(int argc, char **argv)
                 std::memcpy(&h, p.data(), sizeof(h));
                 bytes_ba += p.size(); ++pk_ba;
                 KeyBlock *blk = block_of(A, h.epoch);
-                if (h.subtype == SUBTYPE_LDPC_NACK) alice.on_nack(*blk, (const char *)p.data(), a2b);
+                if (h.subtype == SUBTYPE_LDPC_NACK) {
+                    if (int rc = alice.on_nack(*blk, (const char *)p.data(), a2b)) { std::fprintf(stderr, "on_nack: error %d\n", rc); return 3; }
+                }
                 else if (h.subtype == SUBTYPE_LDPC_DONE) {
                     bool confirmed = false;
                     if (int rc = alice.on_done(*blk, (const char *)p.data(), a2b, confirmed)) { std::fprintf(stderr, "on_done: error %d\n", rc); return 3; }
@@ -97,10 +99,11 @@ int main(int argc, char **argv)
         }
         const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
-        long leak = 0, corrected = 0, diff_blocks = 0;
+        long leak = 0, leak_bob = 0, corrected = 0, diff_blocks = 0;
         std::map<int, int> round_hist;
         for (int b = 0; b < n_blocks; ++b) {
             leak += A[b].leakageBits;
+            leak_bob += B[b].leakageBits;
             corrected += B[b].correctedErrors;
             if (ka[b] != kb[b]) ++diff_blocks;
             round_hist[bob.last_rounds_[A[b].startEpoch]]++;
@@ -112,11 +115,11 @@ int main(int argc, char **argv)
         }
         const double key_bits = (double)n_blocks * workbits;
         std::printf("{\"blocks\": %d, \"workbits\": %d, \"qber\": %.4f, \"frames_per_block\": %d, \"initial_rows\": %d, "
-                    "\"turns\": %d, \"done\": %d, \"blocks_differ\": %ld, \"leak_bits\": %ld, \"corrected_errors\": %ld, "
+                    "\"turns\": %d, \"done\": %d, \"blocks_differ\": %ld, \"leak_bits\": %ld, \"leak_bits_bob\": %ld, \"corrected_errors\": %ld, "
                     "\"efficiency\": %.4f, \"packets_a2b\": %zu, \"packets_b2a\": %zu, \"bytes_a2b\": %zu, \"bytes_b2a\": %zu, "
                     "\"wall_s\": %.6f, \"reconciled_key_bits_per_s\": %.1f, \"crc_mismatches\": %d, \"round_hist\": {",
                     n_blocks, workbits, qber, (workbits + fam->K() - 1) / fam->K(), fam->initial_rows(qber), turns, done,
-                    diff_blocks, leak, corrected, leak / (key_bits * h2(qber)), pk_ab, pk_ba, bytes_ab, bytes_ba, wall,
+                    diff_blocks, leak, leak_bob, corrected, leak / (key_bits * h2(qber)), pk_ab, pk_ba, bytes_ab, bytes_ba, wall,
                     key_bits / wall, alice.mismatches());
         bool first = true;
         for (auto &kv : round_hist) { std::printf("%s\"%d\": %d", first ? "" : ", ", kv.first, kv.second); first = false; }

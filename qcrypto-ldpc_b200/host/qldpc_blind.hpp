@@ -21,8 +21,13 @@
 //   compares them with the CRCs of her own frames (the confirmation step the reference planned, EC/README_LDPC.md:784-788);
 //   a frame whose CRC differs is revealed (subtype 11 with reveal=1) and Bob answers with a new LDPC_DONE;
 //   when all agree both sides call privAmp_sendPrivAmpMsgAndPrivAmp (cascade_biconf.c:892)
-// Leakage: every parity bit sent counts once in pb->leakageBits (EC/subcomponents/priv_amp.c:47,166); a revealed frame
-// counts its K key bits.  Bit vectors are MSB-first 32-bit words (EC/subcomponents/helpers.h:65-68), packets start with
+// Leakage: every parity bit sent counts once in pb->leakageBits (EC/subcomponents/priv_amp.c:47,166), a revealed frame
+// counts its K key bits, and the confirmation counts 32 bits per frame the first time the frame's CRC-32 crosses the
+// channel (CRC-32 is affine in the key: 32 linear parities, exactly like the parity bits cascade_biconf.c counts with
+// leakageBits++).  Both sides keep the same count (Bob's KeyBlock.leakageBits mirrors Alice's).
+// Received packets are not trusted: every length, index and rate field is checked against totalLengthInBytes and the
+// block before anything is copied; a violation returns an ecd2 error code (the reference handlers do the same, e.g.
+// qber_estim.c:372 returns 52).  Bit vectors are MSB-first 32-bit words (EC/subcomponents/helpers.h:65-68), packets start with
 // EcPktHdr_Base (EC/definitions/packets.h:65-71), host-endian, below transferd's 10 000-byte cap per frame
 // (remotecrypto/transferd.h:139): a packet carries at most `frames_per_packet` frames.
 //
@@ -55,6 +60,8 @@ enum : uint32_t {                       // continues EC_SUBTYPES (packets.h:46-5
     SUBTYPE_LDPC_DONE = 12,
 };
 constexpr int ERR_LDPC_UNSUPPORTED = 81;   // errormessage[81] "Unsupported functionality" (EC/ecd2.h:333)
+constexpr int ERR_LDPC_NO_BLOCK = 49;      // errormessage[49] "cannot find processBlock in list"
+constexpr int ERR_LDPC_BAD_PACKET = 85;    // appended by integration/ecd2_ldpc.patch: "LDPC packet inconsistent with its block"
 
 struct EcPktHdr_Base {                  // EC/definitions/packets.h:65-71
     uint32_t tag, totalLengthInBytes, subtype, epoch, numberOfEpochs;
@@ -175,6 +182,14 @@ Packet make_packet(uint32_t subtype, const KeyBlock &b, const H &hdr_fields, siz
     return p;
 }
 inline int frames_of(const KeyBlock &b, int K) { return (b.workbits + K - 1) / K; }
+// header H at the start of a received packet whose declared length must be exactly sizeof(H) + payload(H) bytes
+template <class H>
+bool read_header(const char *buf, uint32_t subtype, H &h)
+{
+    std::memcpy(&h, buf, sizeof(H));
+    return h.base.tag == EC_PACKET_TAG && h.base.subtype == subtype && h.base.totalLengthInBytes >= sizeof(H);
+}
+inline bool payload_is(const EcPktHdr_Base &b, size_t header, uint64_t payload) { return (uint64_t)b.totalLengthInBytes == header + payload; }
 // key bits of frame f of a block as kwords words (the last frame is zero padded on both sides)
 inline void copy_frame_key(const KeyBlock &b, int f, int kwords, uint32_t *dst)
 {
@@ -229,6 +244,8 @@ public:
                             (size_t)fam_->max_rows() * zw * 4);
             f0 += s.frames;
             s.rows_sent.assign(s.frames, fam_->initial_rows(b->localError));
+            s.revealed.assign(s.frames, 0);
+            s.crc_seen.assign(s.frames, 0);
             const int m0 = s.rows_sent[0];
             for (int first = 0; first < s.frames; first += fam_->prm.frames_per_packet) {
                 const int n = std::min(fam_->prm.frames_per_packet, s.frames - first);
@@ -246,40 +263,53 @@ public:
         return 0;
     }
 
-    // handler for SUBTYPE_LDPC_NACK: send DELTA more parity rows of the listed frames (or the key bits after the last row)
+    // handler for SUBTYPE_LDPC_NACK: send DELTA more parity rows of the listed frames (or the key bits after the last row).
+    // Frames of one NACK may sit at different rates (failures of several decode groups are answered together): they are
+    // grouped by the rows already sent, one MORE packet per (from, to) and at most frames_per_packet frames.
     int on_nack(KeyBlock &b, const char *receivebuf, std::vector<Packet> &send)
     {
         EcPktHdr_LdpcNack in;
-        std::memcpy(&in, receivebuf, sizeof(in));
+        if (!detail::read_header(receivebuf, SUBTYPE_LDPC_NACK, in)) return ERR_LDPC_BAD_PACKET;
+        auto sit = st_.find(b.startEpoch);
+        if (sit == st_.end()) return ERR_LDPC_NO_BLOCK;
+        State &s = sit->second;
+        if (in.n_failed == 0 || in.n_failed > (uint32_t)s.frames || !detail::payload_is(in.base, sizeof(in), 4ull * in.n_failed))
+            return ERR_LDPC_BAD_PACKET;
         const uint32_t *idx = reinterpret_cast<const uint32_t *>(receivebuf + sizeof(in));
-        State &s = st_.at(b.startEpoch);
         const int zw = fam_->zwords(), kw = fam_->kwords(), R = fam_->max_rows();
-        // frames of one NACK are at the same rate (they were decoded together)
-        for (uint32_t first = 0; first < in.n_failed; first += (uint32_t)fam_->prm.frames_per_packet) {
-            const uint32_t n = std::min<uint32_t>((uint32_t)fam_->prm.frames_per_packet, in.n_failed - first);
-            const int from = s.rows_sent[idx[first]];
+        std::map<int, std::vector<uint32_t>> by_rate;
+        for (uint32_t k = 0; k < in.n_failed; ++k) {
+            if (idx[k] >= (uint32_t)s.frames) return ERR_LDPC_BAD_PACKET;
+            by_rate[s.rows_sent[idx[k]]].push_back(idx[k]);
+        }
+        for (auto &kv : by_rate) {
+            const int from = kv.first;
+            const std::vector<uint32_t> &fr = kv.second;
             const bool reveal = from >= R;
             const int to = reveal ? R : std::min(R, from + fam_->prm.delta_rows);
             const size_t per = reveal ? (size_t)kw * 4 : (size_t)(to - from) * zw * 4;
-            EcPktHdr_LdpcMore h{};
-            h.round = in.round; h.n_frames = n; h.row_from = (uint32_t)from; h.row_to = (uint32_t)to; h.reveal = reveal;
-            Packet p = detail::make_packet(SUBTYPE_LDPC_MORE, b, h, (size_t)n * 4 + n * per);
-            std::memcpy(p.data() + sizeof(h), idx + first, (size_t)n * 4);
-            for (uint32_t k = 0; k < n; ++k) {
-                const int f = (int)idx[first + k];
-                uint8_t *dst = p.data() + sizeof(h) + (size_t)n * 4 + k * per;
-                if (reveal) {
-                    std::vector<uint32_t> key(kw);
-                    detail::copy_frame_key(b, f, kw, key.data());
-                    std::memcpy(dst, key.data(), per);
-                    b.leakageBits += fam_->K();
-                } else {
-                    std::memcpy(dst, s.parity.data() + ((size_t)f * R + from) * zw, per);
-                    b.leakageBits += (to - from) * fam_->z;
-                    s.rows_sent[f] = to;
+            for (size_t first = 0; first < fr.size(); first += (size_t)fam_->prm.frames_per_packet) {
+                const uint32_t n = (uint32_t)std::min<size_t>((size_t)fam_->prm.frames_per_packet, fr.size() - first);
+                EcPktHdr_LdpcMore h{};
+                h.round = in.round; h.n_frames = n; h.row_from = (uint32_t)from; h.row_to = (uint32_t)to; h.reveal = reveal;
+                Packet p = detail::make_packet(SUBTYPE_LDPC_MORE, b, h, (size_t)n * 4 + n * per);
+                std::memcpy(p.data() + sizeof(h), fr.data() + first, (size_t)n * 4);
+                for (uint32_t k = 0; k < n; ++k) {
+                    const int f = (int)fr[first + k];
+                    uint8_t *dst = p.data() + sizeof(h) + (size_t)n * 4 + k * per;
+                    if (reveal) {
+                        std::vector<uint32_t> key(kw);
+                        detail::copy_frame_key(b, f, kw, key.data());
+                        std::memcpy(dst, key.data(), per);
+                        if (!s.revealed[f]) { b.leakageBits += fam_->K(); s.revealed[f] = 1; }
+                    } else {
+                        std::memcpy(dst, s.parity.data() + ((size_t)f * R + from) * zw, per);
+                        b.leakageBits += (to - from) * fam_->z;
+                        s.rows_sent[f] = to;
+                    }
                 }
+                send.push_back(std::move(p));
             }
-            send.push_back(std::move(p));
         }
         return 0;
     }
@@ -289,10 +319,18 @@ public:
     int on_done(KeyBlock &b, const char *receivebuf, std::vector<Packet> &send, bool &confirmed)
     {
         EcPktHdr_LdpcDone in;
-        std::memcpy(&in, receivebuf, sizeof(in));
+        if (!detail::read_header(receivebuf, SUBTYPE_LDPC_DONE, in)) return ERR_LDPC_BAD_PACKET;
+        auto sit = st_.find(b.startEpoch);
+        if (sit == st_.end()) return ERR_LDPC_NO_BLOCK;
+        State &s = sit->second;
+        if (in.frames != (uint32_t)s.frames || !detail::payload_is(in.base, sizeof(in), 4ull * in.frames)) return ERR_LDPC_BAD_PACKET;
         const uint32_t *theirs = reinterpret_cast<const uint32_t *>(receivebuf + sizeof(in));
         std::vector<uint32_t> mine;
         if (detail::block_crcs(b, fam_->K(), fam_->kwords(), fam_->prm.device, mine)) return ERR_LDPC_UNSUPPORTED;
+        // the CRC-32 of a frame is 32 linear parities of its key bits in the clear: counted once per frame (a frame that had
+        // been revealed before has nothing left to leak)
+        for (int f = 0; f < s.frames; ++f)
+            if (!s.crc_seen[f]) { s.crc_seen[f] = 1; if (!s.revealed[f]) b.leakageBits += 32; }
         std::vector<uint32_t> bad;
         for (uint32_t f = 0; f < in.frames && f < mine.size(); ++f)
             if (mine[f] != theirs[f]) bad.push_back(f);
@@ -310,7 +348,7 @@ public:
                 std::vector<uint32_t> key(kw);
                 detail::copy_frame_key(b, (int)bad[first + k], kw, key.data());
                 std::memcpy(p.data() + sizeof(h) + (size_t)n * 4 + (size_t)k * kw * 4, key.data(), (size_t)kw * 4);
-                b.leakageBits += fam_->K();
+                if (!s.revealed[bad[first + k]]) { b.leakageBits += fam_->K() - 32; s.revealed[bad[first + k]] = 1; }   // its CRC was counted
             }
             send.push_back(std::move(p));
         }
@@ -319,7 +357,12 @@ public:
     int mismatches() const { return mismatches_; }
 
 private:
-    struct State { int frames = 0; std::vector<uint32_t> parity; std::vector<int> rows_sent; };
+    struct State {
+        int frames = 0;
+        std::vector<uint32_t> parity;
+        std::vector<int> rows_sent;
+        std::vector<char> revealed, crc_seen;   // leakage is counted once per revealed frame / disclosed CRC
+    };
     std::shared_ptr<CodeFamily> fam_;
     std::map<uint32_t, State> st_;
     int mismatches_ = 0;
@@ -337,16 +380,26 @@ public:
         const int zw = fam_->zwords(), R = fam_->max_rows(), K = fam_->K();
         for (size_t i = 0; i < pkts.size(); ++i) {
             EcPktHdr_LdpcParity in;
-            std::memcpy(&in, pkts[i], sizeof(in));
+            if (!detail::read_header(pkts[i], SUBTYPE_LDPC_PARITY, in)) return ERR_LDPC_BAD_PACKET;
             KeyBlock &b = *blocks[i];
+            const int nf = detail::frames_of(b, K);
+            if (in.z != (uint32_t)fam_->z || in.rows < 1 || in.rows > (uint32_t)R || in.frames < 1 || in.frames > (uint32_t)nf ||
+                in.first_frame > (uint32_t)nf - in.frames || in.workbits != (uint32_t)b.workbits ||
+                !detail::payload_is(in.base, sizeof(in), 4ull * in.frames * in.rows * zw))
+                return ERR_LDPC_BAD_PACKET;
             State &s = st_[b.startEpoch];
             if (s.frames == 0) {
-                s.frames = detail::frames_of(b, K);
+                s.frames = nf;
                 s.parity.assign((size_t)s.frames * R * zw, 0u);
                 s.rows.assign(s.frames, 0);
                 s.done.assign(s.frames, 0);
+                s.was_revealed.assign(s.frames, 0);
+                s.crc_sent.assign(s.frames, 0);
                 s.received = 0;
             }
+            for (uint32_t f = 0; f < in.frames; ++f)
+                if (s.rows[in.first_frame + f] != 0) return ERR_LDPC_BAD_PACKET;   // a frame's first rows arrive once
+            b.leakageBits += (int)(in.frames * in.rows) * fam_->z;
             for (uint32_t f = 0; f < in.frames; ++f) {
                 std::memcpy(s.parity.data() + (size_t)(in.first_frame + f) * R * zw,
                             pkts[i] + sizeof(in) + (size_t)f * in.rows * zw * 4, (size_t)in.rows * zw * 4);
@@ -372,11 +425,19 @@ public:
         std::vector<Work> work;
         for (size_t i = 0; i < pkts.size(); ++i) {
             EcPktHdr_LdpcMore in;
-            std::memcpy(&in, pkts[i], sizeof(in));
+            if (!detail::read_header(pkts[i], SUBTYPE_LDPC_MORE, in)) return ERR_LDPC_BAD_PACKET;
             KeyBlock &b = *blocks[i];
-            State &s = st_.at(b.startEpoch);
-            const uint32_t *idx = reinterpret_cast<const uint32_t *>(pkts[i] + sizeof(in));
+            auto sit = st_.find(b.startEpoch);
+            if (sit == st_.end()) return ERR_LDPC_NO_BLOCK;
+            State &s = sit->second;
+            if (in.n_frames < 1 || in.n_frames > (uint32_t)s.frames || in.row_to > (uint32_t)R || in.row_from > in.row_to ||
+                (!in.reveal && in.row_from == in.row_to))
+                return ERR_LDPC_BAD_PACKET;
             const size_t per = in.reveal ? (size_t)kw * 4 : (size_t)(in.row_to - in.row_from) * zw * 4;
+            if (!detail::payload_is(in.base, sizeof(in), (4ull + per) * in.n_frames)) return ERR_LDPC_BAD_PACKET;
+            const uint32_t *idx = reinterpret_cast<const uint32_t *>(pkts[i] + sizeof(in));
+            for (uint32_t k = 0; k < in.n_frames; ++k)   // every index inside the block; new rows continue where the frame stands
+                if (idx[k] >= (uint32_t)s.frames || (!in.reveal && (uint32_t)s.rows[idx[k]] != in.row_from)) return ERR_LDPC_BAD_PACKET;
             const char *payload = pkts[i] + sizeof(in) + (size_t)in.n_frames * 4;
             for (uint32_t k = 0; k < in.n_frames; ++k) {
                 const int f = (int)idx[k];
@@ -387,11 +448,13 @@ public:
                     store_frame(b, f, hers.data(), mine.data());
                     s.done[f] = 1;
                     ++s.revealed;
+                    if (!s.was_revealed[f]) { b.leakageBits += fam_->K() - (s.crc_sent[f] ? 32 : 0); s.was_revealed[f] = 1; }
                     if (s.finished) { s.finished = false; ++s.pending; }   // a frame revealed after a CRC mismatch: answer again
                     touched_[&b] = 1;
                 } else {
                     std::memcpy(s.parity.data() + ((size_t)f * R + in.row_from) * zw, payload + k * per, per);
                     s.rows[f] = (int)in.row_to;
+                    b.leakageBits += (int)(in.row_to - in.row_from) * fam_->z;
                     work.push_back(Work{&b, f});
                 }
             }
@@ -414,7 +477,7 @@ private:
         bool queued = false, finished = false;
         std::vector<uint32_t> parity;
         std::vector<int> rows;
-        std::vector<char> done;
+        std::vector<char> done, was_revealed, crc_sent;
     };
     struct Work { KeyBlock *b; int f; };
 
@@ -511,6 +574,8 @@ private:
                 if (*c == b->startEpoch) { b->mainBufPtr[0] ^= 0x00010000u; corrupt_.erase(c); break; }
             std::vector<uint32_t> crc;
             if (detail::block_crcs(*b, fam_->K(), fam_->kwords(), fam_->prm.device, crc)) return ERR_LDPC_UNSUPPORTED;
+            for (int f = 0; f < s.frames; ++f)   // 32 disclosed parities per frame, once (Alice counts the same on receipt)
+                if (!s.crc_sent[f]) { s.crc_sent[f] = 1; if (!s.was_revealed[f]) b->leakageBits += 32; }
             EcPktHdr_LdpcDone h{};
             h.rounds = (uint32_t)s.round; h.frames_revealed = (uint32_t)s.revealed; h.frames = (uint32_t)crc.size();
             Packet p = detail::make_packet(SUBTYPE_LDPC_DONE, *b, h, crc.size() * 4);

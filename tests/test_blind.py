@@ -85,6 +85,7 @@ def test_blind_reconciliation_matches_oracle_model(driver, q, O, data_dir, tmp_p
     codes = {}
     leak = corrected = 0
     rounds = []
+    revealed = set()
     for b in range(n_blocks):
         a_pad = np.zeros(frames * K, np.uint8); a_pad[:workbits] = A[b, :workbits]
         b_pad = np.zeros(frames * K, np.uint8); b_pad[:workbits] = B[b, :workbits]
@@ -113,6 +114,7 @@ def test_blind_reconciliation_matches_oracle_model(driver, q, O, data_dir, tmp_p
                 again = []
                 for f in nxt:
                     if rows[f] >= R:      # every row sent and still failing: Alice reveals the frame
+                        revealed.add((b, f))
                         leak += K
                         corrected += int((a_pad[f * K:(f + 1) * K] != b_pad[f * K:(f + 1) * K]).sum())
                         b_pad[f * K:(f + 1) * K] = a_pad[f * K:(f + 1) * K]
@@ -124,7 +126,9 @@ def test_blind_reconciliation_matches_oracle_model(driver, q, O, data_dir, tmp_p
                 nxt = again
             todo = nxt
         rounds.append(rnd)
-    assert res["leak_bits"] == leak
+    # confirmation: one CRC-32 per frame in the clear = 32 linear parities, counted once for every frame that was not revealed
+    leak += 32 * (n_blocks * frames - len(revealed))
+    assert res["leak_bits"] == leak == res["leak_bits_bob"]
     assert res["corrected_errors"] == corrected == int((A ^ B)[:, :workbits].sum())
     hist = {}
     for r in rounds:
@@ -149,7 +153,8 @@ def test_blind_many_blocks_throughput_line(driver, data_dir, tmp_path):
 @pytest.mark.gpu
 def test_blind_crc_confirmation_catches_a_wrong_frame(driver, q, data_dir, tmp_path):
     """the confirmation step (one CRC-32 per frame in LDPC_DONE): a bit flipped in Bob's block after decoding is caught by
-    Alice, the frame is revealed, and the keys end up identical; the extra leakage is the K bits of that frame"""
+    Alice, the frame is revealed, and the keys end up identical; the extra leakage is the K bits of that frame minus the 32
+    bits its CRC had already cost"""
     n_blocks, workbits, qber = 2, 40000, 0.03
     A, B = _write_keys(tmp_path / "k.bin", n_blocks, workbits, qber, seed=77)
     args = [driver, "%s/NR_1_1_384.qc" % data_dir, str(tmp_path / "k.bin"), str(tmp_path / "c.bin"), "1.9", "2", "20"]
@@ -159,7 +164,31 @@ def test_blind_crc_confirmation_catches_a_wrong_frame(driver, q, data_dir, tmp_p
     assert p.returncode == 0, (p.stderr, p.stdout)
     res = json.loads(p.stdout)
     assert res["crc_mismatches"] == 1 and res["blocks_differ"] == 0 and res["done"] == n_blocks
-    assert res["leak_bits"] == clean["leak_bits"] + 22 * 384
+    assert res["leak_bits"] == clean["leak_bits"] + 22 * 384 - 32 == res["leak_bits_bob"]   # its CRC had been counted already
     words = (workbits + 31) // 32
     got = q.unpack_bits(np.frombuffer(open(tmp_path / "c.bin", "rb").read(), dtype="<u4").reshape(n_blocks, words), words * 32)
     assert (got[:, :workbits] == A[:, :workbits]).all()
+
+
+@pytest.fixture(scope="module")
+def packet_tester(tmp_path_factory, q):
+    exe = str(tmp_path_factory.mktemp("blindpk") / "test_blind_packets")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", HOST,
+                           os.path.join(HOST, "test_blind_packets.cpp"), "-o", exe, q.LIB_PATH,
+                           "-Wl,-rpath," + os.path.dirname(q.LIB_PATH)])
+    return exe
+
+
+def test_bob_rejects_malformed_packets_without_touching_memory(packet_tester, data_dir):
+    """every field of a received packet is checked against totalLengthInBytes and the block before anything is
+    copied (lengths, z, rows <= R, frame indices, row ranges); runs on the CPU -- rejection happens before any decode"""
+    p = subprocess.run([packet_tester, "%s/NR_1_1_384.qc" % data_dir, "bob"], capture_output=True, text=True)
+    assert p.returncode == 0, (p.stdout, p.stderr)
+    assert "bob: all malformed packets rejected" in p.stdout
+
+
+@pytest.mark.gpu
+def test_alice_rejects_malformed_packets(packet_tester, data_dir):
+    p = subprocess.run([packet_tester, "%s/NR_1_1_384.qc" % data_dir, "alice"], capture_output=True, text=True)
+    assert p.returncode == 0, (p.stdout, p.stderr)
+    assert "alice: all malformed packets rejected" in p.stdout

@@ -276,7 +276,7 @@ def test_bit_input_fused_synthesis_equals_two_kernel_path(q, O, data_dir, name, 
     b = plain.decode_bits(noisy_p, 13.0, 31.0, known_mask=km, punct_mask=pm, syndrome=syn)
     for u, v in zip(a, b):
         assert (u == v).all()
-    assert fused.stats()["kernel_launches"] < plain.stats()["kernel_launches"]      # no LLR synthesis launches
+    assert fused.stats()["kernel_launches"] <= plain.stats()["kernel_launches"]     # one magnitude table instead of one LLR synthesis per chunk
     sel = rng.choice(F, 40, replace=False)
     llr = plain.make_llr(noisy_p[sel], 13.0, 31.0, known_mask=km, punct_mask=pm)
     hard, oit, ook, _ = oc.batch_layered_fixed_i8(llr, None if syn is None else q.unpack_bits(syn[sel], oc.M), rule=O.RULE_NMS,
@@ -316,3 +316,56 @@ def test_llr_magnitudes_outside_the_dtype_range_are_rejected(q, data_dir):
             dec.decode_bits(bits, noisy, known)
     assert (dec.make_llr(bits, 127.0, 127.0) == 127).all()
     dec.close()
+
+
+@pytest.mark.parametrize("with_syndrome", [False, True])
+def test_zero_copy_decode_bits_on_pinned_host_buffers(q, O, data_dir, with_syndrome):
+    """qldpc_decode_bits with PINNED host buffers: the decoder kernel reads the packed bits and writes bits / ok / iteration
+    counts in place over PCIe (one launch, no staging copies); results equal the chunked copy pipeline (pageable numpy
+    buffers, and pinned buffers with QLDPC_FLAG_NO_ZERO_COPY) and the oracle"""
+    import torch
+    path = "%s/NR_1_1_384.qc" % data_dir
+    oc = O.Code.from_qc(path)
+    code = q.Code.from_qc_file(path)
+    kw = dict(schedule=q.SCHED_LAYERED, rule=q.RULE_NMS, dtype=q.DTYPE_I8, max_iter=10, early_stop=True, norm_factor=0.75,
+              out_mode=q.OUT_INFO)
+    dec, staged = q.Decoder(code, **kw), q.Decoder(code, flags=q.FLAG_NO_ZERO_COPY, **kw)
+    F = 4000
+    rng = np.random.default_rng(11)
+    known = np.zeros(oc.N, np.uint8)
+    if with_syndrome:
+        x = rng.integers(0, 2, (F, oc.N)).astype(np.uint8)
+        syn = dec.syndrome(q.pack_bits(x))
+        noisy = x ^ (rng.random((F, oc.N)) < 0.04).astype(np.uint8)
+        want = x[:, :oc.K]
+    else:
+        msg = rng.integers(0, 2, (F, oc.K)).astype(np.uint8)
+        noisy = q.unpack_bits(dec.encode_nr(q.pack_bits(msg)), oc.N)
+        noisy[:, :oc.K] ^= (rng.random((F, oc.K)) < 0.04).astype(np.uint8)
+        known[oc.K:] = 1
+        syn, want = None, msg
+    bits_np, km = q.pack_bits(noisy), q.pack_bits(known)
+    ref = dec.decode_bits(bits_np, 12.0, 31.0, known_mask=km, syndrome=syn)          # pageable: chunked pipeline
+    launches0 = dec.stats()["kernel_launches"]
+    h_bits = torch.from_numpy(bits_np.view(np.int32)).pin_memory()
+    h_syn = None if syn is None else torch.from_numpy(syn.view(np.int32)).pin_memory()
+    h_out = torch.zeros((F, dec.out_words), dtype=torch.int32).pin_memory()
+    h_ok = torch.zeros(F, dtype=torch.uint8).pin_memory()
+    h_it = torch.zeros(F, dtype=torch.int16).pin_memory()
+    for d in (dec, staged):
+        h_out.zero_(); h_ok.zero_(); h_it.zero_()
+        rc = q.lib().qldpc_decode_bits(d.h, h_bits.data_ptr(), km.ctypes.data, None, 12.0, 31.0,
+                                       None if h_syn is None else h_syn.data_ptr(), F, h_out.data_ptr(), h_ok.data_ptr(),
+                                       h_it.data_ptr())
+        assert rc == 0
+        assert (h_out.numpy().view(np.uint32) == ref[0]).all() and (h_ok.numpy().astype(bool) == ref[1]).all()
+        assert (h_it.numpy().view(np.uint16) == ref[2]).all()
+    assert dec.stats()["kernel_launches"] - launches0 == 2          # magnitude table + ONE decode launch
+    assert ref[1].all() and (q.unpack_bits(ref[0], oc.K) == want).all()
+    sel = rng.choice(F, 32, replace=False)
+    llr = dec.make_llr(bits_np[sel], 12.0, 31.0, known_mask=km)
+    hard, oit, ook, _ = oc.batch_layered_fixed_i8(llr, None if syn is None else q.unpack_bits(syn[sel], oc.M), rule=O.RULE_NMS,
+                                                  n_ite=10, early_stop=True, norm_eighths=6)
+    assert (oit == ref[2][sel]).all() and (hard[:, :oc.K] == want[sel]).all()
+    dec.close()
+    staged.close()

@@ -83,6 +83,7 @@ struct EcPktHdr_LdpcMore {              // followed by n_frames indices, then pe
 struct EcPktHdr_LdpcDone {              // followed by `frames` CRC-32 values (qldpc_crc32_frames over the K key bits of a frame)
     EcPktHdr_Base base;
     uint32_t rounds, frames_revealed, frames;
+    uint32_t corrected_errors;          // Bob's pb->correctedErrors: Alice needs it for the error-rate estimate of priv_amp.c:118
 };
 
 // the ProcessBlock fields an LDPC handler touches (EC/definitions/processblock.h:102-129)
@@ -335,7 +336,7 @@ public:
         for (uint32_t f = 0; f < in.frames && f < mine.size(); ++f)
             if (mine[f] != theirs[f]) bad.push_back(f);
         confirmed = bad.empty() && in.frames == mine.size();
-        if (confirmed) { st_.erase(b.startEpoch); return 0; }
+        if (confirmed) { b.correctedErrors = (int)in.corrected_errors; st_.erase(b.startEpoch); return 0; }
         mismatches_ += (int)bad.size();
         const int kw = fam_->kwords();
         for (size_t first = 0; first < bad.size(); first += (size_t)fam_->prm.frames_per_packet) {
@@ -578,6 +579,7 @@ private:
                 if (!s.crc_sent[f]) { s.crc_sent[f] = 1; if (!s.was_revealed[f]) b->leakageBits += 32; }
             EcPktHdr_LdpcDone h{};
             h.rounds = (uint32_t)s.round; h.frames_revealed = (uint32_t)s.revealed; h.frames = (uint32_t)crc.size();
+            h.corrected_errors = (uint32_t)b->correctedErrors;
             Packet p = detail::make_packet(SUBTYPE_LDPC_DONE, *b, h, crc.size() * 4);
             std::memcpy(p.data() + sizeof(h), crc.data(), crc.size() * 4);
             send.push_back(std::move(p));

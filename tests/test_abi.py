@@ -17,6 +17,26 @@ def _header_symbols():
     return sorted(set(re.findall(r"\b(qldpc_[a-z0-9_]+)\s*\(", src)))
 
 
+def test_ecd2_face_exports_every_declared_symbol(q):
+    """include/qldpc_ecd2.h: the C face the patched ecd2 daemon binds (integration/ecd2_ldpc.patch); plain C"""
+    import subprocess
+    import tempfile
+    src = open(os.path.join(ROOT, "include", "qldpc_ecd2.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(qldpc_ecd2_[a-z0-9_]+)\s*\(", src)))
+    assert len(declared) == 8
+    for name in declared:
+        assert hasattr(q.lib(), name), "libqldpc_b200.so does not export " + name
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c")
+        open(c, "w").write('#include "qldpc_ecd2.h"\nint main(void){qldpc_ecd2_config c; qldpc_ecd2 *x = 0; qldpc_ecd2_config_default(&c);'
+                           ' return qldpc_ecd2_open(&c, &x) == 81 ? 0 : 1;}\n')     # no base graph -> 81, no crash
+        exe = os.path.join(d, "t")
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), c, "-o", exe,
+                               q.LIB_PATH, "-Wl,-rpath," + os.path.dirname(q.LIB_PATH)])
+        assert subprocess.call([exe]) == 0
+
+
 def test_library_exports_every_declared_symbol(q):
     L = q.lib()
     declared = _header_symbols()

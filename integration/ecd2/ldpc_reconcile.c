@@ -117,6 +117,14 @@ int ldpc_onNack(ProcessBlock *pb, char *receivebuf) { return ldpc_handle(pb, rec
 int ldpc_onMore(ProcessBlock *pb, char *receivebuf) { return ldpc_handle(pb, receivebuf, PROC_ROLE_EC_FOLLOWER); }
 int ldpc_onDone(ProcessBlock *pb, char *receivebuf) { return ldpc_handle(pb, receivebuf, PROC_ROLE_EC_INITIATOR); }
 
+int ldpc_receivePrivAmpMsg(ProcessBlock *pb, char *receivebuf) {
+  /* privAmp_doPrivAmp sizes the final key from the LOCAL pb->leakageBits and ignores the `lostbits` argument it is handed
+     (priv_amp.c:91,166).  Both sides must cut the same number of bits: take the initiator's figure, which already carries
+     the cancellation of the Cascade-only redundancy credit (see ldpc_handle). */
+  pb->leakageBits = ((EcPktHdr_StartPrivAmp *)receivebuf)->lostbits;
+  return privAmp_receivePrivAmpMsg(pb, receivebuf);
+}
+
 void ldpc_releaseBlock(ProcessBlock *pb) {
   if (ldpcContext) qldpc_ecd2_release(ldpcContext, pb->startEpoch);
 }

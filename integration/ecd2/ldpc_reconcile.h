@@ -28,6 +28,8 @@ int ldpc_onParity(ProcessBlock *pb, char *receivebuf);
 int ldpc_onNack(ProcessBlock *pb, char *receivebuf);
 int ldpc_onMore(ProcessBlock *pb, char *receivebuf);
 int ldpc_onDone(ProcessBlock *pb, char *receivebuf);
+/// Subtype 8 on an LDPC block: privAmp_receivePrivAmpMsg with the initiator's leakage figure installed first
+int ldpc_receivePrivAmpMsg(ProcessBlock *pb, char *receivebuf);
 /// drops the per-block protocol state kept in the library (called by freeLdpcData)
 void ldpc_releaseBlock(ProcessBlock *pb);
 

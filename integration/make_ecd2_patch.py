@@ -89,7 +89,7 @@ def main():
         ("// ALGORITHM DATA STRUCT FOR PROCESS BLOCK\n",
          "/// @name LDPC PACKET MANAGERS (subtypes 8..12; 8 = privacy amplification, as for cascade)\n/// @{\n"
          "const PacketHandlerArray ALG_PKTHNDLRS_LDPC_INITIATOR = {\n"
-         "    privAmp_receivePrivAmpMsg,                  ///< Subtype 8\n"
+         "    ldpc_receivePrivAmpMsg,                     ///< Subtype 8\n"
          "    ldpc_onParity,                              ///< Subtype 9  (follower only: answers 45 here)\n"
          "    ldpc_onNack,                                ///< Subtype 10\n"
          "    ldpc_onMore,                                ///< Subtype 11 (follower only)\n"
@@ -99,7 +99,7 @@ def main():
          "    8 + sizeof(ALG_PKTHNDLRS_LDPC_INITIATOR)    // LAST_SUBTYPE, automatically calculated\n"
          "        / sizeof(ALG_PKTHNDLRS_LDPC_INITIATOR[0]) - 1,\n    False                                       // allowNullPrcBlks\n};\n"
          "const PacketHandlerArray ALG_PKTHNDLRS_LDPC_FOLLOWER = {\n"
-         "    privAmp_receivePrivAmpMsg,                  ///< Subtype 8\n"
+         "    ldpc_receivePrivAmpMsg,                     ///< Subtype 8\n"
          "    ldpc_onParity,                              ///< Subtype 9\n"
          "    ldpc_onNack,                                ///< Subtype 10 (initiator only: answers 45 here)\n"
          "    ldpc_onMore,                                ///< Subtype 11\n"

@@ -466,6 +466,8 @@ struct qldpc_decoder_full : qldpc_decoder {
     DevBuf<uint8_t> d_scratch2;
     int gen_grid = 0;
     int flood_block = 0, flood_smem = 0, flood_use_smem = 0;
+    // clustered QC flooding kernel (flooding_qcx.cu): blocks per cluster, co-resident clusters, table bytes
+    int qcx_cl = 0, qcx_clusters = 0, qcx_smem = 0;
 };
 
 static qldpc_decoder_full *full(qldpc_decoder *d) { return static_cast<qldpc_decoder_full *>(d); }
@@ -652,6 +654,25 @@ extern "C" int qldpc_decoder_create(const qldpc_code *code, const qldpc_decoder_
         if (!d->flood_use_smem) {
             d->scratch_msg_bytes = (size_t)d->gen_grid * c.edges * 4;
             d->scratch_app_bytes = (size_t)d->gen_grid * c.n * 4;
+        }
+        // Large quasi-cyclic codes (messages do not fit in shared memory, whole warps per circulant): one frame per cluster
+        // of CL thread blocks, CL chosen so that the state of all frames in flight stays inside L2.
+        if (c.z > 0 && c.z % 32 == 0 && !d->flood_use_smem) {
+            const int smem = flooding_qcx_smem_bytes(c.base_rows, c.base_cols, c.edges / c.z);
+            const size_t state = (size_t)c.edges * flooding_qcx_msg_bytes(cfg->dtype) + (size_t)c.n * flooding_qcx_post_bytes(cfg->dtype);
+            const size_t l2_budget = (size_t)prop.l2CacheSize / 2;
+            for (int cl = 1; cl <= 8 && c.z % (32 * cl) == 0; cl *= 2) {
+                const int n = flooding_qcx_max_clusters(cfg->dtype, cl, smem);
+                if (n < 1) continue;
+                d->qcx_cl = cl; d->qcx_clusters = n; d->qcx_smem = smem;
+                if ((size_t)n * state <= l2_budget) break;
+            }
+            if (d->qcx_cl > 0) {
+                d->kernel_name = "flooding_qc_cluster";
+                d->flood_qc = false;
+                d->scratch_msg_bytes = (size_t)d->qcx_clusters * c.edges * flooding_qcx_msg_bytes(cfg->dtype);
+                d->scratch_app_bytes = (size_t)d->qcx_clusters * c.n * flooding_qcx_post_bytes(cfg->dtype);
+            }
         }
     }
     for (auto &ln : d->lanes.lane)
@@ -885,7 +906,19 @@ static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint3
         p.offset_int = d->offset_int; p.norm_eighths = d->norm_eighths;
         p.vmax = cfg.dtype == QLDPC_DTYPE_I16 ? 32767 : 127;
         p.use_smem = d->flood_use_smem;
-        if (d->flood_qc) {
+        if (d->qcx_cl > 0) {
+            FloodQcxParams xp{};
+            xp.llr = d_llr; xp.syn = d_syndrome; xp.allbits = allbits; xp.ok = d_ok; xp.iters = d_iters;
+            xp.posterior = d_posterior; xp.stats = d->d_stats.p;
+            xp.aux = d->d_qc_aux.p; xp.layers = d->d_qc_layers.p; xp.col_ptr = d->d_qc_col_ptr.p; xp.col_edges = d->d_qc_col_edges.p;
+            xp.c2v = d->d_scratch.p; xp.post = d->d_scratch2.p;
+            xp.F = n_frames; xp.Z = c.z; xp.nnz = c.edges / c.z; xp.N = c.n; xp.M = c.m; xp.brows = c.base_rows; xp.bcols = c.base_cols;
+            xp.cw_words = d->cw_words; xp.syn_words = d->syn_words;
+            xp.max_iter = cfg.max_iter; xp.early_stop = cfg.early_stop; xp.syndrome_depth = cfg.syndrome_depth;
+            xp.rule = cfg.rule; xp.dtype = cfg.dtype; xp.norm = cfg.norm_factor; xp.offset = cfg.offset;
+            xp.offset_int = d->offset_int; xp.norm_eighths = d->norm_eighths; xp.vmax = p.vmax;
+            if ((rc = launch_flooding_qcx(xp, std::min(d->qcx_clusters, n_frames), d->qcx_cl, d->qcx_smem, st))) return rc;
+        } else if (d->flood_qc) {
             FloodQcParams qp{};
             qp.llr = (const float *)d_llr; qp.syn = d_syndrome; qp.allbits = allbits; qp.ok = d_ok; qp.iters = d_iters;
             qp.posterior = (float *)d_posterior; qp.stats = d->d_stats.p;

@@ -1,0 +1,432 @@
+// Flooding belief propagation for LARGE quasi-cyclic codes (the long QKD blocks of BASELINE config 3: N = 65 536, Z = 2 048):
+// one frame per thread-block CLUSTER, state in an L2-resident scratch, float SPA / min-sum and int8 / int16 min-sum.
+//
+// Arithmetic: AFF3CT Decoder_LDPC_BP_flooding<B,Q,Update_rule_{SPA,NMS,OMS}> as the reference instantiates it
+// (BOOT/src/main.cpp:193, decode_siho at :365; "main.cpp (5g-qc)":236-251), restated in
+// oracle/qldpc_oracle.c:ora_decode_flooding_f32 / ora_decode_flooding_fixed -- same sweep structure, same order of every
+// sum and product, same early-stop rule as flooding.cu / flooding_qc.cu.  What differs from those kernels is everything
+// the ncu-less round-1 versions got wrong for a code whose messages (786 KB of fp32 per frame) do not fit on chip:
+//   * they were bound by the LATENCY of dependent global loads (one CTA per frame, a serial loop over 64 variables x dv
+//     edges per thread, table entries fetched from global memory inside it): 0.9 TB/s of message traffic, 14 % of HBM.
+//     Here the circulant tables sit in shared memory and every work item issues ALL its loads (2 x dc in the check phase,
+//     dv + 1 in the variable phase, several items per thread) before the first use: memory-level parallelism instead of
+//     occupancy;
+//   * a frame is worked on by a cluster of CL thread blocks (CL SMs), each owning Z / CL lanes of every circulant, so only
+//     SMs / CL frames are in flight and their messages + posteriors (1.05 MB per frame) stay resident in the 126 MB L2:
+//     the 16 E bytes per sweep are L2 traffic, HBM sees the channel LLRs once per frame.  The phases are
+//     separated by the hardware cluster barrier; the early-termination vote crosses the cluster through distributed
+//     shared memory;
+//   * SPA in fp32 (ex2 / rcp / lg2 special-function units) instead of double-precision libm calls: tanh(|x|/2) as
+//     1 - 2 / (e^|x| + 1) (exact to the last bit near 1, where atanh is ill-conditioned) with an odd series below 0.25, IEEE
+//     division for product / t_j (as the oracle), 2 atanh(r) as ln((1 + r) / (1 - r)) with a series below 0.25.
+//     north_star asks for equal decoded bits and posteriors within 1e-3 relative, not for bit-equal floats; the oracle
+//     stays in double as the checker;
+//   * integer tiers keep their messages in 8 / 16 bits (posteriors in 16 / 32), not in 32-bit words;
+//   * sweep 0 reads no messages at all (they are zero), so the scratch is never cleared.
+#include <cooperative_groups.h>
+
+#include "kernels.hpp"
+
+namespace cg = cooperative_groups;
+
+namespace qldpc {
+
+namespace {
+
+constexpr int kThreads = 512;
+constexpr int kMaxDc = 8;        // check degrees up to this keep their var-to-check values in registers between the passes
+
+// ---- fp32 SPA kernels of the check update ---------------------------------------------------------------------------
+// tanh(a / 2) for a >= 0
+__device__ __forceinline__ float tanh_half(float a)
+{
+    const float h = 0.5f * a, h2 = h * h;
+    const float series = h * (1.0f + h2 * (-0.33333334f + h2 * (0.13333334f + h2 * -0.05396825f)));
+    const float e = __expf(a);                       // ex2.approx: relative error ~2 ulp; +inf for a > 88 -> u = 0
+    const float u = __fdividef(2.0f, e + 1.0f);      // 1 - tanh: its relative error is harmless, the subtraction below is exact-ish
+    return a < 0.25f ? series : 1.0f - u;
+}
+// 2 * atanh(r) for 0 <= r < 1
+__device__ __forceinline__ float two_atanh(float r)
+{
+    const float r2 = r * r;
+    const float series = 2.0f * r * (1.0f + r2 * (0.33333334f + r2 * (0.2f + r2 * (0.14285715f + r2 * 0.11111111f))));
+    const float lg = __logf(__fdividef(1.0f + r, 1.0f - r));
+    return r < 0.25f ? series : lg;
+}
+
+__device__ __forceinline__ int norm8(int v, int k)
+{
+    switch (k) {
+    case 1: return v >> 3;
+    case 2: return v >> 2;
+    case 3: return (v >> 2) + (v >> 3);
+    case 4: return v >> 1;
+    case 5: return (v >> 1) + (v >> 3);
+    case 6: return (v >> 1) + (v >> 2);
+    case 7: return (v >> 1) + (v >> 2) + (v >> 3);
+    default: return v;
+    }
+}
+
+struct RowMeta { int edge_begin, degree; };
+
+// ---- one check (block row `ly`, lane l): reads the posteriors of its variables and its old messages, writes the new ones
+// FIRST: sweep 0, the old messages are zero and not read.  Returns the parity of the hard decisions (early-stop test).
+template <typename MsgT, typename PostT, bool FIRST>
+__device__ __forceinline__ int check_update(const FloodQcxParams &p, const RowMeta ly, const int2 *edges, const PostT *__restrict__ post,
+                                            MsgT *__restrict__ c2v, int l, int Z, int synbit)
+{
+    constexpr bool kFloat = sizeof(PostT) == 4 && sizeof(MsgT) == 4;
+    const int deg = ly.degree;
+    MsgT *cm = c2v + (size_t)ly.edge_begin * Z + l;
+    int sign = synbit, hard = synbit;
+    if (deg <= kMaxDc) {
+        // all loads first, then the arithmetic: 2 x deg requests in flight per thread
+        PostT pv[kMaxDc];
+        MsgT old[kMaxDc];
+#pragma unroll
+        for (int j = 0; j < kMaxDc; ++j) {
+            if (j < deg) {
+                const int2 e = edges[ly.edge_begin + j];            // (block column, shift)
+                int vl = l + e.y;
+                if (vl >= Z) vl -= Z;
+                pv[j] = post[(size_t)e.x * Z + vl];
+                old[j] = FIRST ? (MsgT)0 : cm[(size_t)j * Z];
+            }
+        }
+        if constexpr (kFloat) {
+            float x[kMaxDc], t[kMaxDc];
+            if (p.rule == QLDPC_RULE_SPA) {
+                float product = 1.0f;
+#pragma unroll
+                for (int j = 0; j < kMaxDc; ++j) {
+                    if (j < deg) {
+                        x[j] = pv[j] - old[j];
+                        hard ^= pv[j] < 0.0f;
+                        const float tj = tanh_half(fabsf(x[j]));
+                        t[j] = (tj != 0.0f) ? tj : 1e-12f;
+                        product *= t[j];
+                        sign ^= signbit(x[j]) ? 1 : 0;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < kMaxDc; ++j) {
+                    if (j < deg) {
+                        float rr = product / t[j];
+                        rr = (rr < 1.0f) ? rr : 1.0f - 1.1920929e-07f;
+                        const float mag = two_atanh(rr);
+                        cm[(size_t)j * Z] = (sign ^ (signbit(x[j]) ? 1 : 0)) ? -mag : mag;
+                    }
+                }
+            } else {
+                float min1 = 3.402823466e+38f, min2 = 3.402823466e+38f;
+#pragma unroll
+                for (int j = 0; j < kMaxDc; ++j) {
+                    if (j < deg) {
+                        x[j] = pv[j] - old[j];
+                        hard ^= pv[j] < 0.0f;
+                        const float a = fabsf(x[j]);
+                        sign ^= signbit(x[j]) ? 1 : 0;
+                        min2 = fminf(min2, fmaxf(a, min1));
+                        min1 = fminf(min1, a);
+                    }
+                }
+                const float cst1 = p.rule == QLDPC_RULE_NMS ? min2 * p.norm : fmaxf(0.0f, min2 - p.offset);
+                const float cst2 = p.rule == QLDPC_RULE_NMS ? min1 * p.norm : fmaxf(0.0f, min1 - p.offset);
+#pragma unroll
+                for (int j = 0; j < kMaxDc; ++j) {
+                    if (j < deg) {
+                        const float mag = (fabsf(x[j]) == min1) ? cst1 : cst2;
+                        cm[(size_t)j * Z] = (sign ^ (signbit(x[j]) ? 1 : 0)) ? -mag : mag;
+                    }
+                }
+            }
+        } else {
+            int x[kMaxDc];
+            int min1 = p.vmax, min2 = p.vmax;
+#pragma unroll
+            for (int j = 0; j < kMaxDc; ++j) {
+                if (j < deg) {
+                    x[j] = min(max((int)pv[j] - (int)old[j], -p.vmax), p.vmax);
+                    hard ^= pv[j] < 0;
+                    const int a = abs(x[j]);
+                    sign ^= x[j] < 0;
+                    min2 = min(min2, max(a, min1));
+                    min1 = min(min1, a);
+                }
+            }
+            const int cst1 = p.rule == QLDPC_RULE_OMS ? max(min2 - p.offset_int, 0) : norm8(min2, p.norm_eighths);
+            const int cst2 = p.rule == QLDPC_RULE_OMS ? max(min1 - p.offset_int, 0) : norm8(min1, p.norm_eighths);
+#pragma unroll
+            for (int j = 0; j < kMaxDc; ++j) {
+                if (j < deg) {
+                    const int mag = (abs(x[j]) == min1) ? cst1 : cst2;
+                    cm[(size_t)j * Z] = (MsgT)((sign ^ (x[j] < 0)) ? -mag : mag);
+                }
+            }
+        }
+        return hard;
+    }
+    // any degree: two passes over memory (rows heavier than kMaxDc; rare in the codes this kernel is chosen for)
+    auto v2c = [&](int j, bool count_hard) {
+        const int2 e = edges[ly.edge_begin + j];
+        int vl = l + e.y;
+        if (vl >= Z) vl -= Z;
+        const PostT pvj = post[(size_t)e.x * Z + vl];
+        if (count_hard) hard ^= pvj < (PostT)0;
+        const MsgT o = FIRST ? (MsgT)0 : cm[(size_t)j * Z];
+        if constexpr (kFloat) return (float)pvj - (float)o;
+        else return (float)min(max((int)pvj - (int)o, -p.vmax), p.vmax);   // integers up to 2^24 are exact in a float
+    };
+    if (kFloat && p.rule == QLDPC_RULE_SPA) {
+        float product = 1.0f;
+        for (int j = 0; j < deg; ++j) {
+            const float xv = v2c(j, true);
+            const float tj = tanh_half(fabsf(xv));
+            product *= (tj != 0.0f) ? tj : 1e-12f;
+            sign ^= signbit(xv) ? 1 : 0;
+        }
+        const int hard1 = hard;
+        for (int j = 0; j < deg; ++j) {
+            const float xv = v2c(j, false);
+            const float tj = tanh_half(fabsf(xv));
+            float rr = product / ((tj != 0.0f) ? tj : 1e-12f);
+            rr = (rr < 1.0f) ? rr : 1.0f - 1.1920929e-07f;
+            const float mag = two_atanh(rr);
+            cm[(size_t)j * Z] = (MsgT)((sign ^ (signbit(xv) ? 1 : 0)) ? -mag : mag);
+        }
+        return hard1;
+    }
+    float min1 = kFloat ? 3.402823466e+38f : (float)p.vmax, min2 = min1;
+    for (int j = 0; j < deg; ++j) {
+        const float xv = v2c(j, true);
+        const float a = fabsf(xv);
+        sign ^= signbit(xv) ? 1 : 0;
+        min2 = fminf(min2, fmaxf(a, min1));
+        min1 = fminf(min1, a);
+    }
+    const int hard1 = hard;
+    float cst1, cst2;
+    if constexpr (kFloat) {
+        cst1 = p.rule == QLDPC_RULE_NMS ? min2 * p.norm : fmaxf(0.0f, min2 - p.offset);
+        cst2 = p.rule == QLDPC_RULE_NMS ? min1 * p.norm : fmaxf(0.0f, min1 - p.offset);
+    } else {
+        cst1 = (float)(p.rule == QLDPC_RULE_OMS ? max((int)min2 - p.offset_int, 0) : norm8((int)min2, p.norm_eighths));
+        cst2 = (float)(p.rule == QLDPC_RULE_OMS ? max((int)min1 - p.offset_int, 0) : norm8((int)min1, p.norm_eighths));
+    }
+    for (int j = 0; j < deg; ++j) {
+        const float xv = v2c(j, false);
+        const float mag = (fabsf(xv) == min1) ? cst1 : cst2;
+        const float out = (sign ^ (signbit(xv) ? 1 : 0)) ? -mag : mag;
+        if constexpr (kFloat) cm[(size_t)j * Z] = out;
+        else cm[(size_t)j * Z] = (MsgT)(int)out;
+    }
+    return hard1;
+}
+
+// Shared-memory layout: RowMeta rows[R]; int2 edges[nnz] (block column, shift); int col_ptr[C + 1]; int2 col_edges[nnz] (edge
+// id, shift); int vote[2][8].
+template <typename MsgT, typename PostT, typename InT>
+__global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQcxParams p)
+{
+    extern __shared__ __align__(16) char smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CL = (int)cluster.num_blocks(), q = (int)cluster.block_rank();
+    const int cid = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+    const int tid = threadIdx.x, Z = p.Z, ZL = Z / CL, lane0 = q * ZL;
+    const int R = p.brows, C = p.bcols;
+
+    RowMeta *rows = reinterpret_cast<RowMeta *>(smem);
+    int2 *edges = reinterpret_cast<int2 *>(rows + R);
+    int *col_ptr = reinterpret_cast<int *>(edges + p.nnz);
+    int2 *col_edges = reinterpret_cast<int2 *>(col_ptr + C + 1 + ((C + 1) & 1));   // 8-byte aligned
+    int *vote = reinterpret_cast<int *>(col_edges + p.nnz);
+    for (int r = tid; r < R; r += kThreads) rows[r] = RowMeta{p.layers[r].edge_begin, p.layers[r].degree};
+    for (int e = tid; e < p.nnz; e += kThreads) {
+        edges[e] = make_int2(p.aux[e].col, p.aux[e].shift);
+        col_edges[e] = p.col_edges[e];
+    }
+    for (int c = tid; c <= C; c += kThreads) col_ptr[c] = p.col_ptr[c];
+    if (tid < 16) vote[tid] = 0;
+    cluster.sync();
+
+    MsgT *c2v = reinterpret_cast<MsgT *>(p.c2v) + (size_t)cid * p.nnz * Z;
+    PostT *post = reinterpret_cast<PostT *>(p.post) + (size_t)cid * p.N;
+    unsigned vpar = 0;
+
+    // cluster-wide OR of a per-thread flag: block vote, then every block writes its result into every block's table
+    auto cluster_any = [&](int flag) {
+        const int mine = __syncthreads_or(flag);
+        if (CL == 1) return mine != 0;
+        if (tid < CL) *cluster.map_shared_rank(&vote[vpar * 8 + q], tid) = mine;
+        cluster.sync();
+        int any = 0;
+        for (int k = 0; k < CL; ++k) any |= vote[vpar * 8 + k];
+        vpar ^= 1u;
+        return any != 0;
+    };
+
+    for (int f = cid; f < p.F; f += n_clusters) {
+        const InT *llr = reinterpret_cast<const InT *>(p.llr) + (size_t)f * p.N;
+        const uint32_t *syn = p.syn ? p.syn + (size_t)f * p.syn_words : nullptr;
+        int it = 0, depth = 0;
+        bool ok = false;
+        for (;;) {
+            // ---- variable phase: post[v] = llr[v] + sum of the column's messages in ascending block-row order
+            for (int item = tid; item < C * ZL; item += kThreads) {
+                const int c = item / ZL, m = lane0 + item - c * ZL;
+                const size_t v = (size_t)c * Z + m;
+                PostT sum = (PostT)0;
+                if (it > 0) {
+                    const int k0 = col_ptr[c], k1 = col_ptr[c + 1];
+#pragma unroll 4
+                    for (int k = k0; k < k1; ++k) {
+                        const int2 ce = col_edges[k];            // edge id, shift
+                        int l = m - ce.y;
+                        if (l < 0) l += Z;
+                        sum += (PostT)c2v[(size_t)ce.x * Z + l];
+                    }
+                }
+                post[v] = (PostT)llr[v] + sum;
+            }
+            cluster.sync();
+            const bool last = it >= p.max_iter;
+            if (last) {   // final verdict after the last sweep: syndrome of the hard decisions, no update
+                int bad = 0;
+                for (int item = tid; item < R * ZL; item += kThreads) {
+                    const int r = item / ZL, l = lane0 + item - r * ZL;
+                    const int mi = r * Z + l;
+                    unsigned s = syn ? (syn[mi >> 5] >> (31 - (mi & 31))) & 1u : 0u;
+                    const RowMeta ly = rows[r];
+                    for (int j = 0; j < ly.degree; ++j) {
+                        const int2 e = edges[ly.edge_begin + j];
+                        int vl = l + e.y;
+                        if (vl >= Z) vl -= Z;
+                        s ^= (unsigned)(post[(size_t)e.x * Z + vl] < (PostT)0);
+                    }
+                    bad |= (int)(s & 1u);
+                }
+                ok = !cluster_any(bad);
+                break;
+            }
+            // ---- check phase; the early-termination test (enable_syndrome) of this sweep is computed on the way.
+            // If it passes the decoder stops here: the messages just written are never used, `it` is not advanced.
+            const bool want_check = p.early_stop && it > 0;
+            int bad = 0;
+            for (int item = tid; item < R * ZL; item += kThreads) {
+                const int r = item / ZL, l = lane0 + item - r * ZL;
+                const int mi = r * Z + l;
+                const int synbit = syn ? (int)((syn[mi >> 5] >> (31 - (mi & 31))) & 1u) : 0;
+                bad |= it == 0 ? check_update<MsgT, PostT, true>(p, rows[r], edges, post, c2v, l, Z, synbit)
+                               : check_update<MsgT, PostT, false>(p, rows[r], edges, post, c2v, l, Z, synbit);
+            }
+            if (want_check) {
+                ok = !cluster_any(bad);
+                if (ok) { if (++depth >= p.syndrome_depth) break; }
+                else depth = 0;
+            } else {
+                cluster.sync();
+            }
+            ++it;
+        }
+
+        // ---- outputs: lanes of a warp are consecutive variables, 32-aligned (Z % (32 CL) == 0)
+        uint32_t *ab = p.allbits + (size_t)f * p.cw_words;
+        for (int item = tid; item < C * ZL; item += kThreads) {
+            const int c = item / ZL, m = lane0 + item - c * ZL;
+            const size_t v = (size_t)c * Z + m;
+            const PostT pv = post[v];
+            const unsigned b = __ballot_sync(0xffffffffu, pv < (PostT)0);
+            if ((tid & 31) == 0) ab[v >> 5] = __brev(b);
+            if (p.posterior) {
+                if constexpr (sizeof(PostT) == 4 && sizeof(MsgT) == 4) reinterpret_cast<float *>(p.posterior)[(size_t)f * p.N + v] = (float)pv;
+                else reinterpret_cast<int *>(p.posterior)[(size_t)f * p.N + v] = (int)pv;
+            }
+        }
+        if (q == 0 && tid == 0) {
+            if (p.ok) p.ok[f] = ok ? 1 : 0;
+            if (p.iters) p.iters[f] = (uint16_t)it;
+            if (p.stats) {
+                atomicAdd(&p.stats->frames, 1ull);
+                if (!ok) atomicAdd(&p.stats->failures, 1ull);
+                atomicAdd(&p.stats->iter_sum, (unsigned long long)it);
+                atomicAdd(&p.stats->hist[min(it, QLDPC_ITER_HIST_BINS - 1)], 1ull);
+            }
+        }
+        cluster.sync();   // the scratch is reused by the cluster's next frame
+    }
+}
+
+template <typename MsgT, typename PostT, typename InT>
+int launch_t(const FloodQcxParams &p, int n_clusters, int cl, int smem_bytes, cudaStream_t st)
+{
+    auto kern = flooding_qcx_kernel<MsgT, PostT, InT>;
+    QLDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(n_clusters * cl));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = (size_t)smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cl;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    QLDPC_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+    return QLDPC_OK;
+}
+
+template <typename MsgT, typename PostT, typename InT>
+int max_clusters_t(int cl, int smem_bytes)
+{
+    auto kern = flooding_qcx_kernel<MsgT, PostT, InT>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)cl);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = (size_t)smem_bytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cl;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+}  // namespace
+
+int flooding_qcx_smem_bytes(int brows, int bcols, int nnz)
+{
+    return brows * 8 + nnz * 8 + (bcols + 2) * 4 + nnz * 8 + 16 * 4 + 16;
+}
+
+int flooding_qcx_msg_bytes(int dtype) { return dtype == QLDPC_DTYPE_F32 ? 4 : (dtype == QLDPC_DTYPE_I16 ? 2 : 1); }
+int flooding_qcx_post_bytes(int dtype) { return dtype == QLDPC_DTYPE_I8 ? 2 : 4; }
+
+int flooding_qcx_max_clusters(int dtype, int cl, int smem_bytes)
+{
+    switch (dtype) {
+    case QLDPC_DTYPE_F32: return max_clusters_t<float, float, float>(cl, smem_bytes);
+    case QLDPC_DTYPE_I16: return max_clusters_t<int16_t, int, int16_t>(cl, smem_bytes);
+    default: return max_clusters_t<int8_t, int16_t, int8_t>(cl, smem_bytes);
+    }
+}
+
+int launch_flooding_qcx(const FloodQcxParams &p, int n_clusters, int cl, int smem_bytes, cudaStream_t st)
+{
+    switch (p.dtype) {
+    case QLDPC_DTYPE_F32: return launch_t<float, float, float>(p, n_clusters, cl, smem_bytes, st);
+    case QLDPC_DTYPE_I16: return launch_t<int16_t, int, int16_t>(p, n_clusters, cl, smem_bytes, st);
+    case QLDPC_DTYPE_I8: return launch_t<int8_t, int16_t, int8_t>(p, n_clusters, cl, smem_bytes, st);
+    default: return QLDPC_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace qldpc

@@ -149,6 +149,34 @@ struct FloodQcParams {
 int layered_flood_qc_threads();
 int launch_flooding_qc(const FloodQcParams &p, int grid, int block, int smem_bytes, cudaStream_t st);
 
+// ---- flooding, large quasi-cyclic codes, one frame per thread-block cluster (flooding_qcx.cu) -----------------------
+struct FloodQcxParams {
+    const void *llr;           // F * N values of the decoder's dtype
+    const uint32_t *syn;
+    uint32_t *allbits;
+    uint8_t *ok;
+    uint16_t *iters;
+    void *posterior;           // float (f32) or int32 (i16 / i8)
+    DevStats *stats;
+    const QcEdgeAux *aux;
+    const QcLayer *layers;
+    const int32_t *col_ptr;
+    const int2 *col_edges;
+    void *c2v;                 // n_clusters * nnz * Z messages (float / int16 / int8), L2-resident scratch
+    void *post;                // n_clusters * N posteriors (float / int32 / int16)
+    int F, Z, nnz, N, M, brows, bcols;
+    int cw_words, syn_words;
+    int max_iter, early_stop, syndrome_depth;
+    int rule, dtype;
+    float norm, offset;
+    int offset_int, norm_eighths, vmax;
+};
+int flooding_qcx_smem_bytes(int brows, int bcols, int nnz);
+int flooding_qcx_msg_bytes(int dtype);
+int flooding_qcx_post_bytes(int dtype);
+int flooding_qcx_max_clusters(int dtype, int cl, int smem_bytes);   // co-resident clusters of `cl` blocks on the current device
+int launch_flooding_qcx(const FloodQcxParams &p, int n_clusters, int cl, int smem_bytes, cudaStream_t st);
+
 // ---- bit-level helpers ---------------------------------------------------------------------------
 // syndrome of packed frames: QC codes with Z % 32 == 0 use word-wise rotate + XOR (launch_syndrome_qc), others a CSR gather
 int launch_syndrome_qc(const uint32_t *bits, uint32_t *syn, int F, int brows, int Z, int cw_words, int syn_words,

@@ -37,7 +37,7 @@ def test_n65536_flooding_rate_adapted_vs_oracle(q, O, data_dir, rule, norm, qber
     orr = O.RULE_SPA if rule == "spa" else O.RULE_NMS
     dec = q.Decoder(code, schedule=q.SCHED_FLOODING, rule=qr, dtype=q.DTYPE_F32, max_iter=30, early_stop=True,
                     norm_factor=norm, out_mode=q.OUT_ALL)
-    assert dec.kernel_name == ("flooding_csr" if rule == "spa" else "flooding_qc")
+    assert dec.kernel_name == "flooding_qc_cluster"        # one frame per thread-block cluster, state in L2 (flooding_qcx.cu)
     F = 3
     x, y, syn, punct, short = _frames(q, oc, F, qber, pf, sf, seed=int(qber * 1000) + 1)
     mag = float(np.log((1 - qber) / qber))
@@ -53,4 +53,57 @@ def test_n65536_flooding_rate_adapted_vs_oracle(q, O, data_dir, rule, norm, qber
     np.testing.assert_allclose(post, opost, rtol=1e-3, atol=1e-4)
     if ok.all():   # converged frames reproduce Alice's word, filler bits included
         assert (got == x).all()
+    dec.close()
+
+
+@pytest.mark.parametrize("rule", ["spa", "nms"])
+def test_n65536_more_frames_than_clusters(q, O, data_dir, rule):
+    """more frames than clusters are co-resident (37 clusters of 4 SMs on a B200): every cluster switches frames and reuses
+    its scratch; the first sweep of a frame reads no stale messages; a mix of iteration counts inside the batch"""
+    path = "%s/%s" % (data_dir, CODE)
+    oc = O.Code.from_qc(path)
+    code = q.Code.from_qc_file(path)
+    qr, orr, norm = (q.RULE_SPA, O.RULE_SPA, 1.0) if rule == "spa" else (q.RULE_NMS, O.RULE_NMS, 0.8125)
+    dec = q.Decoder(code, schedule=q.SCHED_FLOODING, rule=qr, dtype=q.DTYPE_F32, max_iter=12, early_stop=True,
+                    norm_factor=norm, out_mode=q.OUT_ALL)
+    F = 90
+    rng = np.random.default_rng(65)
+    x = rng.integers(0, 2, (F, oc.N)).astype(np.uint8)
+    qbers = np.linspace(0.01, 0.075, F)                         # the last frames do not converge in 12 sweeps
+    y = x ^ (rng.random((F, oc.N)) < qbers[:, None])
+    syn_p = dec.syndrome(q.pack_bits(x))
+    llr = np.where(y, -2.9, 2.9).astype(np.float32)
+    out, ok, iters, _ = dec.decode(llr, syn_p)
+    hard, _, oit, ook, _ = oc.batch_flooding_f32(llr, q.unpack_bits(syn_p, oc.M), rule=orr, n_ite=12, early_stop=True, norm=norm)
+    assert (iters == oit).all() and (ok == ook).all() and (q.unpack_bits(out, oc.N) == hard).all()
+    assert ok[:40].all() and not ok.all() and len(set(iters.tolist())) >= 4
+    dec.close()
+
+
+@pytest.mark.parametrize("dtype,rule", [("i8", "nms"), ("i8", "oms"), ("i16", "nms")])
+def test_n65536_fixed_point_flooding_vs_oracle(q, O, data_dir, dtype, rule):
+    """int8 / int16 flooding min-sum on the long block (messages stored in 8 / 16 bits): bits, iteration counts and integer
+    posteriors equal to the oracle's"""
+    path = "%s/%s" % (data_dir, CODE)
+    oc = O.Code.from_qc(path)
+    code = q.Code.from_qc_file(path)
+    dt, mag, vmax = (q.DTYPE_I8, 12, 127) if dtype == "i8" else (q.DTYPE_I16, 200, 32767)
+    qr, orr = (q.RULE_NMS, O.RULE_NMS) if rule == "nms" else (q.RULE_OMS, O.RULE_OMS)
+    dec = q.Decoder(code, schedule=q.SCHED_FLOODING, rule=qr, dtype=dt, max_iter=20, early_stop=True, norm_factor=0.75,
+                    offset=1.0, out_mode=q.OUT_ALL)
+    assert dec.kernel_name == "flooding_qc_cluster"
+    F = 6
+    rng = np.random.default_rng(3)
+    x = rng.integers(0, 2, (F, oc.N)).astype(np.uint8)
+    y = x ^ (rng.random((F, oc.N)) < 0.04)
+    syn_p = dec.syndrome(q.pack_bits(x))
+    syn = q.unpack_bits(syn_p, oc.M)
+    llr = np.where(y, -mag, mag)
+    out, ok, iters, post = dec.decode(llr.astype(dec.np_dtype), syn_p, want_posterior=True)
+    for f in range(F):
+        hard, opost, oit, ook = oc.decode_flooding_fixed(llr[f], syn[f], rule=orr, n_ite=20, early_stop=True, offset=1,
+                                                         norm_eighths=6, vmax=vmax)
+        assert (q.unpack_bits(out[f:f + 1], oc.N)[0] == hard).all() and iters[f] == oit and ok[f] == ook
+        assert (post[f] == opost).all()
+    assert ok.all()
     dec.close()

@@ -414,7 +414,7 @@ def run_ours(args, rank, world, local_rank):
                            "message_scratch_l2_bytes_per_frame": msg_l2_bytes_per_frame,
                            "message_scratch_l2_GBps": msg_l2_bytes_per_frame * F / (launch_ms * 1e-3) / 1e9,
                            "alu_pipe_pct_ncu": NCU_ALU_PIPE_PCT, "issue_active_pct_ncu": NCU_ISSUE_ACTIVE_PCT,
-                           # measured ceilings (tools_onchip_peaks.cu, profiles/r1_onchip_peaks.md)
+                           # measured ceilings (tools/onchip_peaks.cu, profiles/r1_onchip_peaks.md)
                            "smem_peak_GBps_measured": SMEM_PEAK_GBPS, "l2_read_peak_GBps_measured": L2_PEAK_GBPS,
                            "edge_update_frac_of_smem_peak": edge_bytes_per_frame * F / (launch_ms * 1e-3) / 1e9 / SMEM_PEAK_GBPS,
                            "message_scratch_frac_of_l2_peak": msg_l2_bytes_per_frame * F / (launch_ms * 1e-3) / 1e9 / L2_PEAK_GBPS}}

@@ -6,15 +6,19 @@
 //         K, N, n_ite, H, info_bits_pos, tools::Update_rule_SPA<Q>(max_CN_degree),
 //         enable_syndrome, syndrome_depth, n_frames);                             BOOT/src/main.cpp:193
 // and call  decoder->decode_siho(LLRs, dec_bits)  (:365)  and  decoder->reset()  (:389).
-// This class keeps those names, argument meanings (B = one int per bit, Q = float LLRs, n_frames
+// This class keeps those names, argument meanings (B = one int per bit, Q = the LLR type, n_frames
 // frames back to back in one vector) and the error behaviour (exceptions, like tools::invalid_argument /
 // tools::length_error / tools::runtime_error), so the driver loops port by changing one line.
+// Decoder_SISO_SIHO<B,Q> is templated on Q (BOOT/src/main.cpp:113): Q = float selects the fp32 kernels, Q = int8_t /
+// int16_t the fixed-point ones (AFF3CT's Q_8 / Q_16 builds), with Update_rule_NMS's factor restricted to k/8 as in
+// AFF3CT's integer normalize<>.
 //
 // BOOT = errorcorrection/ldpc_examples/my_project_with_aff3ct/examples/bootstrap
 #pragma once
 
 #include <cstdint>
 #include <memory>
+#include <type_traits>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -98,7 +102,13 @@ public:
         qldpc_decoder_config_default(&cfg);
         cfg.schedule = (int)schedule;
         cfg.rule = up_rule.rule;
-        cfg.dtype = QLDPC_DTYPE_F32;   // every decoder the reference instantiates is B=int, Q=float (BOOT/src/main.cpp:113)
+        // every decoder the reference instantiates is B=int, Q=float (BOOT/src/main.cpp:113); the integer Q types reach the
+        // fixed-point kernels (BG1 Z=384 layered int8: the streamed kernel of the headline benchmark)
+        static_assert(std::is_same<Q, float>::value || std::is_same<Q, int8_t>::value || std::is_same<Q, int16_t>::value,
+                      "Q has to be float, int8_t or int16_t");
+        cfg.dtype = std::is_same<Q, float>::value ? QLDPC_DTYPE_F32 : (std::is_same<Q, int8_t>::value ? QLDPC_DTYPE_I8 : QLDPC_DTYPE_I16);
+        if (cfg.dtype != QLDPC_DTYPE_F32 && up_rule.rule == QLDPC_RULE_SPA)
+            throw tools::invalid_argument("Update_rule_SPA needs a floating-point 'Q'");
         cfg.max_iter = n_ite;
         cfg.early_stop = enable_syndrome ? 1 : 0;
         cfg.syndrome_depth = syndrome_depth;
@@ -108,6 +118,8 @@ public:
         cfg.device = device;
         qldpc_decoder *d = nullptr;
         rc = qldpc_decoder_create(H_.get(), &cfg, &d);
+        if (rc == QLDPC_ERR_ARG && cfg.dtype != QLDPC_DTYPE_F32)
+            throw tools::invalid_argument("integer 'Q': 'normalize_factor' has to be k/8 (k = 1..8), 'offset' a non-negative integer");
         if (rc != QLDPC_OK) throw tools::runtime_error(std::string("qldpc_decoder_create: ") + qldpc_strerror(rc));
         dec_.reset(d, &qldpc_decoder_free);
         out_words_ = qldpc_out_words(d);
@@ -122,11 +134,10 @@ public:
     {
         check_sizes(Y_N.size(), (size_t)N_, "Y_N");
         check_sizes(V_K.size(), (size_t)K_, "V_K");
-        std::vector<float> llr(Y_N.begin(), Y_N.end());
         packed_.assign((size_t)n_frames_ * out_words_, 0u);
         ok_.assign((size_t)n_frames_, 0);
         iters_.assign((size_t)n_frames_, 0);
-        const int rc = qldpc_decode(dec_.get(), llr.data(), nullptr, n_frames_, packed_.data(), ok_.data(), iters_.data(), nullptr);
+        const int rc = qldpc_decode(dec_.get(), Y_N.data(), nullptr, n_frames_, packed_.data(), ok_.data(), iters_.data(), nullptr);
         if (rc != QLDPC_OK) throw tools::runtime_error(std::string("decode_siho: ") + qldpc_strerror(rc));
         for (int f = 0; f < n_frames_; ++f)
             for (int i = 0; i < K_; ++i)
@@ -138,13 +149,22 @@ public:
     {
         check_sizes(Y_N1.size(), (size_t)N_, "Y_N1");
         check_sizes(Y_N2.size(), (size_t)N_, "Y_N2");
-        std::vector<float> llr(Y_N1.begin(), Y_N1.end()), post((size_t)n_frames_ * N_);
+        // a-posteriori values come back as float (Q = float) or int32 (integer Q, saturated to Q's range here)
+        typedef typename std::conditional<std::is_same<Q, float>::value, float, int32_t>::type P;
+        std::vector<P> post((size_t)n_frames_ * N_);
         packed_.assign((size_t)n_frames_ * out_words_, 0u);
         ok_.assign((size_t)n_frames_, 0);
         iters_.assign((size_t)n_frames_, 0);
-        const int rc = qldpc_decode(dec_.get(), llr.data(), nullptr, n_frames_, packed_.data(), ok_.data(), iters_.data(), post.data());
+        const int rc = qldpc_decode(dec_.get(), Y_N1.data(), nullptr, n_frames_, packed_.data(), ok_.data(), iters_.data(), post.data());
         if (rc != QLDPC_OK) throw tools::runtime_error(std::string("decode_siso: ") + qldpc_strerror(rc));
-        for (size_t i = 0; i < post.size(); ++i) Y_N2[i] = (Q)post[i];
+        for (size_t i = 0; i < post.size(); ++i) {
+            if (std::is_same<Q, float>::value) Y_N2[i] = (Q)post[i];
+            else {
+                const long lo = std::is_same<Q, int8_t>::value ? -128 : -32768, hi = -lo - 1;
+                const long v = (long)post[i];
+                Y_N2[i] = (Q)(v < lo ? lo : (v > hi ? hi : v));
+            }
+        }
     }
 
     // AFF3CT keeps check-to-variable messages between calls until reset(); this engine starts every call
@@ -169,6 +189,52 @@ private:
     std::vector<uint32_t> packed_;
     std::vector<uint8_t> ok_;
     std::vector<uint16_t> iters_;
+};
+
+// Encoder_LDPC_from_QC<B> ("main.cpp (5g-qc)":177): systematic encoder of a 5G-NR shaped quasi-cyclic code, n_frames
+// frames per call, one B per bit; info_bits_pos = [0, K) (get_info_bits_pos()).
+template <typename B = int>
+class Encoder_LDPC_from_QC {
+public:
+    Encoder_LDPC_from_QC(int K, int N, tools::Sparse_matrix H, int n_frames = 1, int device = 0)
+        : K_(K), N_(N), n_frames_(n_frames), H_(std::move(H))
+    {
+        const qldpc_code_info inf = H_.info();
+        if (N != inf.n || K != inf.n - inf.m) throw tools::invalid_argument("'K' / 'N' do not match H");
+        qldpc_decoder_config cfg;
+        qldpc_decoder_config_default(&cfg);
+        cfg.max_iter = 1;
+        cfg.device = device;
+        qldpc_decoder *d = nullptr;
+        const int rc = qldpc_decoder_create(H_.get(), &cfg, &d);
+        if (rc != QLDPC_OK) throw tools::runtime_error(std::string("qldpc_decoder_create: ") + qldpc_strerror(rc));
+        dec_.reset(d, &qldpc_decoder_free);
+    }
+    std::vector<uint32_t> get_info_bits_pos() const
+    {
+        std::vector<uint32_t> p((size_t)K_);
+        for (int i = 0; i < K_; ++i) p[(size_t)i] = (uint32_t)i;
+        return p;
+    }
+    void encode(const std::vector<B> &U_K, std::vector<B> &X_N)
+    {
+        if (U_K.size() != (size_t)K_ * n_frames_ || X_N.size() != (size_t)N_ * n_frames_)
+            throw tools::length_error("'U_K.size()' / 'X_N.size()' have to be 'K' / 'N' * 'n_frames'");
+        const int kw = (K_ + 31) / 32, cw = qldpc_codeword_words(dec_.get());
+        std::vector<uint32_t> msg((size_t)n_frames_ * kw, 0u), cword((size_t)n_frames_ * cw);
+        for (int f = 0; f < n_frames_; ++f)
+            for (int i = 0; i < K_; ++i)
+                if (U_K[(size_t)f * K_ + i]) msg[(size_t)f * kw + i / 32] |= 1u << (31 - i % 32);
+        const int rc = qldpc_encode_nr(dec_.get(), msg.data(), n_frames_, cword.data());
+        if (rc != QLDPC_OK) throw tools::runtime_error(std::string("Encoder_LDPC_from_QC::encode: ") + qldpc_strerror(rc));
+        for (int f = 0; f < n_frames_; ++f)
+            for (int i = 0; i < N_; ++i) X_N[(size_t)f * N_ + i] = (B)((cword[(size_t)f * cw + i / 32] >> (31 - i % 32)) & 1u);
+    }
+
+private:
+    int K_, N_, n_frames_;
+    tools::Sparse_matrix H_;
+    std::shared_ptr<qldpc_decoder> dec_;
 };
 
 }  // namespace module

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Summarise an .ncu-rep (read on the CPU box): python tools_ncu_summary.py rep.ncu-rep [out.txt] [title]"""
+"""Summarise an .ncu-rep (read on the CPU box): python tools/ncu_summary.py rep.ncu-rep [out.txt] [title]"""
 import csv, subprocess, sys
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout

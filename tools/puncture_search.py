@@ -7,7 +7,7 @@ first `bits_to_puncture` of them (LLR 0; the other parity bits are "sent" and ge
 Here one candidate pattern = ONE decoder call over `--frames` frames (the masks of qldpc_decode_bits are per call), and the
 candidates are tried until one is error free (or all of `--patterns`, with `--all`).
 
-    python tools_puncture_search.py [--code NR_1_1_384.qc] [--qber 0.02] [--puncture 3000] [--frames 2048] [--patterns 16]
+    python tools/puncture_search.py [--code NR_1_1_384.qc] [--qber 0.02] [--puncture 3000] [--frames 2048] [--patterns 16]
 
 `--ref-quirk` reproduces the driver's off-by-one (the confirmed-bit override starts at K+1, so parity
 position K keeps its noisy channel LLR).  Prints one JSON line per pattern and a summary line; runs on the GPU box.
@@ -22,7 +22,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 

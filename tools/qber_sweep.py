@@ -3,7 +3,7 @@
 SPA vs normalised min-sum, rate adaptation by puncturing (p) / shortening (s) a public pseudo-random position set.
 Runs on the GPU box; writes a markdown table (FER, mean iterations, efficiency f = leak / h(QBER), decode Mbit/s of key).
 
-    python tools_qber_sweep.py [--frames 192] [--out gpurun_out/qber_sweep.md]
+    python tools/qber_sweep.py [--frames 192] [--out gpurun_out/qber_sweep.md]
 """
 import argparse
 import importlib
@@ -14,7 +14,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 

@@ -3,9 +3,9 @@
 host-side reduction of the FER / iteration statistics.  STRONG scaling: the stream is fixed, every rank decodes a
 contiguous range of frames (qcrypto-ldpc_b200/sharding.py), no collective on the decode path.
 
-    python tools_stream_10gbit.py                                             # 1 GPU
+    python tools/stream_10gbit.py                                             # 1 GPU
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-        tools_stream_10gbit.py --gpus N [--gbit 10] [--e2e]
+        tools/stream_10gbit.py --gpus N [--gbit 10] [--e2e]
 
 Frames are generated on the device chunk by chunk (not timed); the decode of every chunk is timed with CUDA events on
 the launch stream; --e2e also pushes every chunk through the host-pointer call qldpc_decode_bits (pinned buffers).
@@ -17,7 +17,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench as B  # noqa: E402  (workload constants and the frame synthesiser)
 

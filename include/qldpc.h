@@ -210,6 +210,22 @@ int qldpc_encode_nr(qldpc_decoder *dec, const uint32_t *msg, int32_t n_frames, u
 int qldpc_encode_nr_device(qldpc_decoder *dec, const uint32_t *d_msg, int32_t n_frames, uint32_t *d_cword,
                            void *cuda_stream);
 
+/* ---- encoders for codes without the NR structure (Alice's side of the send-parity formulation) --------------
+ * qldpc_encoder_from_h            module::Encoder_LDPC_from_H<B>(K, N, H, "IDENTITY" | "LU_DEC", ...)   VAR/main.cpp (alist-v1.0.1):144
+ * qldpc_encoder_from_g_alist_file module::Encoder_LDPC<B>(K, N, G, n_frames), G read from the .alist files of BOOT/matrices/G   VAR/main.cpp (alist):143,333
+ * qldpc_encode[_device]           m.encoder->encode(ref_bits, enc_bits)                               VAR/main.cpp (alist):417
+ * from_H: Gauss-Jordan on the host; the code's info_bits_pos stay information positions wherever the rank of H allows it
+ * (always for a full-rank parity part); qldpc_encoder_info_bits_pos returns the positions actually used, k = n - rank(H).
+ * msg: n_frames * ceil(k/32) words, message bit i of a frame = information position pos[i]; cword: n_frames * ceil(n/32). */
+typedef struct qldpc_encoder qldpc_encoder;
+int  qldpc_encoder_from_h(const qldpc_code *code, int32_t device, qldpc_encoder **out);
+int  qldpc_encoder_from_g_alist_file(const char *path, int32_t device, qldpc_encoder **out);
+int  qldpc_encoder_get_info(const qldpc_encoder *enc, int32_t *k, int32_t *n);
+int  qldpc_encoder_info_bits_pos(const qldpc_encoder *enc, int32_t *pos);
+int  qldpc_encode(qldpc_encoder *enc, const uint32_t *msg, int32_t n_frames, uint32_t *cword);
+int  qldpc_encode_device(qldpc_encoder *enc, const uint32_t *d_msg, int32_t n_frames, uint32_t *d_cword, void *cuda_stream);
+void qldpc_encoder_free(qldpc_encoder *enc);
+
 /* ---- statistics (host-side reduction across GPUs is the caller's job) ------------------ */
 #define QLDPC_ITER_HIST_BINS 64
 typedef struct qldpc_stats {

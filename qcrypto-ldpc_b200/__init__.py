@@ -39,6 +39,8 @@ ABI_SYMBOLS = [
     "qldpc_make_llr", "qldpc_make_llr_device", "qldpc_decode_bits", "qldpc_decode_bits_device", "qldpc_encode_nr", "qldpc_encode_nr_device",
     "qldpc_get_stats", "qldpc_reset_stats", "qldpc_decoder_kernel_name", "qldpc_strerror",
     "qldpc_last_cuda_error", "qldpc_version", "qldpc_privacy_amplify", "qldpc_crc32_frames",
+    "qldpc_encoder_from_h", "qldpc_encoder_from_g_alist_file", "qldpc_encoder_get_info", "qldpc_encoder_info_bits_pos",
+    "qldpc_encode", "qldpc_encode_device", "qldpc_encoder_free",
 ]
 
 
@@ -113,6 +115,14 @@ def lib():
         L.qldpc_strerror.restype = C.c_char_p
         L.qldpc_last_cuda_error.restype = C.c_char_p
         L.qldpc_version.restype = C.c_int
+        L.qldpc_encoder_from_h.argtypes = [vp, i32, pp]
+        L.qldpc_encoder_from_g_alist_file.argtypes = [C.c_char_p, i32, pp]
+        L.qldpc_encoder_get_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+        L.qldpc_encoder_info_bits_pos.argtypes = [vp, vp]
+        L.qldpc_encode.argtypes = [vp, vp, i32, vp]
+        L.qldpc_encode_device.argtypes = [vp, vp, i32, vp, vp]
+        L.qldpc_encoder_free.argtypes = [vp]
+        L.qldpc_encoder_free.restype = None
         L.qldpc_privacy_amplify.argtypes = [i32, vp, i32, vp, vp, vp, i32, vp, i32]
         L.qldpc_crc32_frames.argtypes = [i32, vp, i32, i32, i32, vp]
         _lib = L
@@ -302,6 +312,49 @@ class Decoder:
 
     def reset_stats(self):
         _chk(lib().qldpc_reset_stats(self.h), "qldpc_reset_stats")
+
+
+class Encoder:
+    """Systematic encoder of a code without the NR structure: Encoder.from_H(code) (Encoder_LDPC_from_H) or
+    Encoder.from_G_alist(path) (Encoder_LDPC with a generator-matrix file)."""
+
+    def __init__(self, handle):
+        self.h = handle
+        k, n = C.c_int32(), C.c_int32()
+        _chk(lib().qldpc_encoder_get_info(self.h, C.byref(k), C.byref(n)), "qldpc_encoder_get_info")
+        self.k, self.n = k.value, n.value
+        pos = np.zeros(self.k, dtype=np.int32)
+        self.info_bits_pos = pos if lib().qldpc_encoder_info_bits_pos(self.h, _np_ptr(pos)) == 0 else None
+
+    @classmethod
+    def from_H(cls, code, device=0):
+        h = C.c_void_p()
+        _chk(lib().qldpc_encoder_from_h(code.h, device, C.byref(h)), "qldpc_encoder_from_h")
+        return cls(h)
+
+    @classmethod
+    def from_G_alist(cls, path, device=0):
+        h = C.c_void_p()
+        _chk(lib().qldpc_encoder_from_g_alist_file(str(path).encode(), device, C.byref(h)), "qldpc_encoder_from_g_alist_file")
+        return cls(h)
+
+    def encode(self, msg_packed):
+        msg = np.ascontiguousarray(msg_packed, dtype=np.uint32)
+        F = msg.shape[0]
+        cw = np.zeros((F, (self.n + 31) // 32), dtype=np.uint32)
+        _chk(lib().qldpc_encode(self.h, _np_ptr(msg), F, _np_ptr(cw)), "qldpc_encode")
+        return cw
+
+    def close(self):
+        if self.h:
+            lib().qldpc_encoder_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def pack_bits(bits):

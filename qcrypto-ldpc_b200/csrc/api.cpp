@@ -24,7 +24,7 @@ int CudaCheck::fail(cudaError_t e, const char *what)
 
 namespace {
 
-enum { KF_NONE = 0, KF_LAYERED_I8 = 1, KF_LAYERED_GENERIC = 2, KF_FLOODING = 3, KF_LAYERED_I8S = 4 };
+enum { KF_NONE = 0, KF_LAYERED_I8 = 1, KF_LAYERED_GENERIC = 2, KF_FLOODING = 3, KF_LAYERED_I8S = 4, KF_LAYERED_CSR = 5 };
 
 int dtype_size(int dtype) { return dtype == QLDPC_DTYPE_F32 ? 4 : (dtype == QLDPC_DTYPE_I16 ? 2 : 1); }
 
@@ -514,7 +514,10 @@ extern "C" int qldpc_decoder_create(const qldpc_code *code, const qldpc_decoder_
     if (cfg->out_mode != QLDPC_OUT_INFO && cfg->out_mode != QLDPC_OUT_ALL) return QLDPC_ERR_ARG;
     const bool is_int = cfg->dtype != QLDPC_DTYPE_F32;
     if (is_int && cfg->rule == QLDPC_RULE_SPA) return QLDPC_ERR_UNSUPPORTED;   // SPA is float only (as in AFF3CT)
-    if (cfg->schedule == QLDPC_SCHED_LAYERED && code->h.z <= 0) return QLDPC_ERR_UNSUPPORTED;
+    // layered decoding of a non-quasi-cyclic H: float only (the integer layered arithmetic is defined on circulants,
+    // ML/BPSK_nrldpc_sim_FP.m), check degree bounded by the kernel's per-thread store
+    if (cfg->schedule == QLDPC_SCHED_LAYERED && code->h.z <= 0 &&
+        (is_int || code->h.max_chk_degree > layered_csr_max_degree())) return QLDPC_ERR_UNSUPPORTED;
     if (cfg->n_devices < 0 || cfg->n_devices > QLDPC_MAX_DEVICES) return QLDPC_ERR_ARG;
 
     int ndev = 0;
@@ -604,7 +607,16 @@ extern "C" int qldpc_decoder_create(const qldpc_code *code, const qldpc_decoder_
     if ((rc = d->d_stats.ensure(1))) return bail(rc);
     if (cudaMemset(d->d_stats.p, 0, sizeof(DevStats)) != cudaSuccess) return bail(QLDPC_ERR_CUDA);
 
-    if (cfg->schedule == QLDPC_SCHED_LAYERED) {
+    if (cfg->schedule == QLDPC_SCHED_LAYERED && c.z <= 0) {
+        // one thread per frame, frame-minor state (layered_csr.cu); the thread count bounds the scratch to 512 MB
+        d->kernel_family = KF_LAYERED_CSR;
+        d->kernel_name = "layered_csr";
+        const size_t per_thread = (size_t)(c.n + c.edges) * 4;
+        const size_t cap = std::max<size_t>(128, ((512u << 20) / per_thread) / 128 * 128);
+        d->gen_grid = (int)std::min<size_t>(cap, (size_t)d->sm_count * 8 * 128);
+        d->scratch_msg_bytes = (size_t)d->gen_grid * c.edges * 4;
+        d->scratch_app_bytes = (size_t)d->gen_grid * c.n * 4;
+    } else if (cfg->schedule == QLDPC_SCHED_LAYERED) {
         LayeredI8Params p{};
         const bool i8_ok = cfg->dtype == QLDPC_DTYPE_I8 && d->cfg.app_max == 127 && d->cfg.msg_max <= 63;
         const bool fast_s = i8_ok && plan_layered_i8s(d);
@@ -882,7 +894,19 @@ static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint3
         if ((rc = d->d_allbits.ensure((size_t)n_frames * d->cw_words))) return rc;
         allbits = d->d_allbits.p;
     }
-    if (family == KF_LAYERED_GENERIC) {
+    if (family == KF_LAYERED_CSR) {
+        LayeredCsrParams p{};
+        p.llr = (const float *)d_llr; p.syn = d_syndrome; p.allbits = allbits; p.ok = d_ok; p.iters = d_iters;
+        p.posterior = (float *)d_posterior; p.stats = d->d_stats.p;
+        p.row_ptr = d->d_row_ptr.p; p.col_idx = d->d_col_idx.p;
+        p.branch = (float *)d->d_scratch.p; p.var = (float *)d->d_scratch2.p;
+        p.F = n_frames; p.N = c.n; p.M = c.m; p.E = c.edges; p.cw_words = d->cw_words; p.syn_words = d->syn_words;
+        p.max_iter = cfg.max_iter; p.early_stop = cfg.early_stop; p.syndrome_depth = cfg.syndrome_depth;
+        p.rule = cfg.rule; p.norm = cfg.norm_factor; p.offset = cfg.offset;
+        const int threads = std::min(d->gen_grid, (n_frames + 127) / 128 * 128);
+        // the state is indexed with the launch's thread count as stride: every launch lays it out afresh
+        if ((rc = launch_layered_csr(p, threads, st))) return rc;
+    } else if (family == KF_LAYERED_GENERIC) {
         LayeredGenParams p{};
         p.llr = d_llr; p.syn = d_syndrome; p.allbits = allbits; p.ok = d_ok; p.iters = d_iters;
         p.posterior = d_posterior; p.stats = d->d_stats.p;

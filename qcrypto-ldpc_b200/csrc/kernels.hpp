@@ -101,6 +101,26 @@ struct LayeredGenParams {
 };
 int launch_layered_generic(const LayeredGenParams &p, int grid, cudaStream_t st);
 
+// ---- layered, any H (CSR), float: one thread per frame (layered_csr.cu) ------------------------------------------
+struct LayeredCsrParams {
+    const float *llr;
+    const uint32_t *syn;
+    uint32_t *allbits;
+    uint8_t *ok;
+    uint16_t *iters;
+    float *posterior;
+    DevStats *stats;
+    const int32_t *row_ptr, *col_idx;
+    float *var, *branch;       // frame-minor state: N x threads and E x threads floats
+    int F, N, M, E;
+    int cw_words, syn_words;
+    int max_iter, early_stop, syndrome_depth;
+    int rule;
+    float norm, offset;
+};
+int layered_csr_max_degree();
+int launch_layered_csr(const LayeredCsrParams &p, int threads, cudaStream_t st);   // threads: multiple of 128
+
 // ---- flooding (any H; f32 / i16 / i8) -----------------------------------------------------------
 struct FloodParams {
     const void *llr;

@@ -18,9 +18,11 @@
 using namespace qldpc;
 
 #define CONFIRMED_BIT_LLR (-std::log(1e-10 / (1 - 1e-10)))                       // (5g-qc):33
-static double h(double q) { return -q * std::log2(q) - (1 - q) * std::log2(1 - q); }          // :36
-static double f_eff(double ratio, double q) { return (1 - ratio) / h(q); }                   // :38
-static double k_using_f(double eff, double q, double fer) { return (1 - (1 + eff) * h(q)) * (1 - fer); }   // :40
+// the reference's macros evaluate in float (ber is a float, std::log2(float) is float): the recorded puncture counts
+// (92 at ber = 1e-10, where 1 - ber == 1.0f) are only reproduced in float
+static float h(float q) { return (-q) * std::log2(q) - (1 - q) * std::log2(1 - q); }                    // :36
+static float f_eff(float ratio, float q) { return (1 - ratio) / h(q); }                                // :38
+static float k_using_f(float eff, float q, float fer) { return (1 - (1 + eff) * h(q)) * (1 - fer); }   // :40
 
 template <typename Q>
 static int run(const std::string &path, int expansion_factor, float desired_eff, int frames, const tools::Update_rule &rule,
@@ -43,7 +45,7 @@ static int run(const std::string &path, int expansion_factor, float desired_eff,
         bits_to_puncture = (bits_to_puncture / expansion_factor) * expansion_factor;   // :461
         const float R = (float)K / (float)(N - bits_to_puncture);
         const float ratio = 1 - (float)(N - K - bits_to_puncture) / (float)K;      // :464, R(PAR_BITS, INFO_BITS)
-        const float efficiency = (float)f_eff(ratio, ber), key_rate = (float)k_using_f(efficiency, ber, 0.0);
+        const float efficiency = f_eff(ratio, ber), key_rate = k_using_f(efficiency, ber, 0.0f);
         std::printf("\nPunct. Bits (Round down): %d| Reconcil. Effic.: %g| Key Rate (at 0%% FER): %g| Final key len: %g| Code rate: %g\n",
                     bits_to_puncture, efficiency, key_rate, (float)K * key_rate, R);   // :478-483
         std::bernoulli_distribution bit(0.5), flip(ber);

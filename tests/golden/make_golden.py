@@ -52,6 +52,8 @@ def matrices():
     for n in ("PEGReg504x1008.alist", "20.alist", "1998.5.3.2665.alist", "NR_1_0_2.qc", "NR_1_1_192.qc",
               "NR_2_3_112.qc", "NR_1_7_30.qc", "test.qc", "test2.qc"):
         shutil.copyfile(BOOT + "/matrices/H/" + n, os.path.join(DATA, n))
+    # the generator matrix the reference's KAT-E was made with ("main.cpp (alist)":333,443-455)
+    shutil.copyfile(BOOT + "/matrices/G/PEGReg504x1008.alist", os.path.join(DATA, "G_PEGReg504x1008.alist"))
     facts = {}
     for name, Z in (("NR_1_1_384", 384), ("NR_1_1_24", 24), ("NR_2_6_52", 52), ("NR_1_7_240", 240), ("NR_1_0_256", 256)):
         rows = nr_txt_to_qc(name, Z)

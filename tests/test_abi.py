@@ -115,7 +115,7 @@ def test_error_codes(q, data_dir, tmp_path):
     assert L.qldpc_decoder_create(code.h, C.byref(cfg), C.byref(d)) == 6                  # QLDPC_ERR_UNSUPPORTED
     al = q.Code.from_alist("%s/20.alist" % data_dir)
     cfg.rule, cfg.schedule = q.RULE_NMS, q.SCHED_LAYERED
-    assert L.qldpc_decoder_create(al.h, C.byref(cfg), C.byref(d)) == 6                    # layered needs a QC code
+    assert L.qldpc_decoder_create(al.h, C.byref(cfg), C.byref(d)) == 6                    # integer layered decoding needs a QC code (float runs on layered_csr)
 
 
 def test_no_cpu_fallback(q, data_dir):

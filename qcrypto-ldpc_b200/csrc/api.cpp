@@ -670,7 +670,7 @@ extern "C" int qldpc_decoder_create(const qldpc_code *code, const qldpc_decoder_
         // Large quasi-cyclic codes (messages do not fit in shared memory, whole warps per circulant): one frame per cluster
         // of CL thread blocks, CL chosen so that the state of all frames in flight stays inside L2.
         if (c.z > 0 && c.z % 32 == 0 && !d->flood_use_smem) {
-            const int smem = flooding_qcx_smem_bytes(c.base_rows, c.base_cols, c.edges / c.z);
+            const int smem = flooding_qcx_smem_bytes(c.base_rows, c.base_cols, c.edges / c.z, cfg->dtype);
             const size_t state = (size_t)c.edges * flooding_qcx_msg_bytes(cfg->dtype) + (size_t)c.n * flooding_qcx_post_bytes(cfg->dtype);
             const size_t l2_budget = (size_t)prop.l2CacheSize / 2;
             for (int cl = 1; cl <= 8 && c.z % (32 * cl) == 0; cl *= 2) {
@@ -941,6 +941,8 @@ static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint3
             xp.max_iter = cfg.max_iter; xp.early_stop = cfg.early_stop; xp.syndrome_depth = cfg.syndrome_depth;
             xp.rule = cfg.rule; xp.dtype = cfg.dtype; xp.norm = cfg.norm_factor; xp.offset = cfg.offset;
             xp.offset_int = d->offset_int; xp.norm_eighths = d->norm_eighths; xp.vmax = p.vmax;
+            xp.ring_off = flooding_qcx_table_bytes(c.base_rows, c.base_cols, c.edges / c.z);
+            xp.fast_spa = (cfg.flags & QLDPC_FLAG_FAST_SPA) ? 1 : 0;
             if ((rc = launch_flooding_qcx(xp, std::min(d->qcx_clusters, n_frames), d->qcx_cl, d->qcx_smem, st))) return rc;
         } else if (d->flood_qc) {
             FloodQcParams qp{};

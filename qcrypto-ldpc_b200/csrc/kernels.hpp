@@ -190,8 +190,11 @@ struct FloodQcxParams {
     int rule, dtype;
     float norm, offset;
     int offset_int, norm_eighths, vmax;
+    int ring_off;              // float tiers: byte offset of the cp.async ring in dynamic shared memory (= table bytes)
+    int fast_spa;              // SPA transcendentals in fp32 on the SFUs instead of double (QLDPC_FLAG_FAST_SPA)
 };
-int flooding_qcx_smem_bytes(int brows, int bcols, int nnz);
+int flooding_qcx_table_bytes(int brows, int bcols, int nnz);
+int flooding_qcx_smem_bytes(int brows, int bcols, int nnz, int dtype);
 int flooding_qcx_msg_bytes(int dtype);
 int flooding_qcx_post_bytes(int dtype);
 int flooding_qcx_max_clusters(int dtype, int cl, int smem_bytes);   // co-resident clusters of `cl` blocks on the current device

@@ -54,6 +54,17 @@ def test_n65536_flooding_rate_adapted_vs_oracle(q, O, data_dir, rule, norm, qber
     if ok.all():   # converged frames reproduce Alice's word, filler bits included
         assert (got == x).all()
     dec.close()
+    if rule == "spa":
+        # QLDPC_FLAG_FAST_SPA: fp32 transcendentals.  Same bits, flags and iteration counts; posteriors within 1e-3 except for
+        # saturated messages, where one last-bit difference in 1 - r moves 2 atanh(r) by ln 2 / ln 3/2 / ...
+        fast = q.Decoder(code, schedule=q.SCHED_FLOODING, rule=qr, dtype=q.DTYPE_F32, max_iter=30, early_stop=True,
+                         out_mode=q.OUT_ALL, flags=q.FLAG_FAST_SPA)
+        out2, ok2, iters2, post2 = fast.decode(llr, q.pack_bits(syn), want_posterior=True)
+        assert (out2 == out).all() and (ok2 == ok).all() and (iters2 == iters).all()
+        dev = np.abs(post2 - opost)
+        outside = dev > 1e-3 * np.abs(opost) + 1e-4
+        assert outside.mean() < 1e-3 and dev.max() < 1.5 and (np.abs(opost[outside]) > 20).all()
+        fast.close()
 
 
 @pytest.mark.parametrize("rule", ["spa", "nms"])

@@ -52,11 +52,14 @@ def main():
     st = torch.cuda.current_stream().cuda_stream
     mag = math.log((1 - qber) / qber)
     results = []
-    cases = (("SPA f32", q.RULE_SPA, q.DTYPE_F32, 1.0, mag, torch.float32, 16), ("NMS 13/16 f32", q.RULE_NMS, q.DTYPE_F32, 0.8125, mag, torch.float32, 16),
-             ("NMS 6/8 i16", q.RULE_NMS, q.DTYPE_I16, 0.75, round(mag * 64), torch.int16, 8), ("NMS 6/8 i8", q.RULE_NMS, q.DTYPE_I8, 0.75, round(mag * 4), torch.int8, 4))
-    for name, rule, dt, norm, m, tdt, bytes_per_edge in cases:
+    cases = (("SPA f32", q.RULE_SPA, q.DTYPE_F32, 1.0, mag, torch.float32, 16, 0),
+             ("SPA f32 fast (QLDPC_FLAG_FAST_SPA)", q.RULE_SPA, q.DTYPE_F32, 1.0, mag, torch.float32, 16, q.FLAG_FAST_SPA),
+             ("NMS 13/16 f32", q.RULE_NMS, q.DTYPE_F32, 0.8125, mag, torch.float32, 16, 0),
+             ("NMS 6/8 i16", q.RULE_NMS, q.DTYPE_I16, 0.75, round(mag * 64), torch.int16, 8, 0),
+             ("NMS 6/8 i8", q.RULE_NMS, q.DTYPE_I8, 0.75, round(mag * 4), torch.int8, 4, 0))
+    for name, rule, dt, norm, m, tdt, bytes_per_edge, flags in cases:
         dec = q.Decoder(code, schedule=q.SCHED_FLOODING, rule=rule, dtype=dt, max_iter=args.max_iter, early_stop=True,
-                        norm_factor=norm, out_mode=q.OUT_ALL)
+                        norm_factor=norm, out_mode=q.OUT_ALL, flags=flags)
         syn = torch.empty((F, dec.syn_words), dtype=torch.int32, device=dev)
         dec.syndrome_device(xb.data_ptr(), F, syn.data_ptr(), st)
         llr = torch.empty((F, N), dtype=tdt, device=dev)

@@ -14,7 +14,10 @@ scaling), no collective on the decode path; only the FER / iteration statistics 
 
 `value`  = device-resident throughput (CUDA events around K launches of the decode kernel, max over ranks)
 `e2e`    = the same batch through the host-buffer C-ABI call qldpc_decode_bits(): pinned packed key bits in,
-           packed bits / ok / iteration counts out, copies inside the timed region.
+           packed bits / ok / iteration counts out, every byte crossing PCIe inside the timed region (the decoder kernel
+           reads the pinned bits and writes its results in place: zero copy, one launch per call).
+`fixed10` = the same batch with early termination OFF (10 full iterations per frame, north_star "with 10 iterations").
+`roofline` names the BINDING resource of the decode kernel (max of the HBM and the shared-memory term).
 """
 import argparse
 import importlib
@@ -35,14 +38,26 @@ QBER = 0.03
 LLR_NOISY, LLR_KNOWN = 14.0, 31.0      # ln((1-q)/q)=3.476 at scale 2^2 -> 14; known parity saturates the 6-bit range
 MAX_ITER = 10
 NORM = 0.75
-# figures of the committed ncu capture of the decode kernel (profiles/r1_v7_layered_i8s_ncu_summary.txt)
 MSG_SCRATCH_BYTES_PER_FRAME = 81 * 96 * 16          # 81 16-byte message blocks per thread, 96 threads (BG1 Z=384)
-NCU_DRAM_BYTES_PER_FRAME = 186.2e3                   # dram__bytes_read + write per frame (message scratch share held in L2: ~half)
-NCU_TRAFFIC_SOURCE = "profiles/r1_v7_layered_i8s_ncu_summary.txt (ncu --set full, 14800 frames, scaled per frame)"
-NCU_ALU_PIPE_PCT = 55.7
-SMEM_PEAK_GBPS = 37060.0                              # shared-memory loads, all SMs (profiles/r1_onchip_peaks.json)
-L2_PEAK_GBPS = 17600.0                                # L2 reads over a 64 MB buffer (same file)
-NCU_ISSUE_ACTIVE_PCT = 65.0
+# Nothing from a profiler is pasted here: the counters of the latest committed ncu capture of the decode kernel are read
+# from profiles/ncu_latest.json (written by tools/ncu_summary.py next to the human-readable summary; it names the capture
+# and the commit it was taken at), the measured on-chip ceilings from profiles/r1_onchip_peaks.json.
+
+
+def ncu_latest():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_latest.json")))
+    except Exception:
+        return None
+
+
+def onchip_peaks():
+    """measured shared-memory / L2 ceilings of the B200 (tools/onchip_peaks.cu), GB/s"""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r1_onchip_peaks.json")))
+        return float(d["smem_read_GBps"]["b128"]), float(d["l2_read_GBps"]), "measured (profiles/r1_onchip_peaks.json)"
+    except Exception:
+        return 37060.0, 17600.0, "profiles/r1_onchip_peaks.md (file unreadable)"
 
 
 def parse_args():
@@ -56,6 +71,7 @@ def parse_args():
     ap.add_argument("--rule", default="nms", choices=["nms", "oms"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fixed10", action="store_true", help="skip the extra fixed-10-iterations measurement")
     ap.add_argument("--no-fused-bits", action="store_true", help="qldpc_decode_bits as two kernels (LLR synthesis + decode)")
     ap.add_argument("--no-l2-persist", action="store_true", help="do not set QLDPC_FLAG_L2_PERSIST")
     ap.add_argument("--no-zero-copy", action="store_true", help="qldpc_decode_bits stages pinned buffers through device copies")
@@ -203,6 +219,37 @@ def synth_frames_cpu(n, seed=1234):
     return llr, oc
 
 
+def kernel_roofline(F, N, out_words, edges, mean_iters, launch_ms, hbm_peak, hbm_src, smem_peak, l2_peak, onchip_src, ncu):
+    """SURVEY.md 8d for the on-chip layered decoder: achieved = max(B_hbm * fps / BW_hbm, B_smem * fps / BW_smem), both terms
+    reported; the larger fraction names the bound.  Algorithmic bytes per frame: HBM = int8 LLRs in + packed information
+    bits, ok flag and iteration count out; shared memory = 4 bytes per edge-lane per iteration (read L, read R, write L,
+    write R).  `traffic` = DRAM bytes per launch from the latest committed ncu capture of this kernel (profiles/ncu_latest.json)."""
+    sec = launch_ms * 1e-3
+    hbm_bytes = N + out_words * 4 + 1 + 2
+    smem_bytes = mean_iters * edges * 4
+    l2_msg_bytes = (2 * mean_iters - 1) * MSG_SCRATCH_BYTES_PER_FRAME   # messages: written every iteration, read from the 2nd on
+    hbm_gbps, smem_gbps, l2_gbps = hbm_bytes * F / sec / 1e9, smem_bytes * F / sec / 1e9, l2_msg_bytes * F / sec / 1e9
+    terms = {"hbm": {"bytes_per_frame": hbm_bytes, "achieved": hbm_gbps, "peak": hbm_peak, "frac": hbm_gbps / hbm_peak, "peak_source": hbm_src},
+             "smem": {"bytes_per_frame": smem_bytes, "achieved": smem_gbps, "peak": smem_peak, "frac": smem_gbps / smem_peak,
+                      "peak_source": onchip_src},
+             "l2_message_scratch": {"bytes_per_frame": l2_msg_bytes, "achieved": l2_gbps, "peak": l2_peak, "frac": l2_gbps / l2_peak,
+                                    "peak_source": onchip_src}}
+    bound = "smem" if terms["smem"]["frac"] >= terms["hbm"]["frac"] else "hbm"
+    r = {"bound": bound, "kernel": "layered_i8s_kernel", "achieved": terms[bound]["achieved"], "peak": terms[bound]["peak"], "unit": "GB/s",
+         "frac": terms[bound]["frac"], "peak_source": terms[bound]["peak_source"], "bytes_per_frame": terms[bound]["bytes_per_frame"],
+         "launch_ms": launch_ms, "edge_updates_per_s": mean_iters * edges * F / sec, "terms": terms,
+         "note": "the decode state is on chip (beliefs in shared memory, messages in an L2-resident scratch); the kernel is limited by "
+                 "instruction issue on the ALU / fp16-FMA pipes well before either byte ceiling (DESIGN.md 4.1, profiles/)"}
+    if ncu and ncu.get("dram_bytes_per_frame"):
+        r["traffic"] = ncu["dram_bytes_per_frame"] * F
+        r["traffic_per_frame"] = ncu["dram_bytes_per_frame"]
+        r["traffic_source"] = "%s (kernel %s, read at commit %s)" % (ncu.get("summary"), ncu.get("kernel"), ncu.get("read_at_commit"))
+        r["ncu"] = {k: ncu.get(k) for k in ("issue_active_pct", "warps_active_pct", "alu_pipe_pct", "fma_fp16_pipe_pct", "registers_per_thread")}
+    else:
+        r["traffic"] = None
+    return r
+
+
 def workload_config(args, world):
     return {"workload": "5G-NR BG1 Z=384 (N=26112,K=8448) int8 layered normalised min-sum 6/8, max %d iters, %s, BSC QBER 3%%, "
                         "send-parity formulation (info LLR +-14, parity +-31), %d frames per GPU per step" %
@@ -340,6 +387,41 @@ def run_ours(args, rank, world, local_rank):
     stats = dec.stats()
     launches = stats["kernel_launches"]
 
+    # ---- the same batch without early termination (north_star: "with 10 iterations"): one more decoder, 2 timed launches
+    fixed10 = None
+    if not args.fixed_iters and not args.no_fixed10:
+        decf = q.Decoder(code, schedule=q.SCHED_LAYERED, rule=rule, dtype=q.DTYPE_I8, max_iter=MAX_ITER, early_stop=False,
+                         norm_factor=NORM, offset=2.0, out_mode=q.OUT_INFO, device=local_rank,
+                         flags=0 if args.no_l2_persist else q.FLAG_L2_PERSIST)
+        for _ in range(2):
+            decf.decode_device(llr.data_ptr(), 0, F, out.data_ptr(), ok.data_ptr(), iters.data_ptr(), 0, st)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(2):
+            decf.decode_device(llr.data_ptr(), 0, F, out.data_ptr(), ok.data_ptr(), iters.data_ptr(), 0, st)
+        e1.record()
+        torch.cuda.synchronize()
+        assert bool((out[:, :kw] == msg).all()) and bool(ok.all()) and bool((iters == MAX_ITER).all())
+        fixed10 = {"ms": e0.elapsed_time(e1) / 2}
+        decf.close()
+    # ---- device-resident BIT input (qldpc_decode_bits_device): the kernel synthesises its LLRs from 3 264 B of key bits per frame
+    bit_in = None
+    if not args.no_e2e:
+        for _ in range(2):
+            q._chk(q.lib().qldpc_decode_bits_device(dec.h, noisy.data_ptr(), known.data_ptr(), None, LLR_NOISY, LLR_KNOWN, None, F,
+                                                    out.data_ptr(), ok.data_ptr(), iters.data_ptr(), st), "qldpc_decode_bits_device")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            q._chk(q.lib().qldpc_decode_bits_device(dec.h, noisy.data_ptr(), known.data_ptr(), None, LLR_NOISY, LLR_KNOWN, None, F,
+                                                    out.data_ptr(), ok.data_ptr(), iters.data_ptr(), st), "qldpc_decode_bits_device")
+        e1.record()
+        torch.cuda.synchronize()
+        assert bool((out[:, :kw] == msg).all()) and bool(ok.all())
+        bit_in = {"ms": e0.elapsed_time(e1) / 3}
+
     # ---- end to end through the host-buffer C ABI (pinned host buffers, copies inside the timed region)
     # headline e2e: qldpc_decode_bits -- what an ecd2 LDPC handler calls: packed sifted-key bits in
     # (pb->mainBufPtr layout), packed corrected bits / ok / iteration counts out.  Secondary: the LLR-facing
@@ -383,41 +465,22 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- reductions over ranks: time = max, statistics = sum (host side, CPU tensors over gloo)
     sh = importlib.import_module("qcrypto-ldpc_b200.sharding")
-    red, tmax = sh.reduce_stats(stats, [total_ms, e2e["s"] * 1e3 if e2e else 0.0, e2e["s_llr"] * 1e3 if e2e else 0.0],
+    red, tmax = sh.reduce_stats(stats, [total_ms, e2e["s"] * 1e3 if e2e else 0.0, e2e["s_llr"] * 1e3 if e2e else 0.0,
+                                        fixed10["ms"] if fixed10 else 0.0, bit_in["ms"] if bit_in else 0.0],
                                 dist if world > 1 else None)
     if rank != 0:
         return
-    total_ms, e2e_ms, e2e_llr_ms = tmax
+    total_ms, e2e_ms, e2e_llr_ms, fixed10_ms, bit_in_ms = tmax
     frames_total = F * world * args.steps
     value = frames_total * K / (total_ms * 1e-3) / 1e6
     mean_iters, fer = red["mean_iters"], red["fer"]
     assert red["frames"] == frames_total, (red["frames"], frames_total)
 
     peak, peak_src = measured_peak_hbm()
-    # HBM algorithmic bytes per frame: int8 LLRs in; packed info bits, ok, iteration count out.
-    # The check-to-variable messages are streamed through a scratch that is meant to live in L2; the part of it that
-    # L2 does not hold shows up as extra DRAM traffic (`traffic`, from the committed ncu capture, per launch).
-    bytes_per_frame = N + dec.out_words * 4 + 1 + 2
+    smem_peak, l2_peak, onchip_src = onchip_peaks()
+    ncu = ncu_latest()
     launch_ms = float(np.mean(per_launch_ms))
-    achieved = bytes_per_frame * F / (launch_ms * 1e-3) / 1e9
-    edge_bytes_per_frame = mean_iters * code.edges * 4        # read L, read R, write L, write R: one byte each per edge-lane
-    msg_l2_bytes_per_frame = (2 * mean_iters - 1) * MSG_SCRATCH_BYTES_PER_FRAME   # written every iteration, read from the 2nd on
-    roofline = {"bound": "hbm", "kernel": "layered_i8s_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": NCU_DRAM_BYTES_PER_FRAME * F, "traffic_source": NCU_TRAFFIC_SOURCE,
-                "bytes_per_frame": bytes_per_frame, "launch_ms": launch_ms,
-                "note": "the decode state is on chip (beliefs in shared memory, messages in an L2-resident scratch): the kernel "
-                        "is bound by instruction issue / the ALU pipe, not by HBM (DESIGN.md 4.1, profiles/)",
-                "onchip": {"edge_update_bytes_per_frame": edge_bytes_per_frame,
-                           "edge_update_GBps": edge_bytes_per_frame * F / (launch_ms * 1e-3) / 1e9,
-                           "edge_updates_per_s": mean_iters * code.edges * F / (launch_ms * 1e-3),
-                           "message_scratch_l2_bytes_per_frame": msg_l2_bytes_per_frame,
-                           "message_scratch_l2_GBps": msg_l2_bytes_per_frame * F / (launch_ms * 1e-3) / 1e9,
-                           "alu_pipe_pct_ncu": NCU_ALU_PIPE_PCT, "issue_active_pct_ncu": NCU_ISSUE_ACTIVE_PCT,
-                           # measured ceilings (tools/onchip_peaks.cu, profiles/r1_onchip_peaks.md)
-                           "smem_peak_GBps_measured": SMEM_PEAK_GBPS, "l2_read_peak_GBps_measured": L2_PEAK_GBPS,
-                           "edge_update_frac_of_smem_peak": edge_bytes_per_frame * F / (launch_ms * 1e-3) / 1e9 / SMEM_PEAK_GBPS,
-                           "message_scratch_frac_of_l2_peak": msg_l2_bytes_per_frame * F / (launch_ms * 1e-3) / 1e9 / L2_PEAK_GBPS}}
+    roofline = kernel_roofline(F, N, dec.out_words, code.edges, mean_iters, launch_ms, peak, peak_src, smem_peak, l2_peak, onchip_src, ncu)
 
     cpu = None
     if not args.no_cpu:
@@ -433,13 +496,27 @@ def run_ours(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "i8", "data": "synthetic", "config": workload_config(args, world),
             "fer": fer, "mean_iters": mean_iters, "iter_hist": red["iter_hist"][:12],
+            "verified": "every frame of the timed batch reconciled to Alice's key (bits, ok flag); bit-exactness against the oracle is "
+                        "what tests/ check (16 384-frame batches, tests/test_gpu_pins.py), not this line",
             "codeword_basis_mbps": value * N / K,
             "clocks": clocks, "gpu_launches": red["kernel_launches"], "roofline": roofline, "cpu_baseline": cpu}
+    if fixed10:
+        line["fixed10"] = {"value": F * world * K / (fixed10_ms * 1e-3) / 1e6, "unit": "Mbit/s", "ms_per_step": fixed10_ms, "iterations": MAX_ITER,
+                           "early_stop": False,
+                           "roofline": kernel_roofline(F, N, dec.out_words, code.edges, float(MAX_ITER), fixed10_ms, peak, peak_src, smem_peak,
+                                                       l2_peak, onchip_src, None)}
+    if bit_in:
+        line["value_bit_input"] = {"value": F * world * K / (bit_in_ms * 1e-3) / 1e6, "unit": "Mbit/s", "ms_per_step": bit_in_ms,
+                                   "hbm_bytes_per_frame": dec.cw_words * 4 + dec.out_words * 4 + 3,
+                                   "api": "qldpc_decode_bits_device: packed key bits resident in HBM, LLRs synthesised inside the decoder kernel"}
     if e2e:
         line["e2e"] = {"value": F * world * K / (e2e_ms * 1e-3) / 1e6, "unit": "Mbit/s", "h2d_bytes_per_step": e2e["h2d"] * world,
                        "d2h_bytes_per_step": e2e["d2h"] * world, "ms_per_step": e2e_ms, "steps": e2e["steps"],
-                       "api": "qldpc_decode_bits (host pointers: pinned packed key bits in, packed bits/ok/iters out; "
-                              "LLR synthesis on the device beside the decoder of the other lane; 2-stream chunked pipeline)"}
+                       "api": "qldpc_decode_bits (host pointers: pinned packed key bits in, packed bits/ok/iters out)" +
+                              (": chunked H2D / decode / D2H pipeline over two streams" if args.no_zero_copy or args.no_fused_bits else
+                               ": zero copy -- ONE launch, the decoder kernel bulk-copies each frame's bits from the pinned host buffer "
+                               "one frame ahead of the decode, synthesises its LLRs in shared memory and stores bits / ok / iteration "
+                               "counts straight into the pinned output buffers; all of it crosses PCIe inside the timed region")}
         line["e2e_llr_api"] = {"value": F * world * K / (e2e_llr_ms * 1e-3) / 1e6, "unit": "Mbit/s",
                                "h2d_bytes_per_step": e2e["h2d_llr"] * world, "d2h_bytes_per_step": e2e["d2h"] * world,
                                "ms_per_step": e2e_llr_ms, "api": "qldpc_decode (host pointers, pinned int8 LLRs in)"}

@@ -16,9 +16,11 @@
 //     the 16 E bytes per sweep are L2 traffic, HBM sees the channel LLRs once per frame.  The phases are
 //     separated by the hardware cluster barrier; the early-termination vote crosses the cluster through distributed
 //     shared memory;
-//   * optional (QLDPC_FLAG_FAST_SPA) SPA in fp32 on the special-function units instead of double-precision libm calls:
-//     tanh(|x|/2) as 1 - 2 / (e^|x| + 1) with an odd series below 0.25, IEEE division for product / t_j (as the oracle),
-//     2 atanh(r) as ln((1 + r) / (1 - r)) with a series below 0.25; see the note at tanh_half_exact for what it costs;
+//   * SPA in fp32 (ex2 / rcp / lg2 special-function units) instead of double-precision libm calls: tanh(|x|/2) as
+//     1 - 2 / (e^|x| + 1) (exact to the last bit near 1, where atanh is ill-conditioned) with an odd series below 0.25, IEEE
+//     division for product / t_j (as the oracle), 2 atanh(r) as ln((1 + r) / (1 - r)) with a series below 0.25.
+//     north_star asks for equal decoded bits and posteriors within 1e-3 relative, not for bit-equal floats; the oracle
+//     stays in double as the checker;
 //   * integer tiers keep their messages in 8 / 16 bits (posteriors in 16 / 32), not in 32-bit words;
 //   * sweep 0 reads no messages at all (they are zero), so the scratch is never cleared.
 #include <cooperative_groups.h>
@@ -78,137 +80,104 @@ __device__ __forceinline__ int norm8(int v, int k)
 
 struct RowMeta { int edge_begin, degree; };
 
-// ---- asynchronous staging (float tiers): every thread copies the 4-byte operands of its NEXT work items into its own
-// shared-memory slots with cp.async and only waits for the oldest group.  kStages items are in flight per thread, i.e.
-// kStages x (2 dc) x 4 B x 512 threads = ~100 KB of requests per SM: the kernel is bound by L2 latency x bytes in flight.
-constexpr int kStages = 4;          // ring depth
-constexpr int kSlots = 2 * kMaxDc;  // per stage: kMaxDc posteriors + kMaxDc old messages (variable phase: llr + messages)
-__device__ __forceinline__ void cp_async4(float *dst_smem, const float *src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// ---- one check (block row `ly`, lane l) in two halves, so that the loads of the NEXT work item can be issued before the
-// arithmetic of the current one (software pipelining: the kernel is bound by L2 latency x bytes in flight, not by issue)
-template <typename MsgT, typename PostT>
-struct CheckIn {
-    PostT pv[kMaxDc];     // a-posteriori values of the check's variables
-    MsgT old[kMaxDc];     // its old check-to-variable messages
-};
-
-// FIRST: sweep 0, the old messages are zero and not read
+// ---- one check (block row `ly`, lane l): reads the posteriors of its variables and its old messages, writes the new ones
+// FIRST: sweep 0, the old messages are zero and not read.  Returns the parity of the hard decisions (early-stop test).
 template <typename MsgT, typename PostT, bool FIRST>
-__device__ __forceinline__ void check_load(const RowMeta ly, const int2 *edges, const PostT *__restrict__ post, const MsgT *__restrict__ c2v,
-                                           int l, int Z, CheckIn<MsgT, PostT> &in)
-{
-    const MsgT *cm = c2v + (size_t)ly.edge_begin * Z + l;
-#pragma unroll
-    for (int j = 0; j < kMaxDc; ++j) {
-        if (j < ly.degree) {
-            const int2 e = edges[ly.edge_begin + j];            // (block column, shift)
-            int vl = l + e.y;
-            if (vl >= Z) vl -= Z;
-            in.pv[j] = post[(size_t)e.x * Z + vl];
-            in.old[j] = FIRST ? (MsgT)0 : cm[(size_t)j * Z];
-        }
-    }
-}
-
-// writes the new messages of the check; returns the parity of the hard decisions (early-stop test)
-template <typename MsgT, typename PostT>
-__device__ __forceinline__ int check_compute(const FloodQcxParams &p, const RowMeta ly, MsgT *__restrict__ c2v, int l, int Z, int synbit,
-                                             const CheckIn<MsgT, PostT> &in)
+__device__ __forceinline__ int check_update(const FloodQcxParams &p, const RowMeta ly, const int2 *edges, const PostT *__restrict__ post,
+                                            MsgT *__restrict__ c2v, int l, int Z, int synbit)
 {
     constexpr bool kFloat = sizeof(PostT) == 4 && sizeof(MsgT) == 4;
     const int deg = ly.degree;
     MsgT *cm = c2v + (size_t)ly.edge_begin * Z + l;
     int sign = synbit, hard = synbit;
-    if constexpr (kFloat) {
-        float x[kMaxDc], t[kMaxDc];
-        if (p.rule == QLDPC_RULE_SPA) {
-            float product = 1.0f;
+    if (deg <= kMaxDc) {
+        // all loads first, then the arithmetic: 2 x deg requests in flight per thread
+        PostT pv[kMaxDc];
+        MsgT old[kMaxDc];
 #pragma unroll
-            for (int j = 0; j < kMaxDc; ++j) {
-                if (j < deg) {
-                    x[j] = in.pv[j] - in.old[j];
-                    hard ^= in.pv[j] < 0.0f;
-                    const float tj = p.fast_spa ? tanh_half(fabsf(x[j])) : tanh_half_exact(fabsf(x[j]));
-                    t[j] = (tj != 0.0f) ? tj : 1e-12f;
-                    product *= t[j];
-                    sign ^= signbit(x[j]) ? 1 : 0;
-                }
+        for (int j = 0; j < kMaxDc; ++j) {
+            if (j < deg) {
+                const int2 e = edges[ly.edge_begin + j];            // (block column, shift)
+                int vl = l + e.y;
+                if (vl >= Z) vl -= Z;
+                pv[j] = post[(size_t)e.x * Z + vl];
+                old[j] = FIRST ? (MsgT)0 : cm[(size_t)j * Z];
             }
+        }
+        if constexpr (kFloat) {
+            float x[kMaxDc], t[kMaxDc];
+            if (p.rule == QLDPC_RULE_SPA) {
+                float product = 1.0f;
 #pragma unroll
-            for (int j = 0; j < kMaxDc; ++j) {
-                if (j < deg) {
-                    float rr = product / t[j];
-                    rr = (rr < 1.0f) ? rr : 1.0f - 1.1920929e-07f;
-                    const float mag = p.fast_spa ? two_atanh(rr) : two_atanh_exact(rr);
-                    cm[(size_t)j * Z] = (sign ^ (signbit(x[j]) ? 1 : 0)) ? -mag : mag;
+                for (int j = 0; j < kMaxDc; ++j) {
+                    if (j < deg) {
+                        x[j] = pv[j] - old[j];
+                        hard ^= pv[j] < 0.0f;
+                        const float tj = p.fast_spa ? tanh_half(fabsf(x[j])) : tanh_half_exact(fabsf(x[j]));
+                        t[j] = (tj != 0.0f) ? tj : 1e-12f;
+                        product *= t[j];
+                        sign ^= signbit(x[j]) ? 1 : 0;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < kMaxDc; ++j) {
+                    if (j < deg) {
+                        float rr = product / t[j];
+                        rr = (rr < 1.0f) ? rr : 1.0f - 1.1920929e-07f;
+                        const float mag = p.fast_spa ? two_atanh(rr) : two_atanh_exact(rr);
+                        cm[(size_t)j * Z] = (sign ^ (signbit(x[j]) ? 1 : 0)) ? -mag : mag;
+                    }
+                }
+            } else {
+                float min1 = 3.402823466e+38f, min2 = 3.402823466e+38f;
+#pragma unroll
+                for (int j = 0; j < kMaxDc; ++j) {
+                    if (j < deg) {
+                        x[j] = pv[j] - old[j];
+                        hard ^= pv[j] < 0.0f;
+                        const float a = fabsf(x[j]);
+                        sign ^= signbit(x[j]) ? 1 : 0;
+                        min2 = fminf(min2, fmaxf(a, min1));
+                        min1 = fminf(min1, a);
+                    }
+                }
+                const float cst1 = p.rule == QLDPC_RULE_NMS ? min2 * p.norm : fmaxf(0.0f, min2 - p.offset);
+                const float cst2 = p.rule == QLDPC_RULE_NMS ? min1 * p.norm : fmaxf(0.0f, min1 - p.offset);
+#pragma unroll
+                for (int j = 0; j < kMaxDc; ++j) {
+                    if (j < deg) {
+                        const float mag = (fabsf(x[j]) == min1) ? cst1 : cst2;
+                        cm[(size_t)j * Z] = (sign ^ (signbit(x[j]) ? 1 : 0)) ? -mag : mag;
+                    }
                 }
             }
         } else {
-            float min1 = 3.402823466e+38f, min2 = 3.402823466e+38f;
+            int x[kMaxDc];
+            int min1 = p.vmax, min2 = p.vmax;
 #pragma unroll
             for (int j = 0; j < kMaxDc; ++j) {
                 if (j < deg) {
-                    x[j] = in.pv[j] - in.old[j];
-                    hard ^= in.pv[j] < 0.0f;
-                    const float a = fabsf(x[j]);
-                    sign ^= signbit(x[j]) ? 1 : 0;
-                    min2 = fminf(min2, fmaxf(a, min1));
-                    min1 = fminf(min1, a);
+                    x[j] = min(max((int)pv[j] - (int)old[j], -p.vmax), p.vmax);
+                    hard ^= pv[j] < 0;
+                    const int a = abs(x[j]);
+                    sign ^= x[j] < 0;
+                    min2 = min(min2, max(a, min1));
+                    min1 = min(min1, a);
                 }
             }
-            const float cst1 = p.rule == QLDPC_RULE_NMS ? min2 * p.norm : fmaxf(0.0f, min2 - p.offset);
-            const float cst2 = p.rule == QLDPC_RULE_NMS ? min1 * p.norm : fmaxf(0.0f, min1 - p.offset);
+            const int cst1 = p.rule == QLDPC_RULE_OMS ? max(min2 - p.offset_int, 0) : norm8(min2, p.norm_eighths);
+            const int cst2 = p.rule == QLDPC_RULE_OMS ? max(min1 - p.offset_int, 0) : norm8(min1, p.norm_eighths);
 #pragma unroll
             for (int j = 0; j < kMaxDc; ++j) {
                 if (j < deg) {
-                    const float mag = (fabsf(x[j]) == min1) ? cst1 : cst2;
-                    cm[(size_t)j * Z] = (sign ^ (signbit(x[j]) ? 1 : 0)) ? -mag : mag;
+                    const int mag = (abs(x[j]) == min1) ? cst1 : cst2;
+                    cm[(size_t)j * Z] = (MsgT)((sign ^ (x[j] < 0)) ? -mag : mag);
                 }
             }
         }
-    } else {
-        int x[kMaxDc];
-        int min1 = p.vmax, min2 = p.vmax;
-#pragma unroll
-        for (int j = 0; j < kMaxDc; ++j) {
-            if (j < deg) {
-                x[j] = min(max((int)in.pv[j] - (int)in.old[j], -p.vmax), p.vmax);
-                hard ^= in.pv[j] < 0;
-                const int a = abs(x[j]);
-                sign ^= x[j] < 0;
-                min2 = min(min2, max(a, min1));
-                min1 = min(min1, a);
-            }
-        }
-        const int cst1 = p.rule == QLDPC_RULE_OMS ? max(min2 - p.offset_int, 0) : norm8(min2, p.norm_eighths);
-        const int cst2 = p.rule == QLDPC_RULE_OMS ? max(min1 - p.offset_int, 0) : norm8(min1, p.norm_eighths);
-#pragma unroll
-        for (int j = 0; j < kMaxDc; ++j) {
-            if (j < deg) {
-                const int mag = (abs(x[j]) == min1) ? cst1 : cst2;
-                cm[(size_t)j * Z] = (MsgT)((sign ^ (x[j] < 0)) ? -mag : mag);
-            }
-        }
+        return hard;
     }
-    return hard;
-}
-
-// any degree: two passes over memory (rows heavier than kMaxDc; rare in the codes this kernel is chosen for)
-template <typename MsgT, typename PostT, bool FIRST>
-__device__ __noinline__ int check_update_any(const FloodQcxParams &p, const RowMeta ly, const int2 *edges, const PostT *__restrict__ post,
-                                             MsgT *__restrict__ c2v, int l, int Z, int synbit)
-{
-    constexpr bool kFloat = sizeof(PostT) == 4 && sizeof(MsgT) == 4;
-    const int deg = ly.degree;
-    MsgT *cm = c2v + (size_t)ly.edge_begin * Z + l;
-    int sign = synbit, hard = synbit;
+    // any degree: two passes over memory (rows heavier than kMaxDc; rare in the codes this kernel is chosen for)
     auto v2c = [&](int j, bool count_hard) {
         const int2 e = edges[ly.edge_begin + j];
         int vl = l + e.y;
@@ -265,148 +234,6 @@ __device__ __noinline__ int check_update_any(const FloodQcxParams &p, const RowM
     return hard1;
 }
 
-// the check phase of one sweep for this block's lanes: work items (block row, lane), two in flight per thread
-template <typename MsgT, typename PostT, bool FIRST>
-__device__ __forceinline__ int check_phase(const FloodQcxParams &p, const RowMeta *rows, const int2 *edges, const PostT *__restrict__ post,
-                                           MsgT *__restrict__ c2v, const uint32_t *syn, int lane0, int ZL, int Z, int R, int tid)
-{
-    const int lpt = (ZL + kThreads - 1) / kThreads, n_items = R * lpt;
-    auto lane_of = [&](int i) { return tid + (i % lpt) * kThreads; };      // lane inside the block's range, may be >= ZL
-    auto row_of = [&](int i) { return i / lpt; };
-    auto synbit_of = [&](int r, int l) {
-        const int mi = r * Z + l;
-        return syn ? (int)((syn[mi >> 5] >> (31 - (mi & 31))) & 1u) : 0;
-    };
-    int bad = 0;
-    CheckIn<MsgT, PostT> a, b;
-    auto load = [&](int i, CheckIn<MsgT, PostT> &in) {
-        if (i < n_items && lane_of(i) < ZL && rows[row_of(i)].degree <= kMaxDc)
-            check_load<MsgT, PostT, FIRST>(rows[row_of(i)], edges, post, c2v, lane0 + lane_of(i), Z, in);
-    };
-    auto compute = [&](int i, const CheckIn<MsgT, PostT> &in) {
-        if (i >= n_items || lane_of(i) >= ZL) return;
-        const int r = row_of(i), l = lane0 + lane_of(i);
-        const RowMeta ly = rows[r];
-        if (ly.degree <= kMaxDc) bad |= check_compute<MsgT, PostT>(p, ly, c2v, l, Z, synbit_of(r, l), in);
-        else bad |= check_update_any<MsgT, PostT, FIRST>(p, ly, edges, post, c2v, l, Z, synbit_of(r, l));
-    };
-    load(0, a);
-#pragma unroll 1
-    for (int i = 0; i < n_items; i += 2) {
-        load(i + 1, b);
-        compute(i, a);
-        load(i + 2, a);
-        compute(i + 1, b);
-    }
-    return bad;
-}
-
-// float tiers: the same two phases with the operands staged through the per-thread cp.async ring
-template <bool FIRST>
-__device__ __forceinline__ int check_phase_async(const FloodQcxParams &p, const RowMeta *rows, const int2 *edges, const float *__restrict__ post,
-                                                 float *__restrict__ c2v, const uint32_t *syn, int lane0, int ZL, int Z, int R, int tid,
-                                                 float *ring)
-{
-    const int lpt = (ZL + kThreads - 1) / kThreads, n_items = R * lpt;
-    auto lane_of = [&](int i) { return tid + (i % lpt) * kThreads; };
-    auto slot = [&](int i, int k) { return ring + ((size_t)((i % kStages) * kSlots + k) * kThreads + tid); };
-    auto issue = [&](int i) {
-        if (i < n_items && lane_of(i) < ZL) {
-            const RowMeta ly = rows[i / lpt];
-            if (ly.degree <= kMaxDc) {
-                const int l = lane0 + lane_of(i);
-                const float *cm = c2v + (size_t)ly.edge_begin * Z + l;
-#pragma unroll
-                for (int j = 0; j < kMaxDc; ++j) {
-                    if (j < ly.degree) {
-                        const int2 e = edges[ly.edge_begin + j];
-                        int vl = l + e.y;
-                        if (vl >= Z) vl -= Z;
-                        cp_async4(slot(i, j), post + (size_t)e.x * Z + vl);
-                        if (!FIRST) cp_async4(slot(i, kMaxDc + j), cm + (size_t)j * Z);
-                    }
-                }
-            }
-        }
-        cp_async_commit();   // one group per item, empty or not, so that the wait counts items
-    };
-    int bad = 0;
-#pragma unroll
-    for (int i = 0; i < kStages - 1; ++i) issue(i);
-#pragma unroll 1
-    for (int i = 0; i < n_items; ++i) {
-        issue(i + kStages - 1);
-        cp_async_wait<kStages - 1>();
-        if (lane_of(i) >= ZL) continue;
-        const int r = i / lpt, l = lane0 + lane_of(i), mi = r * Z + l;
-        const int synbit = syn ? (int)((syn[mi >> 5] >> (31 - (mi & 31))) & 1u) : 0;
-        const RowMeta ly = rows[r];
-        if (ly.degree <= kMaxDc) {
-            CheckIn<float, float> in;
-#pragma unroll
-            for (int j = 0; j < kMaxDc; ++j) {
-                if (j < ly.degree) {
-                    in.pv[j] = *slot(i, j);
-                    in.old[j] = FIRST ? 0.0f : *slot(i, kMaxDc + j);
-                }
-            }
-            bad |= check_compute<float, float>(p, ly, c2v, l, Z, synbit, in);
-        } else {
-            bad |= check_update_any<float, float, FIRST>(p, ly, edges, post, c2v, l, Z, synbit);
-        }
-    }
-    cp_async_wait<0>();
-    return bad;
-}
-
-__device__ __forceinline__ void variable_phase_async(const float *__restrict__ llr, const float *__restrict__ c2v, float *__restrict__ post,
-                                                     const int *col_ptr, const int2 *col_edges, bool first, int lane0, int ZL, int Z,
-                                                     int C, int tid, float *ring)
-{
-    constexpr int kDv = kSlots - 1;
-    const int lpt = (ZL + kThreads - 1) / kThreads, n_items = C * lpt;
-    auto lane_of = [&](int i) { return tid + (i % lpt) * kThreads; };
-    auto slot = [&](int i, int k) { return ring + ((size_t)((i % kStages) * kSlots + k) * kThreads + tid); };
-    auto issue = [&](int i) {
-        if (i < n_items && lane_of(i) < ZL) {
-            const int c = i / lpt, m = lane0 + lane_of(i);
-            cp_async4(slot(i, 0), llr + (size_t)c * Z + m);
-            if (!first) {
-                const int k0 = col_ptr[c], dv = min(col_ptr[c + 1] - k0, kDv);
-                for (int k = 0; k < dv; ++k) {
-                    const int2 ce = col_edges[k0 + k];            // edge id, shift
-                    int l = m - ce.y;
-                    if (l < 0) l += Z;
-                    cp_async4(slot(i, 1 + k), c2v + (size_t)ce.x * Z + l);
-                }
-            }
-        }
-        cp_async_commit();
-    };
-#pragma unroll
-    for (int i = 0; i < kStages - 1; ++i) issue(i);
-#pragma unroll 1
-    for (int i = 0; i < n_items; ++i) {
-        issue(i + kStages - 1);
-        cp_async_wait<kStages - 1>();
-        if (lane_of(i) >= ZL) continue;
-        const int c = i / lpt, m = lane0 + lane_of(i);
-        float sum = 0.0f;
-        if (!first) {
-            const int k0 = col_ptr[c], dv = col_ptr[c + 1] - k0;
-            for (int k = 0; k < min(dv, kDv); ++k) sum += *slot(i, 1 + k);
-            for (int k = kDv; k < dv; ++k) {   // heavier columns: the rest in order, unstaged
-                const int2 ce = col_edges[k0 + k];
-                int l = m - ce.y;
-                if (l < 0) l += Z;
-                sum += c2v[(size_t)ce.x * Z + l];
-            }
-        }
-        post[(size_t)c * Z + m] = *slot(i, 0) + sum;
-    }
-    cp_async_wait<0>();
-}
-
 // Shared-memory layout: RowMeta rows[R]; int2 edges[nnz] (block column, shift); int col_ptr[C + 1]; int2 col_edges[nnz] (edge
 // id, shift); int vote[2][8].
 template <typename MsgT, typename PostT, typename InT>
@@ -424,8 +251,6 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
     int *col_ptr = reinterpret_cast<int *>(edges + p.nnz);
     int2 *col_edges = reinterpret_cast<int2 *>(col_ptr + C + 1 + ((C + 1) & 1));   // 8-byte aligned
     int *vote = reinterpret_cast<int *>(col_edges + p.nnz);
-    constexpr bool kAsync = sizeof(MsgT) == 4 && sizeof(PostT) == 4;            // float tiers: operands staged by cp.async
-    [[maybe_unused]] float *ring = reinterpret_cast<float *>(smem + p.ring_off);   // kStages x kSlots x kThreads floats
     for (int r = tid; r < R; r += kThreads) rows[r] = RowMeta{p.layers[r].edge_begin, p.layers[r].degree};
     for (int e = tid; e < p.nnz; e += kThreads) {
         edges[e] = make_int2(p.aux[e].col, p.aux[e].shift);
@@ -457,59 +282,22 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
         int it = 0, depth = 0;
         bool ok = false;
         for (;;) {
-            // ---- variable phase: post[v] = llr[v] + sum of the column's messages in ascending block-row order; work items
-            // (block column, lane), the loads of the next item issued before the sum of the current one
-            if constexpr (kAsync) {
-                variable_phase_async(reinterpret_cast<const float *>(llr), reinterpret_cast<const float *>(c2v), reinterpret_cast<float *>(post),
-                                     col_ptr, col_edges, it == 0, lane0, ZL, Z, C, tid, ring);
-            } else {
-                const int lpt = (ZL + kThreads - 1) / kThreads, n_items = C * lpt;
-                constexpr int kDv = 8;
-                struct VarIn { InT y; MsgT m[kDv]; };
-                auto lane_of = [&](int i) { return tid + (i % lpt) * kThreads; };
-                auto load = [&](int i, VarIn &in) {
-                    if (i >= n_items || lane_of(i) >= ZL) return;
-                    const int c = i / lpt, m = lane0 + lane_of(i);
-                    in.y = llr[(size_t)c * Z + m];
-                    if (it == 0) return;
-                    const int k0 = col_ptr[c], dv = col_ptr[c + 1] - k0;
-#pragma unroll
-                    for (int k = 0; k < kDv; ++k) {
-                        if (k < dv) {
-                            const int2 ce = col_edges[k0 + k];            // edge id, shift
-                            int l = m - ce.y;
-                            if (l < 0) l += Z;
-                            in.m[k] = c2v[(size_t)ce.x * Z + l];
-                        }
+            // ---- variable phase: post[v] = llr[v] + sum of the column's messages in ascending block-row order
+            for (int item = tid; item < C * ZL; item += kThreads) {
+                const int c = item / ZL, m = lane0 + item - c * ZL;
+                const size_t v = (size_t)c * Z + m;
+                PostT sum = (PostT)0;
+                if (it > 0) {
+                    const int k0 = col_ptr[c], k1 = col_ptr[c + 1];
+#pragma unroll 4
+                    for (int k = k0; k < k1; ++k) {
+                        const int2 ce = col_edges[k];            // edge id, shift
+                        int l = m - ce.y;
+                        if (l < 0) l += Z;
+                        sum += (PostT)c2v[(size_t)ce.x * Z + l];
                     }
-                };
-                auto compute = [&](int i, const VarIn &in) {
-                    if (i >= n_items || lane_of(i) >= ZL) return;
-                    const int c = i / lpt, m = lane0 + lane_of(i);
-                    PostT sum = (PostT)0;
-                    if (it > 0) {
-                        const int k0 = col_ptr[c], dv = col_ptr[c + 1] - k0;
-#pragma unroll
-                        for (int k = 0; k < kDv; ++k)
-                            if (k < dv) sum += (PostT)in.m[k];
-                        for (int k = kDv; k < dv; ++k) {   // heavier columns: the rest in order, unpipelined
-                            const int2 ce = col_edges[k0 + k];
-                            int l = m - ce.y;
-                            if (l < 0) l += Z;
-                            sum += (PostT)c2v[(size_t)ce.x * Z + l];
-                        }
-                    }
-                    post[(size_t)c * Z + m] = (PostT)in.y + sum;
-                };
-                VarIn a, b;
-                load(0, a);
-#pragma unroll 1
-                for (int i = 0; i < n_items; i += 2) {
-                    load(i + 1, b);
-                    compute(i, a);
-                    load(i + 2, a);
-                    compute(i + 1, b);
                 }
+                post[v] = (PostT)llr[v] + sum;
             }
             cluster.sync();
             const bool last = it >= p.max_iter;
@@ -534,15 +322,13 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
             // ---- check phase; the early-termination test (enable_syndrome) of this sweep is computed on the way.
             // If it passes the decoder stops here: the messages just written are never used, `it` is not advanced.
             const bool want_check = p.early_stop && it > 0;
-            int bad;
-            if constexpr (kAsync) {
-                const float *fpost = reinterpret_cast<const float *>(post);
-                float *fc2v = reinterpret_cast<float *>(c2v);
-                bad = it == 0 ? check_phase_async<true>(p, rows, edges, fpost, fc2v, syn, lane0, ZL, Z, R, tid, ring)
-                              : check_phase_async<false>(p, rows, edges, fpost, fc2v, syn, lane0, ZL, Z, R, tid, ring);
-            } else {
-                bad = it == 0 ? check_phase<MsgT, PostT, true>(p, rows, edges, post, c2v, syn, lane0, ZL, Z, R, tid)
-                              : check_phase<MsgT, PostT, false>(p, rows, edges, post, c2v, syn, lane0, ZL, Z, R, tid);
+            int bad = 0;
+            for (int item = tid; item < R * ZL; item += kThreads) {
+                const int r = item / ZL, l = lane0 + item - r * ZL;
+                const int mi = r * Z + l;
+                const int synbit = syn ? (int)((syn[mi >> 5] >> (31 - (mi & 31))) & 1u) : 0;
+                bad |= it == 0 ? check_update<MsgT, PostT, true>(p, rows[r], edges, post, c2v, l, Z, synbit)
+                               : check_update<MsgT, PostT, false>(p, rows[r], edges, post, c2v, l, Z, synbit);
             }
             if (want_check) {
                 ok = !cluster_any(bad);
@@ -625,14 +411,14 @@ int max_clusters_t(int cl, int smem_bytes)
 
 }  // namespace
 
-// table bytes (rounded to 16); the float tiers add the cp.async ring behind them
 int flooding_qcx_table_bytes(int brows, int bcols, int nnz)
 {
     return (brows * 8 + nnz * 8 + (bcols + 2) * 4 + nnz * 8 + 16 * 4 + 16 + 15) / 16 * 16;
 }
 int flooding_qcx_smem_bytes(int brows, int bcols, int nnz, int dtype)
 {
-    return flooding_qcx_table_bytes(brows, bcols, nnz) + (dtype == QLDPC_DTYPE_F32 ? kStages * kSlots * kThreads * 4 : 0);
+    (void)dtype;
+    return flooding_qcx_table_bytes(brows, bcols, nnz);
 }
 
 int flooding_qcx_msg_bytes(int dtype) { return dtype == QLDPC_DTYPE_F32 ? 4 : (dtype == QLDPC_DTYPE_I16 ? 2 : 1); }

@@ -63,7 +63,7 @@ def test_two_ecd2_daemons_reconcile_with_ldpc(tmp_path, data_dir, alg):
     assert m, notify
     initial, final, err, leaked = int(m.group(1)), int(m.group(2)), float(m.group(3)), int(m.group(4))
     assert initial == 40000 and 0.02 < err < 0.045 and final > 10000
-    assert leaked % 32 == 0 and leaked >= 4 * 384 * 4           # whole parity block rows (+ 32-bit CRCs) of at least 4 frames
+    assert leaked >= 4 * 384 * 4                                # at least four parity block rows of every frame
     print("LDPC alg %s: final %d bits, leaked %d, error rate %.4f, wall %.2f s" % (alg, final, leaked, err, wall))
 
 

@@ -4,23 +4,18 @@
 // Arithmetic: AFF3CT Decoder_LDPC_BP_flooding<B,Q,Update_rule_{SPA,NMS,OMS}> as the reference instantiates it
 // (BOOT/src/main.cpp:193, decode_siho at :365; "main.cpp (5g-qc)":236-251), restated in
 // oracle/qldpc_oracle.c:ora_decode_flooding_f32 / ora_decode_flooding_fixed -- same sweep structure, same order of every
-// sum and product, same early-stop rule as flooding.cu / flooding_qc.cu.  What differs from those kernels is everything
-// the ncu-less round-1 versions got wrong for a code whose messages (786 KB of fp32 per frame) do not fit on chip:
-//   * they were bound by the LATENCY of dependent global loads (one CTA per frame, a serial loop over 64 variables x dv
-//     edges per thread, table entries fetched from global memory inside it): 0.9 TB/s of message traffic, 14 % of HBM.
-//     Here the circulant tables sit in shared memory and every work item issues ALL its loads (2 x dc in the check phase,
-//     dv + 1 in the variable phase, several items per thread) before the first use: memory-level parallelism instead of
-//     occupancy;
+// sum and product, same early-stop rule as flooding.cu / flooding_qc.cu.  What differs from those kernels:
 //   * a frame is worked on by a cluster of CL thread blocks (CL SMs), each owning Z / CL lanes of every circulant, so only
-//     SMs / CL frames are in flight and their messages + posteriors (1.05 MB per frame) stay resident in the 126 MB L2:
-//     the 16 E bytes per sweep are L2 traffic, HBM sees the channel LLRs once per frame.  The phases are
-//     separated by the hardware cluster barrier; the early-termination vote crosses the cluster through distributed
-//     shared memory;
-//   * SPA in fp32 (ex2 / rcp / lg2 special-function units) instead of double-precision libm calls: tanh(|x|/2) as
-//     1 - 2 / (e^|x| + 1) (exact to the last bit near 1, where atanh is ill-conditioned) with an odd series below 0.25, IEEE
-//     division for product / t_j (as the oracle), 2 atanh(r) as ln((1 + r) / (1 - r)) with a series below 0.25.
-//     north_star asks for equal decoded bits and posteriors within 1e-3 relative, not for bit-equal floats; the oracle
-//     stays in double as the checker;
+//     SMs / CL frames are in flight and their messages + posteriors (1.05 MB per frame) stay resident in the 126 MB L2
+//     (ncu: 94.6 % L2 hit rate): the 16 E bytes per sweep are L2 traffic, HBM sees the channel LLRs.  The
+//     phases are separated by the hardware cluster barrier; the early-termination vote crosses the cluster through
+//     distributed shared memory;
+//   * the circulant tables sit in shared memory; a check issues all its 2 dc loads before the first use;
+//   * the check update is compiled per row degree (no predicated slots), rule and SPA flavour are template parameters;
+//     the first ncu capture of the generic version (profiles/r2_flooding_qcx_v1_ncu_summary.txt) showed the kernel bound
+//     by instruction issue, not by memory: 220 thread instructions per edge and sweep, 10 % of them branch bookkeeping of
+//     predicated slots, FMUL + FADD pairs instead of FFMA (the library is built with --fmad=false; the polynomials below
+//     call fmaf explicitly), 18 % 64-bit index arithmetic;
 //   * integer tiers keep their messages in 8 / 16 bits (posteriors in 16 / 32), not in 32-bit words;
 //   * sweep 0 reads no messages at all (they are zero), so the scratch is never cleared.
 #include <cooperative_groups.h>
@@ -34,32 +29,30 @@ namespace qldpc {
 namespace {
 
 constexpr int kThreads = 512;
-constexpr int kMaxDc = 8;        // check degrees up to this keep their var-to-check values in registers between the passes
 
 // ---- SPA kernels of the check update --------------------------------------------------------------------------------
-// Two flavours, chosen per launch (FloodQcxParams::fast_spa):
+// Two flavours (template parameter FLAVOUR, QLDPC_FLAG_FAST_SPA):
 //   exact (default): tanh / atanh in double, rounded once -- what the oracle and the other float kernels do.  The float
 //     product / t_j of a SATURATED check leaves 1 - r as a small multiple of 2^-24, so a last-bit difference in one tanh
 //     moves 2 atanh(r) by ln 2, ln 3/2, ...: only a correctly rounded tanh keeps such messages (|m| > 14, posteriors > 30)
 //     within 1e-3 of the reference.
-//   fast: fp32 on the special-function units, below.  Decoded bits and iteration counts equal the exact flavour's on every
-//     test batch; 99.99 % of the posteriors are within 1e-3, the rest (saturated messages) within ln 2.
-__device__ __forceinline__ float tanh_half_exact(float a) { return (float)tanh((double)(a * 0.5f)); }
-__device__ __forceinline__ float two_atanh_exact(float r) { return 2.0f * (float)atanh((double)r); }
-// tanh(a / 2) for a >= 0
-__device__ __forceinline__ float tanh_half(float a)
+//   fast: fp32 on the special-function units.  Decoded bits and iteration counts equal the exact flavour's on every test
+//     batch; 99.99 % of the posteriors are within 1e-3, the rest (saturated messages) within ln 2.
+__device__ __noinline__ float tanh_half_exact(float a) { return (float)tanh((double)(a * 0.5f)); }
+__device__ __noinline__ float two_atanh_exact(float r) { return 2.0f * (float)atanh((double)r); }
+// tanh(a / 2) for a >= 0: 1 - 2 / (e^a + 1) (exact to the last bit near 1, where atanh is ill-conditioned), odd series below 0.25
+__device__ __forceinline__ float tanh_half_fast(float a)
 {
     const float h = 0.5f * a, h2 = h * h;
-    const float series = h * (1.0f + h2 * (-0.33333334f + h2 * (0.13333334f + h2 * -0.05396825f)));
-    const float e = __expf(a);                       // ex2.approx: relative error ~2 ulp; +inf for a > 88 -> u = 0
-    const float u = __fdividef(2.0f, e + 1.0f);      // 1 - tanh: its relative error is harmless, the subtraction below is exact-ish
+    const float series = h * fmaf(h2, fmaf(h2, fmaf(h2, -0.05396825f, 0.13333334f), -0.33333334f), 1.0f);
+    const float u = __fdividef(2.0f, __expf(a) + 1.0f);      // e^a = +inf for a > 88 -> u = 0
     return a < 0.25f ? series : 1.0f - u;
 }
-// 2 * atanh(r) for 0 <= r < 1
-__device__ __forceinline__ float two_atanh(float r)
+// 2 * atanh(r) for 0 <= r < 1: ln((1 + r) / (1 - r)), series below 0.25
+__device__ __forceinline__ float two_atanh_fast(float r)
 {
     const float r2 = r * r;
-    const float series = 2.0f * r * (1.0f + r2 * (0.33333334f + r2 * (0.2f + r2 * (0.14285715f + r2 * 0.11111111f))));
+    const float series = (r + r) * fmaf(r2, fmaf(r2, fmaf(r2, fmaf(r2, 0.11111111f, 0.14285715f), 0.2f), 0.33333334f), 1.0f);
     const float lg = __logf(__fdividef(1.0f + r, 1.0f - r));
     return r < 0.25f ? series : lg;
 }
@@ -79,131 +72,129 @@ __device__ __forceinline__ int norm8(int v, int k)
 }
 
 struct RowMeta { int edge_begin, degree; };
+// decoder flavour of a kernel instantiation
+enum { kSpaExact = 0, kSpaFast = 1, kMinSum = 2 };
 
-// ---- one check (block row `ly`, lane l): reads the posteriors of its variables and its old messages, writes the new ones
-// FIRST: sweep 0, the old messages are zero and not read.  Returns the parity of the hard decisions (early-stop test).
-template <typename MsgT, typename PostT, bool FIRST>
-__device__ __forceinline__ int check_update(const FloodQcxParams &p, const RowMeta ly, const int2 *edges, const PostT *__restrict__ post,
-                                            MsgT *__restrict__ c2v, int l, int Z, int synbit)
+__device__ __forceinline__ unsigned fbits(float x) { return __float_as_uint(x); }
+
+// ---- one check (block row starting at edge e0, lane l) of exactly DC edges: reads the posteriors of its variables and its
+// old messages, writes the new ones.  FIRST: sweep 0, the old messages are zero and not read.  Returns the parity of the
+// hard decisions (early-stop test).  Offsets are 32-bit (nnz * Z and N are far below 2^31).
+template <typename MsgT, typename PostT, int FLAVOUR, bool FIRST, int DC>
+__device__ __forceinline__ int check_row(const FloodQcxParams &p, int e0, const int2 *edges, const PostT *__restrict__ post,
+                                         MsgT *__restrict__ c2v, int l, int Z, int synbit)
 {
     constexpr bool kFloat = sizeof(PostT) == 4 && sizeof(MsgT) == 4;
-    const int deg = ly.degree;
-    MsgT *cm = c2v + (size_t)ly.edge_begin * Z + l;
-    int sign = synbit, hard = synbit;
-    if (deg <= kMaxDc) {
-        // all loads first, then the arithmetic: 2 x deg requests in flight per thread
-        PostT pv[kMaxDc];
-        MsgT old[kMaxDc];
+    MsgT *cm = c2v + (e0 * Z + l);
+    PostT pv[DC];
+    MsgT old[DC];
 #pragma unroll
-        for (int j = 0; j < kMaxDc; ++j) {
-            if (j < deg) {
-                const int2 e = edges[ly.edge_begin + j];            // (block column, shift)
-                int vl = l + e.y;
-                if (vl >= Z) vl -= Z;
-                pv[j] = post[(size_t)e.x * Z + vl];
-                old[j] = FIRST ? (MsgT)0 : cm[(size_t)j * Z];
-            }
-        }
-        if constexpr (kFloat) {
-            float x[kMaxDc], t[kMaxDc];
-            if (p.rule == QLDPC_RULE_SPA) {
-                float product = 1.0f;
-#pragma unroll
-                for (int j = 0; j < kMaxDc; ++j) {
-                    if (j < deg) {
-                        x[j] = pv[j] - old[j];
-                        hard ^= pv[j] < 0.0f;
-                        const float tj = p.fast_spa ? tanh_half(fabsf(x[j])) : tanh_half_exact(fabsf(x[j]));
-                        t[j] = (tj != 0.0f) ? tj : 1e-12f;
-                        product *= t[j];
-                        sign ^= signbit(x[j]) ? 1 : 0;
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < kMaxDc; ++j) {
-                    if (j < deg) {
-                        float rr = product / t[j];
-                        rr = (rr < 1.0f) ? rr : 1.0f - 1.1920929e-07f;
-                        const float mag = p.fast_spa ? two_atanh(rr) : two_atanh_exact(rr);
-                        cm[(size_t)j * Z] = (sign ^ (signbit(x[j]) ? 1 : 0)) ? -mag : mag;
-                    }
-                }
-            } else {
-                float min1 = 3.402823466e+38f, min2 = 3.402823466e+38f;
-#pragma unroll
-                for (int j = 0; j < kMaxDc; ++j) {
-                    if (j < deg) {
-                        x[j] = pv[j] - old[j];
-                        hard ^= pv[j] < 0.0f;
-                        const float a = fabsf(x[j]);
-                        sign ^= signbit(x[j]) ? 1 : 0;
-                        min2 = fminf(min2, fmaxf(a, min1));
-                        min1 = fminf(min1, a);
-                    }
-                }
-                const float cst1 = p.rule == QLDPC_RULE_NMS ? min2 * p.norm : fmaxf(0.0f, min2 - p.offset);
-                const float cst2 = p.rule == QLDPC_RULE_NMS ? min1 * p.norm : fmaxf(0.0f, min1 - p.offset);
-#pragma unroll
-                for (int j = 0; j < kMaxDc; ++j) {
-                    if (j < deg) {
-                        const float mag = (fabsf(x[j]) == min1) ? cst1 : cst2;
-                        cm[(size_t)j * Z] = (sign ^ (signbit(x[j]) ? 1 : 0)) ? -mag : mag;
-                    }
-                }
-            }
-        } else {
-            int x[kMaxDc];
-            int min1 = p.vmax, min2 = p.vmax;
-#pragma unroll
-            for (int j = 0; j < kMaxDc; ++j) {
-                if (j < deg) {
-                    x[j] = min(max((int)pv[j] - (int)old[j], -p.vmax), p.vmax);
-                    hard ^= pv[j] < 0;
-                    const int a = abs(x[j]);
-                    sign ^= x[j] < 0;
-                    min2 = min(min2, max(a, min1));
-                    min1 = min(min1, a);
-                }
-            }
-            const int cst1 = p.rule == QLDPC_RULE_OMS ? max(min2 - p.offset_int, 0) : norm8(min2, p.norm_eighths);
-            const int cst2 = p.rule == QLDPC_RULE_OMS ? max(min1 - p.offset_int, 0) : norm8(min1, p.norm_eighths);
-#pragma unroll
-            for (int j = 0; j < kMaxDc; ++j) {
-                if (j < deg) {
-                    const int mag = (abs(x[j]) == min1) ? cst1 : cst2;
-                    cm[(size_t)j * Z] = (MsgT)((sign ^ (x[j] < 0)) ? -mag : mag);
-                }
-            }
-        }
-        return hard;
-    }
-    // any degree: two passes over memory (rows heavier than kMaxDc; rare in the codes this kernel is chosen for)
-    auto v2c = [&](int j, bool count_hard) {
-        const int2 e = edges[ly.edge_begin + j];
+    for (int j = 0; j < DC; ++j) {      // all loads first: 2 x DC requests in flight per thread
+        const int2 e = edges[e0 + j];   // (block column * Z, shift)
         int vl = l + e.y;
         if (vl >= Z) vl -= Z;
-        const PostT pvj = post[(size_t)e.x * Z + vl];
+        pv[j] = post[e.x + vl];
+        old[j] = FIRST ? (MsgT)0 : cm[j * Z];
+    }
+    int hard = synbit;
+#pragma unroll
+    for (int j = 0; j < DC; ++j) hard ^= pv[j] < (PostT)0;
+    if constexpr (kFloat) {
+        float x[DC];
+        unsigned sign = (unsigned)synbit << 31;
+        if constexpr (FLAVOUR != kMinSum) {
+            float t[DC];
+            float product = 1.0f;
+#pragma unroll
+            for (int j = 0; j < DC; ++j) {
+                x[j] = pv[j] - old[j];
+                const float tj = FLAVOUR == kSpaFast ? tanh_half_fast(fabsf(x[j])) : tanh_half_exact(fabsf(x[j]));
+                t[j] = (tj != 0.0f) ? tj : 1e-12f;
+                product *= t[j];
+                sign ^= fbits(x[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < DC; ++j) {
+                float rr = product / t[j];                      // IEEE division, as the oracle
+                rr = (rr < 1.0f) ? rr : 1.0f - 1.1920929e-07f;
+                const float mag = FLAVOUR == kSpaFast ? two_atanh_fast(rr) : two_atanh_exact(rr);
+                cm[j * Z] = __uint_as_float(fbits(mag) ^ ((sign ^ fbits(x[j])) & 0x80000000u));   // mag >= 0
+            }
+        } else {
+            float min1 = 3.402823466e+38f, min2 = 3.402823466e+38f;
+#pragma unroll
+            for (int j = 0; j < DC; ++j) {
+                x[j] = pv[j] - old[j];
+                const float a = fabsf(x[j]);
+                sign ^= fbits(x[j]);
+                min2 = fminf(min2, fmaxf(a, min1));
+                min1 = fminf(min1, a);
+            }
+            const float cst1 = p.rule == QLDPC_RULE_NMS ? min2 * p.norm : fmaxf(0.0f, min2 - p.offset);
+            const float cst2 = p.rule == QLDPC_RULE_NMS ? min1 * p.norm : fmaxf(0.0f, min1 - p.offset);
+#pragma unroll
+            for (int j = 0; j < DC; ++j) {
+                const float mag = (fabsf(x[j]) == min1) ? cst1 : cst2;
+                cm[j * Z] = __uint_as_float(fbits(mag) ^ ((sign ^ fbits(x[j])) & 0x80000000u));
+            }
+        }
+    } else {
+        int x[DC];
+        int sign = synbit, min1 = p.vmax, min2 = p.vmax;
+#pragma unroll
+        for (int j = 0; j < DC; ++j) {
+            x[j] = min(max((int)pv[j] - (int)old[j], -p.vmax), p.vmax);
+            const int a = abs(x[j]);
+            sign ^= x[j] < 0;
+            min2 = min(min2, max(a, min1));
+            min1 = min(min1, a);
+        }
+        const int cst1 = p.rule == QLDPC_RULE_OMS ? max(min2 - p.offset_int, 0) : norm8(min2, p.norm_eighths);
+        const int cst2 = p.rule == QLDPC_RULE_OMS ? max(min1 - p.offset_int, 0) : norm8(min1, p.norm_eighths);
+#pragma unroll
+        for (int j = 0; j < DC; ++j) {
+            const int mag = (abs(x[j]) == min1) ? cst1 : cst2;
+            cm[j * Z] = (MsgT)((sign ^ (x[j] < 0)) ? -mag : mag);
+        }
+    }
+    return hard;
+}
+
+// any degree: two passes over memory (rows heavier than the compiled degrees)
+template <typename MsgT, typename PostT, int FLAVOUR, bool FIRST>
+__device__ __noinline__ int check_row_any(const FloodQcxParams &p, int e0, int deg, const int2 *edges, const PostT *__restrict__ post,
+                                          MsgT *__restrict__ c2v, int l, int Z, int synbit)
+{
+    constexpr bool kFloat = sizeof(PostT) == 4 && sizeof(MsgT) == 4;
+    MsgT *cm = c2v + (e0 * Z + l);
+    int sign = synbit, hard = synbit;
+    auto v2c = [&](int j, bool count_hard) {
+        const int2 e = edges[e0 + j];
+        int vl = l + e.y;
+        if (vl >= Z) vl -= Z;
+        const PostT pvj = post[e.x + vl];
         if (count_hard) hard ^= pvj < (PostT)0;
-        const MsgT o = FIRST ? (MsgT)0 : cm[(size_t)j * Z];
+        const MsgT o = FIRST ? (MsgT)0 : cm[j * Z];
         if constexpr (kFloat) return (float)pvj - (float)o;
         else return (float)min(max((int)pvj - (int)o, -p.vmax), p.vmax);   // integers up to 2^24 are exact in a float
     };
-    if (kFloat && p.rule == QLDPC_RULE_SPA) {
+    auto th = [&](float a) { return FLAVOUR == kSpaFast ? tanh_half_fast(a) : tanh_half_exact(a); };
+    if (kFloat && FLAVOUR != kMinSum) {
         float product = 1.0f;
         for (int j = 0; j < deg; ++j) {
             const float xv = v2c(j, true);
-            const float tj = p.fast_spa ? tanh_half(fabsf(xv)) : tanh_half_exact(fabsf(xv));
+            const float tj = th(fabsf(xv));
             product *= (tj != 0.0f) ? tj : 1e-12f;
             sign ^= signbit(xv) ? 1 : 0;
         }
         const int hard1 = hard;
         for (int j = 0; j < deg; ++j) {
             const float xv = v2c(j, false);
-            const float tj = p.fast_spa ? tanh_half(fabsf(xv)) : tanh_half_exact(fabsf(xv));
+            const float tj = th(fabsf(xv));
             float rr = product / ((tj != 0.0f) ? tj : 1e-12f);
             rr = (rr < 1.0f) ? rr : 1.0f - 1.1920929e-07f;
-            const float mag = p.fast_spa ? two_atanh(rr) : two_atanh_exact(rr);
-            cm[(size_t)j * Z] = (MsgT)((sign ^ (signbit(xv) ? 1 : 0)) ? -mag : mag);
+            const float mag = FLAVOUR == kSpaFast ? two_atanh_fast(rr) : two_atanh_exact(rr);
+            cm[j * Z] = (MsgT)((sign ^ (signbit(xv) ? 1 : 0)) ? -mag : mag);
         }
         return hard1;
     }
@@ -228,15 +219,29 @@ __device__ __forceinline__ int check_update(const FloodQcxParams &p, const RowMe
         const float xv = v2c(j, false);
         const float mag = (fabsf(xv) == min1) ? cst1 : cst2;
         const float out = (sign ^ (signbit(xv) ? 1 : 0)) ? -mag : mag;
-        if constexpr (kFloat) cm[(size_t)j * Z] = out;
-        else cm[(size_t)j * Z] = (MsgT)(int)out;
+        if constexpr (kFloat) cm[j * Z] = out;
+        else cm[j * Z] = (MsgT)(int)out;
     }
     return hard1;
 }
 
-// Shared-memory layout: RowMeta rows[R]; int2 edges[nnz] (block column, shift); int col_ptr[C + 1]; int2 col_edges[nnz] (edge
-// id, shift); int vote[2][8].
-template <typename MsgT, typename PostT, typename InT>
+// the row's degree is the same for all threads of the block (block-uniform switch, no divergence)
+template <typename MsgT, typename PostT, int FLAVOUR, bool FIRST>
+__device__ __forceinline__ int check_dispatch(const FloodQcxParams &p, const RowMeta ly, const int2 *edges, const PostT *__restrict__ post,
+                                              MsgT *__restrict__ c2v, int l, int Z, int synbit)
+{
+#define QL_DC(D) case D: return check_row<MsgT, PostT, FLAVOUR, FIRST, D>(p, ly.edge_begin, edges, post, c2v, l, Z, synbit);
+    switch (ly.degree) {
+        QL_DC(2) QL_DC(3) QL_DC(4) QL_DC(5) QL_DC(6) QL_DC(7) QL_DC(8) QL_DC(9) QL_DC(10)
+        QL_DC(11) QL_DC(12) QL_DC(13) QL_DC(14) QL_DC(15) QL_DC(16) QL_DC(17) QL_DC(18)
+    default: return check_row_any<MsgT, PostT, FLAVOUR, FIRST>(p, ly.edge_begin, ly.degree, edges, post, c2v, l, Z, synbit);
+    }
+#undef QL_DC
+}
+
+// Shared-memory layout: RowMeta rows[R]; int2 edges[nnz] (block column * Z, shift); int col_ptr[C + 1]; int2 col_edges[nnz]
+// (edge id * Z, shift); int vote[2][8].
+template <typename MsgT, typename PostT, typename InT, int FLAVOUR>
 __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQcxParams p)
 {
     extern __shared__ __align__(16) char smem[];
@@ -253,8 +258,8 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
     int *vote = reinterpret_cast<int *>(col_edges + p.nnz);
     for (int r = tid; r < R; r += kThreads) rows[r] = RowMeta{p.layers[r].edge_begin, p.layers[r].degree};
     for (int e = tid; e < p.nnz; e += kThreads) {
-        edges[e] = make_int2(p.aux[e].col, p.aux[e].shift);
-        col_edges[e] = p.col_edges[e];
+        edges[e] = make_int2(p.aux[e].col * Z, p.aux[e].shift);
+        col_edges[e] = make_int2(p.col_edges[e].x * Z, p.col_edges[e].y);
     }
     for (int c = tid; c <= C; c += kThreads) col_ptr[c] = p.col_ptr[c];
     if (tid < 16) vote[tid] = 0;
@@ -285,16 +290,16 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
             // ---- variable phase: post[v] = llr[v] + sum of the column's messages in ascending block-row order
             for (int item = tid; item < C * ZL; item += kThreads) {
                 const int c = item / ZL, m = lane0 + item - c * ZL;
-                const size_t v = (size_t)c * Z + m;
+                const int v = c * Z + m;
                 PostT sum = (PostT)0;
                 if (it > 0) {
                     const int k0 = col_ptr[c], k1 = col_ptr[c + 1];
 #pragma unroll 4
                     for (int k = k0; k < k1; ++k) {
-                        const int2 ce = col_edges[k];            // edge id, shift
+                        const int2 ce = col_edges[k];            // edge id * Z, shift
                         int l = m - ce.y;
                         if (l < 0) l += Z;
-                        sum += (PostT)c2v[(size_t)ce.x * Z + l];
+                        sum += (PostT)c2v[ce.x + l];
                     }
                 }
                 post[v] = (PostT)llr[v] + sum;
@@ -312,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
                         const int2 e = edges[ly.edge_begin + j];
                         int vl = l + e.y;
                         if (vl >= Z) vl -= Z;
-                        s ^= (unsigned)(post[(size_t)e.x * Z + vl] < (PostT)0);
+                        s ^= (unsigned)(post[e.x + vl] < (PostT)0);
                     }
                     bad |= (int)(s & 1u);
                 }
@@ -327,8 +332,8 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
                 const int r = item / ZL, l = lane0 + item - r * ZL;
                 const int mi = r * Z + l;
                 const int synbit = syn ? (int)((syn[mi >> 5] >> (31 - (mi & 31))) & 1u) : 0;
-                bad |= it == 0 ? check_update<MsgT, PostT, true>(p, rows[r], edges, post, c2v, l, Z, synbit)
-                               : check_update<MsgT, PostT, false>(p, rows[r], edges, post, c2v, l, Z, synbit);
+                bad |= it == 0 ? check_dispatch<MsgT, PostT, FLAVOUR, true>(p, rows[r], edges, post, c2v, l, Z, synbit)
+                               : check_dispatch<MsgT, PostT, FLAVOUR, false>(p, rows[r], edges, post, c2v, l, Z, synbit);
             }
             if (want_check) {
                 ok = !cluster_any(bad);
@@ -344,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
         uint32_t *ab = p.allbits + (size_t)f * p.cw_words;
         for (int item = tid; item < C * ZL; item += kThreads) {
             const int c = item / ZL, m = lane0 + item - c * ZL;
-            const size_t v = (size_t)c * Z + m;
+            const int v = c * Z + m;
             const PostT pv = post[v];
             const unsigned b = __ballot_sync(0xffffffffu, pv < (PostT)0);
             if ((tid & 31) == 0) ab[v >> 5] = __brev(b);
@@ -367,10 +372,9 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
     }
 }
 
-template <typename MsgT, typename PostT, typename InT>
-int launch_t(const FloodQcxParams &p, int n_clusters, int cl, int smem_bytes, cudaStream_t st)
+template <typename K>
+int launch_k(K kern, const FloodQcxParams &p, int n_clusters, int cl, int smem_bytes, cudaStream_t st)
 {
-    auto kern = flooding_qcx_kernel<MsgT, PostT, InT>;
     QLDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(n_clusters * cl));
@@ -388,10 +392,9 @@ int launch_t(const FloodQcxParams &p, int n_clusters, int cl, int smem_bytes, cu
     return QLDPC_OK;
 }
 
-template <typename MsgT, typename PostT, typename InT>
-int max_clusters_t(int cl, int smem_bytes)
+template <typename K>
+int max_clusters_k(K kern, int cl, int smem_bytes)
 {
-    auto kern = flooding_qcx_kernel<MsgT, PostT, InT>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) { cudaGetLastError(); return 0; }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)cl);
@@ -426,19 +429,22 @@ int flooding_qcx_post_bytes(int dtype) { return dtype == QLDPC_DTYPE_I8 ? 2 : 4;
 
 int flooding_qcx_max_clusters(int dtype, int cl, int smem_bytes)
 {
-    switch (dtype) {
-    case QLDPC_DTYPE_F32: return max_clusters_t<float, float, float>(cl, smem_bytes);
-    case QLDPC_DTYPE_I16: return max_clusters_t<int16_t, int, int16_t>(cl, smem_bytes);
-    default: return max_clusters_t<int8_t, int16_t, int8_t>(cl, smem_bytes);
+    switch (dtype) {   // register count and shared memory are the same for all flavours of a type
+    case QLDPC_DTYPE_F32: return max_clusters_k(flooding_qcx_kernel<float, float, float, kSpaExact>, cl, smem_bytes);
+    case QLDPC_DTYPE_I16: return max_clusters_k(flooding_qcx_kernel<int16_t, int, int16_t, kMinSum>, cl, smem_bytes);
+    default: return max_clusters_k(flooding_qcx_kernel<int8_t, int16_t, int8_t, kMinSum>, cl, smem_bytes);
     }
 }
 
 int launch_flooding_qcx(const FloodQcxParams &p, int n_clusters, int cl, int smem_bytes, cudaStream_t st)
 {
     switch (p.dtype) {
-    case QLDPC_DTYPE_F32: return launch_t<float, float, float>(p, n_clusters, cl, smem_bytes, st);
-    case QLDPC_DTYPE_I16: return launch_t<int16_t, int, int16_t>(p, n_clusters, cl, smem_bytes, st);
-    case QLDPC_DTYPE_I8: return launch_t<int8_t, int16_t, int8_t>(p, n_clusters, cl, smem_bytes, st);
+    case QLDPC_DTYPE_F32:
+        if (p.rule != QLDPC_RULE_SPA) return launch_k(flooding_qcx_kernel<float, float, float, kMinSum>, p, n_clusters, cl, smem_bytes, st);
+        if (p.fast_spa) return launch_k(flooding_qcx_kernel<float, float, float, kSpaFast>, p, n_clusters, cl, smem_bytes, st);
+        return launch_k(flooding_qcx_kernel<float, float, float, kSpaExact>, p, n_clusters, cl, smem_bytes, st);
+    case QLDPC_DTYPE_I16: return launch_k(flooding_qcx_kernel<int16_t, int, int16_t, kMinSum>, p, n_clusters, cl, smem_bytes, st);
+    case QLDPC_DTYPE_I8: return launch_k(flooding_qcx_kernel<int8_t, int16_t, int8_t, kMinSum>, p, n_clusters, cl, smem_bytes, st);
     default: return QLDPC_ERR_UNSUPPORTED;
     }
 }

@@ -467,7 +467,7 @@ struct qldpc_decoder_full : qldpc_decoder {
     int gen_grid = 0;
     int flood_block = 0, flood_smem = 0, flood_use_smem = 0;
     // clustered QC flooding kernel (flooding_qcx.cu): blocks per cluster, co-resident clusters, table bytes
-    int qcx_cl = 0, qcx_clusters = 0, qcx_smem = 0;
+    int qcx_cl = 0, qcx_clusters = 0, qcx_smem = 0, qcx_lanes = 0;
 };
 
 static qldpc_decoder_full *full(qldpc_decoder *d) { return static_cast<qldpc_decoder_full *>(d); }
@@ -670,20 +670,25 @@ extern "C" int qldpc_decoder_create(const qldpc_code *code, const qldpc_decoder_
         // Large quasi-cyclic codes (messages do not fit in shared memory, whole warps per circulant): one frame per cluster
         // of CL thread blocks, CL chosen so that the state of all frames in flight stays inside L2.
         if (c.z > 0 && c.z % 32 == 0 && !d->flood_use_smem) {
-            const int smem = flooding_qcx_smem_bytes(c.base_rows, c.base_cols, c.edges / c.z, cfg->dtype);
-            const size_t state = (size_t)c.edges * flooding_qcx_msg_bytes(cfg->dtype) + (size_t)c.n * flooding_qcx_post_bytes(cfg->dtype);
+            const int nnz = c.edges / c.z, zp = flooding_qcx_run_lanes(c.z);
+            const int smem = flooding_qcx_smem_bytes(c.base_rows, c.base_cols, nnz, cfg->dtype);
+            const size_t msg_bytes = (size_t)nnz * zp * flooding_qcx_msg_bytes(cfg->dtype);
+            const size_t post_bytes = (size_t)c.base_cols * zp * flooding_qcx_post_bytes(cfg->dtype);
             const size_t l2_budget = (size_t)prop.l2CacheSize / 2;
+            int max_deg = 0;
+            for (int r = 0; r < c.m; ++r) max_deg = std::max(max_deg, c.row_ptr[r + 1] - c.row_ptr[r]);
+            d->qcx_lanes = flooding_qcx_lanes_per_thread(max_deg);
             for (int cl = 1; cl <= 8 && c.z % (32 * cl) == 0; cl *= 2) {
-                const int n = flooding_qcx_max_clusters(cfg->dtype, cl, smem);
+                const int n = flooding_qcx_max_clusters(cfg->dtype, d->qcx_lanes, cl, smem);
                 if (n < 1) continue;
                 d->qcx_cl = cl; d->qcx_clusters = n; d->qcx_smem = smem;
-                if ((size_t)n * state <= l2_budget) break;
+                if ((size_t)n * (msg_bytes + post_bytes) <= l2_budget) break;
             }
             if (d->qcx_cl > 0) {
                 d->kernel_name = "flooding_qc_cluster";
                 d->flood_qc = false;
-                d->scratch_msg_bytes = (size_t)d->qcx_clusters * c.edges * flooding_qcx_msg_bytes(cfg->dtype);
-                d->scratch_app_bytes = (size_t)d->qcx_clusters * c.n * flooding_qcx_post_bytes(cfg->dtype);
+                d->scratch_msg_bytes = (size_t)d->qcx_clusters * msg_bytes;
+                d->scratch_app_bytes = (size_t)d->qcx_clusters * post_bytes;
             }
         }
     }
@@ -941,7 +946,7 @@ static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint3
             xp.max_iter = cfg.max_iter; xp.early_stop = cfg.early_stop; xp.syndrome_depth = cfg.syndrome_depth;
             xp.rule = cfg.rule; xp.dtype = cfg.dtype; xp.norm = cfg.norm_factor; xp.offset = cfg.offset;
             xp.offset_int = d->offset_int; xp.norm_eighths = d->norm_eighths; xp.vmax = p.vmax;
-            xp.ring_off = flooding_qcx_table_bytes(c.base_rows, c.base_cols, c.edges / c.z);
+            xp.lanes = d->qcx_lanes;
             xp.fast_spa = (cfg.flags & QLDPC_FLAG_FAST_SPA) ? 1 : 0;
             if ((rc = launch_flooding_qcx(xp, std::min(d->qcx_clusters, n_frames), d->qcx_cl, d->qcx_smem, st))) return rc;
         } else if (d->flood_qc) {

@@ -1,21 +1,25 @@
-// Flooding belief propagation for LARGE quasi-cyclic codes (the long QKD blocks of BASELINE config 3: N = 65 536, Z = 2 048):
-// one frame per thread-block CLUSTER, state in an L2-resident scratch, float SPA / min-sum and int8 / int16 min-sum.
+// Flooding belief propagation for LARGE quasi-cyclic codes (the long QKD blocks of BASELINE config 3: N = 65 536, Z = 2 048
+// or 1 024): one frame per thread-block CLUSTER, state in an L2-resident scratch, float SPA / min-sum and int8 / int16 min-sum.
 //
 // Arithmetic: AFF3CT Decoder_LDPC_BP_flooding<B,Q,Update_rule_{SPA,NMS,OMS}> as the reference instantiates it
 // (BOOT/src/main.cpp:193, decode_siho at :365; "main.cpp (5g-qc)":236-251), restated in
 // oracle/qldpc_oracle.c:ora_decode_flooding_f32 / ora_decode_flooding_fixed -- same sweep structure, same order of every
 // sum and product, same early-stop rule as flooding.cu / flooding_qc.cu.  What differs from those kernels:
 //   * a frame is worked on by a cluster of CL thread blocks (CL SMs), each owning Z / CL lanes of every circulant, so only
-//     SMs / CL frames are in flight and their messages + posteriors (1.05 MB per frame) stay resident in the 126 MB L2
-//     (ncu: 94.6 % L2 hit rate): the 16 E bytes per sweep are L2 traffic, HBM sees the channel LLRs.  The
-//     phases are separated by the hardware cluster barrier; the early-termination vote crosses the cluster through
-//     distributed shared memory;
-//   * the circulant tables sit in shared memory; a check issues all its 2 dc loads before the first use;
+//     SMs / CL frames are in flight and their messages + posteriors (1.05 MB per frame) stay resident in the 126 MB L2:
+//     the 16 E bytes per sweep are L2 traffic, HBM sees the channel LLRs.  The phases are separated by the
+//     hardware cluster barrier; the early-termination vote crosses the cluster through distributed shared memory;
+//   * a thread works on V = 4 (row degree <= 8) or 2 CONSECUTIVE lanes of a circulant at a time: its own messages are one
+//     aligned 128-bit (float) / 64-bit / 32-bit access per edge, and the table look-up, the cyclic shift and the address
+//     arithmetic of an edge are paid once per V lanes.  The cyclic shift makes the other operand (the posteriors in the
+//     check phase, the messages in the variable phase) a run of V consecutive lanes that starts anywhere; every run of Z
+//     lanes in the scratch is therefore followed by a copy of its first lanes (stride Z + 4), so that such a run never
+//     wraps: one wrapped start index + V loads at immediate offsets;
+//   * the circulant tables sit in shared memory; a work item issues all its loads before the first use (V (dc + dc) values
+//     in flight per thread);
 //   * the check update is compiled per row degree (no predicated slots), rule and SPA flavour are template parameters;
 //     the first ncu capture of the generic version (profiles/r2_flooding_qcx_v1_ncu_summary.txt) showed the kernel bound
-//     by instruction issue, not by memory: 220 thread instructions per edge and sweep, 10 % of them branch bookkeeping of
-//     predicated slots, FMUL + FADD pairs instead of FFMA (the library is built with --fmad=false; the polynomials below
-//     call fmaf explicitly), 18 % 64-bit index arithmetic;
+//     by instruction issue, not by memory: 220 thread instructions per edge and sweep;
 //   * integer tiers keep their messages in 8 / 16 bits (posteriors in 16 / 32), not in 32-bit words;
 //   * sweep 0 reads no messages at all (they are zero), so the scratch is never cleared.
 #include <cooperative_groups.h>
@@ -29,6 +33,9 @@ namespace qldpc {
 namespace {
 
 constexpr int kThreads = 512;
+constexpr int kPad = 4;              // lanes appended to every run of Z lanes in the scratch (copy of lanes 0 .. 3)
+constexpr int kMaxDcV4 = 8;          // rows up to this degree: 4 lanes per thread (codes whose heaviest row is heavier: 2)
+constexpr int kMaxDcV2 = 20;         // compiled row degrees; heavier rows take the two-pass loop
 
 // ---- SPA kernels of the check update --------------------------------------------------------------------------------
 // Two flavours (template parameter FLAVOUR, QLDPC_FLAG_FAST_SPA):
@@ -72,184 +79,230 @@ __device__ __forceinline__ int norm8(int v, int k)
 }
 
 struct RowMeta { int edge_begin, degree; };
+// the update rule's parameters, by value (a reference to the kernel parameters handed to a non-inlined function would
+// make the compiler copy them to local memory)
+struct Upd { int rule, offset_int, norm_eighths, vmax; float norm, offset; };
 // decoder flavour of a kernel instantiation
 enum { kSpaExact = 0, kSpaFast = 1, kMinSum = 2 };
 
 __device__ __forceinline__ unsigned fbits(float x) { return __float_as_uint(x); }
 
-// ---- one check (block row starting at edge e0, lane l) of exactly DC edges: reads the posteriors of its variables and its
-// old messages, writes the new ones.  FIRST: sweep 0, the old messages are zero and not read.  Returns the parity of the
-// hard decisions (early-stop test).  Offsets are 32-bit (nnz * Z and N are far below 2^31).
-template <typename MsgT, typename PostT, int FLAVOUR, bool FIRST, int DC>
-__device__ __forceinline__ int check_row(const FloodQcxParams &p, int e0, const int2 *edges, const PostT *__restrict__ post,
-                                         MsgT *__restrict__ c2v, int l, int Z, int synbit)
+// V consecutive values, aligned as one vector access
+template <typename T, int V> struct alignas(sizeof(T) * V) Vec { T v[V]; };
+
+// ---- one work item of the check phase: block row starting at edge e0 with exactly DC edges, check lanes l0 .. l0 + V - 1
+// (l0 % V == 0).  Reads the posteriors of their variables and their old messages, writes the new ones.  FIRST: sweep 0, the
+// old messages are zero and not read.  synbits: the V syndrome bits, lane l0 in bit V - 1.  Returns the OR of the
+// hard-decision parities (early-stop test).  Offsets are 32-bit (nnz * (Z + 4) and N are far below 2^31).
+template <typename MsgT, typename PostT, int FLAVOUR, bool FIRST, int DC, int V>
+__device__ __forceinline__ int check_item(const Upd p, int e0, const int2 *edges, const PostT *post, MsgT *c2v, int l0,
+                                          int Z, unsigned synbits)
 {
     constexpr bool kFloat = sizeof(PostT) == 4 && sizeof(MsgT) == 4;
-    MsgT *cm = c2v + (e0 * Z + l);
-    PostT pv[DC];
-    MsgT old[DC];
+    typedef Vec<MsgT, V> MV;
+    const int Zp = Z + kPad;
+    PostT pv[DC][V];
+    MV old[DC];
+    MsgT *cm = c2v + (e0 * Zp + l0);
 #pragma unroll
-    for (int j = 0; j < DC; ++j) {      // all loads first: 2 x DC requests in flight per thread
-        const int2 e = edges[e0 + j];   // (block column * Z, shift)
-        int vl = l + e.y;
+    for (int j = 0; j < DC; ++j) {          // all loads first: (V + 1) x DC requests in flight per thread
+        const int2 e = edges[e0 + j];       // (block column * (Z + 4), shift)
+        int vl = l0 + e.y;
         if (vl >= Z) vl -= Z;
-        pv[j] = post[e.x + vl];
-        old[j] = FIRST ? (MsgT)0 : cm[j * Z];
+        const PostT *pp = post + (e.x + vl);
+#pragma unroll
+        for (int i = 0; i < V; ++i) pv[j][i] = pp[i];
+        if (!FIRST) old[j] = *reinterpret_cast<const MV *>(cm + j * Zp);
     }
-    int hard = synbit;
+    int bad = 0;
+    MV out[DC];
 #pragma unroll
-    for (int j = 0; j < DC; ++j) hard ^= pv[j] < (PostT)0;
-    if constexpr (kFloat) {
-        float x[DC];
-        unsigned sign = (unsigned)synbit << 31;
-        if constexpr (FLAVOUR != kMinSum) {
-            float t[DC];
-            float product = 1.0f;
+    for (int i = 0; i < V; ++i) {
+        const int synbit = (int)((synbits >> (V - 1 - i)) & 1u);
+        int hard = synbit;
 #pragma unroll
-            for (int j = 0; j < DC; ++j) {
-                x[j] = pv[j] - old[j];
-                const float tj = FLAVOUR == kSpaFast ? tanh_half_fast(fabsf(x[j])) : tanh_half_exact(fabsf(x[j]));
-                t[j] = (tj != 0.0f) ? tj : 1e-12f;
-                product *= t[j];
-                sign ^= fbits(x[j]);
-            }
+        for (int j = 0; j < DC; ++j) hard ^= pv[j][i] < (PostT)0;
+        bad |= hard;
+        if constexpr (kFloat) {
+            unsigned sign = (unsigned)synbit << 31;
+            if constexpr (FLAVOUR != kMinSum) {
+                float ts[DC];               // tanh(|x| / 2) with the sign of x
+                float product = 1.0f;
 #pragma unroll
-            for (int j = 0; j < DC; ++j) {
-                float rr = product / t[j];                      // IEEE division, as the oracle
-                rr = (rr < 1.0f) ? rr : 1.0f - 1.1920929e-07f;
-                const float mag = FLAVOUR == kSpaFast ? two_atanh_fast(rr) : two_atanh_exact(rr);
-                cm[j * Z] = __uint_as_float(fbits(mag) ^ ((sign ^ fbits(x[j])) & 0x80000000u));   // mag >= 0
+                for (int j = 0; j < DC; ++j) {
+                    const float x = pv[j][i] - (FIRST ? 0.0f : (float)old[j].v[i]);
+                    const float tj = FLAVOUR == kSpaFast ? tanh_half_fast(fabsf(x)) : tanh_half_exact(fabsf(x));
+                    const float t = (tj != 0.0f) ? tj : 1e-12f;
+                    product *= t;
+                    sign ^= fbits(x);
+                    ts[j] = __uint_as_float(fbits(t) | (fbits(x) & 0x80000000u));
+                }
+#pragma unroll
+                for (int j = 0; j < DC; ++j) {
+                    float rr = product / fabsf(ts[j]);               // IEEE division, as the oracle
+                    rr = (rr < 1.0f) ? rr : 1.0f - 1.1920929e-07f;
+                    const float mag = FLAVOUR == kSpaFast ? two_atanh_fast(rr) : two_atanh_exact(rr);
+                    out[j].v[i] = (MsgT)__uint_as_float(fbits(mag) ^ ((sign ^ fbits(ts[j])) & 0x80000000u));   // mag >= 0
+                }
+            } else {
+                float x[DC];
+                float min1 = 3.402823466e+38f, min2 = 3.402823466e+38f;
+#pragma unroll
+                for (int j = 0; j < DC; ++j) {
+                    x[j] = pv[j][i] - (FIRST ? 0.0f : (float)old[j].v[i]);
+                    const float a = fabsf(x[j]);
+                    sign ^= fbits(x[j]);
+                    min2 = fminf(min2, fmaxf(a, min1));
+                    min1 = fminf(min1, a);
+                }
+                const float cst1 = p.rule == QLDPC_RULE_NMS ? min2 * p.norm : fmaxf(0.0f, min2 - p.offset);
+                const float cst2 = p.rule == QLDPC_RULE_NMS ? min1 * p.norm : fmaxf(0.0f, min1 - p.offset);
+#pragma unroll
+                for (int j = 0; j < DC; ++j) {
+                    const float mag = (fabsf(x[j]) == min1) ? cst1 : cst2;
+                    out[j].v[i] = (MsgT)__uint_as_float(fbits(mag) ^ ((sign ^ fbits(x[j])) & 0x80000000u));
+                }
             }
         } else {
-            float min1 = 3.402823466e+38f, min2 = 3.402823466e+38f;
+            int x[DC];
+            int sign = synbit, min1 = p.vmax, min2 = p.vmax;
 #pragma unroll
             for (int j = 0; j < DC; ++j) {
-                x[j] = pv[j] - old[j];
-                const float a = fabsf(x[j]);
-                sign ^= fbits(x[j]);
-                min2 = fminf(min2, fmaxf(a, min1));
-                min1 = fminf(min1, a);
+                x[j] = min(max((int)pv[j][i] - (FIRST ? 0 : (int)old[j].v[i]), -p.vmax), p.vmax);
+                const int a = abs(x[j]);
+                sign ^= x[j] < 0;
+                min2 = min(min2, max(a, min1));
+                min1 = min(min1, a);
             }
-            const float cst1 = p.rule == QLDPC_RULE_NMS ? min2 * p.norm : fmaxf(0.0f, min2 - p.offset);
-            const float cst2 = p.rule == QLDPC_RULE_NMS ? min1 * p.norm : fmaxf(0.0f, min1 - p.offset);
+            const int cst1 = p.rule == QLDPC_RULE_OMS ? max(min2 - p.offset_int, 0) : norm8(min2, p.norm_eighths);
+            const int cst2 = p.rule == QLDPC_RULE_OMS ? max(min1 - p.offset_int, 0) : norm8(min1, p.norm_eighths);
 #pragma unroll
             for (int j = 0; j < DC; ++j) {
-                const float mag = (fabsf(x[j]) == min1) ? cst1 : cst2;
-                cm[j * Z] = __uint_as_float(fbits(mag) ^ ((sign ^ fbits(x[j])) & 0x80000000u));
+                const int mag = (abs(x[j]) == min1) ? cst1 : cst2;
+                out[j].v[i] = (MsgT)((sign ^ (x[j] < 0)) ? -mag : mag);
             }
-        }
-    } else {
-        int x[DC];
-        int sign = synbit, min1 = p.vmax, min2 = p.vmax;
-#pragma unroll
-        for (int j = 0; j < DC; ++j) {
-            x[j] = min(max((int)pv[j] - (int)old[j], -p.vmax), p.vmax);
-            const int a = abs(x[j]);
-            sign ^= x[j] < 0;
-            min2 = min(min2, max(a, min1));
-            min1 = min(min1, a);
-        }
-        const int cst1 = p.rule == QLDPC_RULE_OMS ? max(min2 - p.offset_int, 0) : norm8(min2, p.norm_eighths);
-        const int cst2 = p.rule == QLDPC_RULE_OMS ? max(min1 - p.offset_int, 0) : norm8(min1, p.norm_eighths);
-#pragma unroll
-        for (int j = 0; j < DC; ++j) {
-            const int mag = (abs(x[j]) == min1) ? cst1 : cst2;
-            cm[j * Z] = (MsgT)((sign ^ (x[j] < 0)) ? -mag : mag);
         }
     }
-    return hard;
+#pragma unroll
+    for (int j = 0; j < DC; ++j) {
+        *reinterpret_cast<MV *>(cm + j * Zp) = out[j];
+        if (l0 < kPad) *reinterpret_cast<MV *>(cm + j * Zp + Z) = out[j];      // the copy of lanes 0 .. 3 behind the run
+    }
+    return bad;
 }
 
 // any degree: two passes over memory (rows heavier than the compiled degrees)
-template <typename MsgT, typename PostT, int FLAVOUR, bool FIRST>
-__device__ __noinline__ int check_row_any(const FloodQcxParams &p, int e0, int deg, const int2 *edges, const PostT *__restrict__ post,
-                                          MsgT *__restrict__ c2v, int l, int Z, int synbit)
+template <typename MsgT, typename PostT, int FLAVOUR, bool FIRST, int V>
+__device__ __noinline__ int check_item_any(const Upd p, int e0, int deg, const int2 *edges, const PostT *post, MsgT *c2v,
+                                           int l0, int Z, unsigned synbits)
 {
     constexpr bool kFloat = sizeof(PostT) == 4 && sizeof(MsgT) == 4;
-    MsgT *cm = c2v + (e0 * Z + l);
-    int sign = synbit, hard = synbit;
-    auto v2c = [&](int j, bool count_hard) {
-        const int2 e = edges[e0 + j];
-        int vl = l + e.y;
-        if (vl >= Z) vl -= Z;
-        const PostT pvj = post[e.x + vl];
-        if (count_hard) hard ^= pvj < (PostT)0;
-        const MsgT o = FIRST ? (MsgT)0 : cm[j * Z];
-        if constexpr (kFloat) return (float)pvj - (float)o;
-        else return (float)min(max((int)pvj - (int)o, -p.vmax), p.vmax);   // integers up to 2^24 are exact in a float
-    };
-    auto th = [&](float a) { return FLAVOUR == kSpaFast ? tanh_half_fast(a) : tanh_half_exact(a); };
-    if (kFloat && FLAVOUR != kMinSum) {
-        float product = 1.0f;
+    const int Zp = Z + kPad;
+    int bad = 0;
+    for (int i = 0; i < V; ++i) {
+        const int l = l0 + i, synbit = (int)((synbits >> (V - 1 - i)) & 1u);
+        MsgT *cm = c2v + (e0 * Zp + l);
+        int sign = synbit, hard = synbit;
+        auto v2c = [&](int j, bool count_hard) {
+            const int2 e = edges[e0 + j];
+            int vl = l + e.y;
+            if (vl >= Z) vl -= Z;
+            const PostT pvj = post[e.x + vl];
+            if (count_hard) hard ^= pvj < (PostT)0;
+            const MsgT o = FIRST ? (MsgT)0 : cm[j * Zp];
+            if constexpr (kFloat) return (float)pvj - (float)o;
+            else return (float)min(max((int)pvj - (int)o, -p.vmax), p.vmax);   // integers up to 2^24 are exact in a float
+        };
+        auto put = [&](int j, MsgT m) {
+            cm[j * Zp] = m;
+            if (l < kPad) cm[j * Zp + Z] = m;
+        };
+        auto th = [&](float a) { return FLAVOUR == kSpaFast ? tanh_half_fast(a) : tanh_half_exact(a); };
+        if (kFloat && FLAVOUR != kMinSum) {
+            float product = 1.0f;
+            for (int j = 0; j < deg; ++j) {
+                const float xv = v2c(j, true);
+                const float tj = th(fabsf(xv));
+                product *= (tj != 0.0f) ? tj : 1e-12f;
+                sign ^= signbit(xv) ? 1 : 0;
+            }
+            bad |= hard;
+            for (int j = 0; j < deg; ++j) {
+                const float xv = v2c(j, false);
+                const float tj = th(fabsf(xv));
+                float rr = product / ((tj != 0.0f) ? tj : 1e-12f);
+                rr = (rr < 1.0f) ? rr : 1.0f - 1.1920929e-07f;
+                const float mag = FLAVOUR == kSpaFast ? two_atanh_fast(rr) : two_atanh_exact(rr);
+                put(j, (MsgT)((sign ^ (signbit(xv) ? 1 : 0)) ? -mag : mag));
+            }
+            continue;
+        }
+        float min1 = kFloat ? 3.402823466e+38f : (float)p.vmax, min2 = min1;
         for (int j = 0; j < deg; ++j) {
             const float xv = v2c(j, true);
-            const float tj = th(fabsf(xv));
-            product *= (tj != 0.0f) ? tj : 1e-12f;
+            const float a = fabsf(xv);
             sign ^= signbit(xv) ? 1 : 0;
+            min2 = fminf(min2, fmaxf(a, min1));
+            min1 = fminf(min1, a);
         }
-        const int hard1 = hard;
+        bad |= hard;
+        float cst1, cst2;
+        if constexpr (kFloat) {
+            cst1 = p.rule == QLDPC_RULE_NMS ? min2 * p.norm : fmaxf(0.0f, min2 - p.offset);
+            cst2 = p.rule == QLDPC_RULE_NMS ? min1 * p.norm : fmaxf(0.0f, min1 - p.offset);
+        } else {
+            cst1 = (float)(p.rule == QLDPC_RULE_OMS ? max((int)min2 - p.offset_int, 0) : norm8((int)min2, p.norm_eighths));
+            cst2 = (float)(p.rule == QLDPC_RULE_OMS ? max((int)min1 - p.offset_int, 0) : norm8((int)min1, p.norm_eighths));
+        }
         for (int j = 0; j < deg; ++j) {
             const float xv = v2c(j, false);
-            const float tj = th(fabsf(xv));
-            float rr = product / ((tj != 0.0f) ? tj : 1e-12f);
-            rr = (rr < 1.0f) ? rr : 1.0f - 1.1920929e-07f;
-            const float mag = FLAVOUR == kSpaFast ? two_atanh_fast(rr) : two_atanh_exact(rr);
-            cm[j * Z] = (MsgT)((sign ^ (signbit(xv) ? 1 : 0)) ? -mag : mag);
+            const float mag = (fabsf(xv) == min1) ? cst1 : cst2;
+            const float o = (sign ^ (signbit(xv) ? 1 : 0)) ? -mag : mag;
+            if constexpr (kFloat) put(j, o);
+            else put(j, (MsgT)(int)o);
         }
-        return hard1;
     }
-    float min1 = kFloat ? 3.402823466e+38f : (float)p.vmax, min2 = min1;
-    for (int j = 0; j < deg; ++j) {
-        const float xv = v2c(j, true);
-        const float a = fabsf(xv);
-        sign ^= signbit(xv) ? 1 : 0;
-        min2 = fminf(min2, fmaxf(a, min1));
-        min1 = fminf(min1, a);
-    }
-    const int hard1 = hard;
-    float cst1, cst2;
-    if constexpr (kFloat) {
-        cst1 = p.rule == QLDPC_RULE_NMS ? min2 * p.norm : fmaxf(0.0f, min2 - p.offset);
-        cst2 = p.rule == QLDPC_RULE_NMS ? min1 * p.norm : fmaxf(0.0f, min1 - p.offset);
-    } else {
-        cst1 = (float)(p.rule == QLDPC_RULE_OMS ? max((int)min2 - p.offset_int, 0) : norm8((int)min2, p.norm_eighths));
-        cst2 = (float)(p.rule == QLDPC_RULE_OMS ? max((int)min1 - p.offset_int, 0) : norm8((int)min1, p.norm_eighths));
-    }
-    for (int j = 0; j < deg; ++j) {
-        const float xv = v2c(j, false);
-        const float mag = (fabsf(xv) == min1) ? cst1 : cst2;
-        const float out = (sign ^ (signbit(xv) ? 1 : 0)) ? -mag : mag;
-        if constexpr (kFloat) cm[j * Z] = out;
-        else cm[j * Z] = (MsgT)(int)out;
-    }
-    return hard1;
+    return bad;
 }
 
-// the row's degree is the same for all threads of the block (block-uniform switch, no divergence)
-template <typename MsgT, typename PostT, int FLAVOUR, bool FIRST>
-__device__ __forceinline__ int check_dispatch(const FloodQcxParams &p, const RowMeta ly, const int2 *edges, const PostT *__restrict__ post,
-                                              MsgT *__restrict__ c2v, int l, int Z, int synbit)
+// the row's degree is the same for all threads of a warp when Z / CL is a multiple of 32 V (no divergence)
+template <typename MsgT, typename PostT, int FLAVOUR, bool FIRST, int V>
+__device__ __forceinline__ int check_dispatch(const Upd p, const RowMeta ly, const int2 *edges, const PostT *post, MsgT *c2v,
+                                              int l0, int Z, unsigned synbits)
 {
-#define QL_DC(D) case D: return check_row<MsgT, PostT, FLAVOUR, FIRST, D>(p, ly.edge_begin, edges, post, c2v, l, Z, synbit);
-    switch (ly.degree) {
-        QL_DC(2) QL_DC(3) QL_DC(4) QL_DC(5) QL_DC(6) QL_DC(7) QL_DC(8) QL_DC(9) QL_DC(10)
-        QL_DC(11) QL_DC(12) QL_DC(13) QL_DC(14) QL_DC(15) QL_DC(16) QL_DC(17) QL_DC(18)
-    default: return check_row_any<MsgT, PostT, FLAVOUR, FIRST>(p, ly.edge_begin, ly.degree, edges, post, c2v, l, Z, synbit);
+#define QL_DC(D) case D: return check_item<MsgT, PostT, FLAVOUR, FIRST, D, V>(p, ly.edge_begin, edges, post, c2v, l0, Z, synbits);
+    if constexpr (V == 4) {
+        switch (ly.degree) {
+            QL_DC(2) QL_DC(3) QL_DC(4) QL_DC(5) QL_DC(6) QL_DC(7) QL_DC(8)
+        default: break;
+        }
+    } else {
+        switch (ly.degree) {
+            QL_DC(2) QL_DC(3) QL_DC(4) QL_DC(5) QL_DC(6) QL_DC(7) QL_DC(8) QL_DC(9) QL_DC(10)
+            QL_DC(11) QL_DC(12) QL_DC(13) QL_DC(14) QL_DC(15) QL_DC(16) QL_DC(17) QL_DC(18) QL_DC(19) QL_DC(20)
+        default: break;
+        }
     }
 #undef QL_DC
+    return check_item_any<MsgT, PostT, FLAVOUR, FIRST, V>(p, ly.edge_begin, ly.degree, edges, post, c2v, l0, Z, synbits);
 }
 
-// Shared-memory layout: RowMeta rows[R]; int2 edges[nnz] (block column * Z, shift); int col_ptr[C + 1]; int2 col_edges[nnz]
-// (edge id * Z, shift); int vote[2][8].
-template <typename MsgT, typename PostT, typename InT, int FLAVOUR>
+// Shared-memory layout: RowMeta rows[R]; int2 edges[nnz] (block column * (Z + 4), shift); int col_ptr[C + 1]; int2 col_edges[nnz]
+// (edge id * (Z + 4), shift); int vote[2][8].
+// Scratch layout (per cluster): messages c2v[edge][Z + 4] indexed by CHECK lane, posteriors post[block column][Z + 4]; the
+// four lanes behind a run repeat its first four.
+template <typename MsgT, typename PostT, typename InT, int FLAVOUR, int V>
 __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQcxParams p)
 {
     extern __shared__ __align__(16) char smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int CL = (int)cluster.num_blocks(), q = (int)cluster.block_rank();
     const int cid = blockIdx.x / CL, n_clusters = gridDim.x / CL;
-    const int tid = threadIdx.x, Z = p.Z, ZL = Z / CL, lane0 = q * ZL;
+    const int tid = threadIdx.x, Z = p.Z, Zp = Z + kPad, ZL = Z / CL, lane0 = q * ZL, QL = ZL / V;
     const int R = p.brows, C = p.bcols;
+    typedef Vec<MsgT, V> MV;
+    typedef Vec<PostT, V> PV;
+    typedef Vec<InT, V> IV;
 
     RowMeta *rows = reinterpret_cast<RowMeta *>(smem);
     int2 *edges = reinterpret_cast<int2 *>(rows + R);
@@ -258,16 +311,17 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
     int *vote = reinterpret_cast<int *>(col_edges + p.nnz);
     for (int r = tid; r < R; r += kThreads) rows[r] = RowMeta{p.layers[r].edge_begin, p.layers[r].degree};
     for (int e = tid; e < p.nnz; e += kThreads) {
-        edges[e] = make_int2(p.aux[e].col * Z, p.aux[e].shift);
-        col_edges[e] = make_int2(p.col_edges[e].x * Z, p.col_edges[e].y);
+        edges[e] = make_int2(p.aux[e].col * Zp, p.aux[e].shift);
+        col_edges[e] = make_int2(p.col_edges[e].x * Zp, p.col_edges[e].y);
     }
     for (int c = tid; c <= C; c += kThreads) col_ptr[c] = p.col_ptr[c];
     if (tid < 16) vote[tid] = 0;
     cluster.sync();
 
-    MsgT *c2v = reinterpret_cast<MsgT *>(p.c2v) + (size_t)cid * p.nnz * Z;
-    PostT *post = reinterpret_cast<PostT *>(p.post) + (size_t)cid * p.N;
+    MsgT *c2v = reinterpret_cast<MsgT *>(p.c2v) + (size_t)cid * p.nnz * Zp;
+    PostT *post = reinterpret_cast<PostT *>(p.post) + (size_t)cid * C * Zp;
     unsigned vpar = 0;
+    const Upd upd{p.rule, p.offset_int, p.norm_eighths, p.vmax, p.norm, p.offset};
 
     // cluster-wide OR of a per-thread flag: block vote, then every block writes its result into every block's table
     auto cluster_any = [&](int flag) {
@@ -280,6 +334,12 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
         vpar ^= 1u;
         return any != 0;
     };
+    // the V syndrome bits of check lanes l0 .. l0 + V - 1 of block row r (one word: V divides 32, l0 % V == 0), lane l0 highest
+    auto syn_of = [&](const uint32_t *syn, int r, int l0) {
+        if (!syn) return 0u;
+        const int mi = r * Z + l0;
+        return (syn[mi >> 5] >> (32 - V - (mi & 31))) & ((1u << V) - 1u);
+    };
 
     for (int f = cid; f < p.F; f += n_clusters) {
         const InT *llr = reinterpret_cast<const InT *>(p.llr) + (size_t)f * p.N;
@@ -288,38 +348,59 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
         bool ok = false;
         for (;;) {
             // ---- variable phase: post[v] = llr[v] + sum of the column's messages in ascending block-row order
-            for (int item = tid; item < C * ZL; item += kThreads) {
-                const int c = item / ZL, m = lane0 + item - c * ZL;
-                const int v = c * Z + m;
-                PostT sum = (PostT)0;
+            for (int item = tid; item < C * QL; item += kThreads) {     // (block column, V consecutive variable lanes)
+                const int c = item / QL, m0 = lane0 + (item - c * QL) * V;
+                const IV y = *reinterpret_cast<const IV *>(llr + (c * Z + m0));
+                PostT sum[V];
+#pragma unroll
+                for (int i = 0; i < V; ++i) sum[i] = (PostT)0;
                 if (it > 0) {
-                    const int k0 = col_ptr[c], k1 = col_ptr[c + 1];
-#pragma unroll 4
-                    for (int k = k0; k < k1; ++k) {
-                        const int2 ce = col_edges[k];            // edge id * Z, shift
-                        int l = m - ce.y;
-                        if (l < 0) l += Z;
-                        sum += (PostT)c2v[ce.x + l];
+                    const int ka = col_ptr[c], kb = col_ptr[c + 1];
+                    constexpr int kDv = 4;              // edges of the column in flight at a time
+                    for (int k = ka; k < kb; k += kDv) {
+                        MsgT m[kDv][V];
+#pragma unroll
+                        for (int u = 0; u < kDv; ++u) {
+                            if (k + u < kb) {
+                                const int2 ce = col_edges[k + u];            // edge id * (Z + 4), shift
+                                int l = m0 - ce.y;
+                                if (l < 0) l += Z;
+                                const MsgT *mp = c2v + (ce.x + l);
+#pragma unroll
+                                for (int i = 0; i < V; ++i) m[u][i] = mp[i];
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < kDv; ++u) {      // ascending block-row order
+                            if (k + u < kb) {
+#pragma unroll
+                                for (int i = 0; i < V; ++i) sum[i] += (PostT)m[u][i];
+                            }
+                        }
                     }
                 }
-                post[v] = (PostT)llr[v] + sum;
+                PV o;
+#pragma unroll
+                for (int i = 0; i < V; ++i) o.v[i] = (PostT)y.v[i] + sum[i];
+                *reinterpret_cast<PV *>(post + (c * Zp + m0)) = o;
+                if (m0 < kPad) *reinterpret_cast<PV *>(post + (c * Zp + Z + m0)) = o;
             }
             cluster.sync();
             const bool last = it >= p.max_iter;
             if (last) {   // final verdict after the last sweep: syndrome of the hard decisions, no update
                 int bad = 0;
-                for (int item = tid; item < R * ZL; item += kThreads) {
-                    const int r = item / ZL, l = lane0 + item - r * ZL;
-                    const int mi = r * Z + l;
-                    unsigned s = syn ? (syn[mi >> 5] >> (31 - (mi & 31))) & 1u : 0u;
+                for (int item = tid; item < R * QL; item += kThreads) {
+                    const int r = item / QL, l0 = lane0 + (item - r * QL) * V;
+                    unsigned s = syn_of(syn, r, l0);
                     const RowMeta ly = rows[r];
                     for (int j = 0; j < ly.degree; ++j) {
                         const int2 e = edges[ly.edge_begin + j];
-                        int vl = l + e.y;
+                        int vl = l0 + e.y;
                         if (vl >= Z) vl -= Z;
-                        s ^= (unsigned)(post[e.x + vl] < (PostT)0);
+#pragma unroll
+                        for (int i = 0; i < V; ++i) s ^= (unsigned)(post[e.x + vl + i] < (PostT)0) << (V - 1 - i);
                     }
-                    bad |= (int)(s & 1u);
+                    bad |= (int)s;
                 }
                 ok = !cluster_any(bad);
                 break;
@@ -328,12 +409,11 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
             // If it passes the decoder stops here: the messages just written are never used, `it` is not advanced.
             const bool want_check = p.early_stop && it > 0;
             int bad = 0;
-            for (int item = tid; item < R * ZL; item += kThreads) {
-                const int r = item / ZL, l = lane0 + item - r * ZL;
-                const int mi = r * Z + l;
-                const int synbit = syn ? (int)((syn[mi >> 5] >> (31 - (mi & 31))) & 1u) : 0;
-                bad |= it == 0 ? check_dispatch<MsgT, PostT, FLAVOUR, true>(p, rows[r], edges, post, c2v, l, Z, synbit)
-                               : check_dispatch<MsgT, PostT, FLAVOUR, false>(p, rows[r], edges, post, c2v, l, Z, synbit);
+            for (int item = tid; item < R * QL; item += kThreads) {     // (block row, V consecutive check lanes)
+                const int r = item / QL, l0 = lane0 + (item - r * QL) * V;
+                const unsigned sb = syn_of(syn, r, l0);
+                bad |= it == 0 ? check_dispatch<MsgT, PostT, FLAVOUR, true, V>(upd, rows[r], edges, post, c2v, l0, Z, sb)
+                               : check_dispatch<MsgT, PostT, FLAVOUR, false, V>(upd, rows[r], edges, post, c2v, l0, Z, sb);
             }
             if (want_check) {
                 ok = !cluster_any(bad);
@@ -350,7 +430,7 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
         for (int item = tid; item < C * ZL; item += kThreads) {
             const int c = item / ZL, m = lane0 + item - c * ZL;
             const int v = c * Z + m;
-            const PostT pv = post[v];
+            const PostT pv = post[c * Zp + m];
             const unsigned b = __ballot_sync(0xffffffffu, pv < (PostT)0);
             if ((tid & 31) == 0) ab[v >> 5] = __brev(b);
             if (p.posterior) {
@@ -426,27 +506,32 @@ int flooding_qcx_smem_bytes(int brows, int bcols, int nnz, int dtype)
 
 int flooding_qcx_msg_bytes(int dtype) { return dtype == QLDPC_DTYPE_F32 ? 4 : (dtype == QLDPC_DTYPE_I16 ? 2 : 1); }
 int flooding_qcx_post_bytes(int dtype) { return dtype == QLDPC_DTYPE_I8 ? 2 : 4; }
+int flooding_qcx_run_lanes(int Z) { return Z + kPad; }
+int flooding_qcx_lanes_per_thread(int max_row_degree) { return max_row_degree <= kMaxDcV4 ? 4 : 2; }
 
-int flooding_qcx_max_clusters(int dtype, int cl, int smem_bytes)
+#define QL_QCX_KERNELS(X, V)                                                                  \
+    X(QLDPC_DTYPE_F32, kSpaExact, (flooding_qcx_kernel<float, float, float, kSpaExact, V>))   \
+    X(QLDPC_DTYPE_F32, kSpaFast, (flooding_qcx_kernel<float, float, float, kSpaFast, V>))     \
+    X(QLDPC_DTYPE_F32, kMinSum, (flooding_qcx_kernel<float, float, float, kMinSum, V>))       \
+    X(QLDPC_DTYPE_I16, kMinSum, (flooding_qcx_kernel<int16_t, int, int16_t, kMinSum, V>))     \
+    X(QLDPC_DTYPE_I8, kMinSum, (flooding_qcx_kernel<int8_t, int16_t, int8_t, kMinSum, V>))
+
+int flooding_qcx_max_clusters(int dtype, int lanes, int cl, int smem_bytes)
 {
-    switch (dtype) {   // register count and shared memory are the same for all flavours of a type
-    case QLDPC_DTYPE_F32: return max_clusters_k(flooding_qcx_kernel<float, float, float, kSpaExact>, cl, smem_bytes);
-    case QLDPC_DTYPE_I16: return max_clusters_k(flooding_qcx_kernel<int16_t, int, int16_t, kMinSum>, cl, smem_bytes);
-    default: return max_clusters_k(flooding_qcx_kernel<int8_t, int16_t, int8_t, kMinSum>, cl, smem_bytes);
-    }
+    // register count and shared memory are the same for all flavours of a type: ask for the min-sum one
+#define QL_X(DT, FL, K) if (dtype == DT && FL == kMinSum) return max_clusters_k(K, cl, smem_bytes);
+    if (lanes == 4) { QL_QCX_KERNELS(QL_X, 4) } else { QL_QCX_KERNELS(QL_X, 2) }
+#undef QL_X
+    return 0;
 }
 
 int launch_flooding_qcx(const FloodQcxParams &p, int n_clusters, int cl, int smem_bytes, cudaStream_t st)
 {
-    switch (p.dtype) {
-    case QLDPC_DTYPE_F32:
-        if (p.rule != QLDPC_RULE_SPA) return launch_k(flooding_qcx_kernel<float, float, float, kMinSum>, p, n_clusters, cl, smem_bytes, st);
-        if (p.fast_spa) return launch_k(flooding_qcx_kernel<float, float, float, kSpaFast>, p, n_clusters, cl, smem_bytes, st);
-        return launch_k(flooding_qcx_kernel<float, float, float, kSpaExact>, p, n_clusters, cl, smem_bytes, st);
-    case QLDPC_DTYPE_I16: return launch_k(flooding_qcx_kernel<int16_t, int, int16_t, kMinSum>, p, n_clusters, cl, smem_bytes, st);
-    case QLDPC_DTYPE_I8: return launch_k(flooding_qcx_kernel<int8_t, int16_t, int8_t, kMinSum>, p, n_clusters, cl, smem_bytes, st);
-    default: return QLDPC_ERR_UNSUPPORTED;
-    }
+    const int flavour = (p.dtype == QLDPC_DTYPE_F32 && p.rule == QLDPC_RULE_SPA) ? (p.fast_spa ? kSpaFast : kSpaExact) : kMinSum;
+#define QL_X(DT, FL, K) if (p.dtype == DT && flavour == FL) return launch_k(K, p, n_clusters, cl, smem_bytes, st);
+    if (p.lanes == 4) { QL_QCX_KERNELS(QL_X, 4) } else { QL_QCX_KERNELS(QL_X, 2) }
+#undef QL_X
+    return QLDPC_ERR_UNSUPPORTED;
 }
 
 }  // namespace qldpc

@@ -182,22 +182,24 @@ struct FloodQcxParams {
     const QcLayer *layers;
     const int32_t *col_ptr;
     const int2 *col_edges;
-    void *c2v;                 // n_clusters * nnz * Z messages (float / int16 / int8), L2-resident scratch
-    void *post;                // n_clusters * N posteriors (float / int32 / int16)
+    void *c2v;                 // n_clusters * nnz * (Z + 4) messages (float / int16 / int8), L2-resident scratch
+    void *post;                // n_clusters * bcols * (Z + 4) posteriors (float / int32 / int16)
     int F, Z, nnz, N, M, brows, bcols;
     int cw_words, syn_words;
     int max_iter, early_stop, syndrome_depth;
     int rule, dtype;
     float norm, offset;
     int offset_int, norm_eighths, vmax;
-    int ring_off;              // float tiers: byte offset of the cp.async ring in dynamic shared memory (= table bytes)
+    int lanes;                 // consecutive circulant lanes per thread: 4 (heaviest row <= 8 edges) or 2
     int fast_spa;              // SPA transcendentals in fp32 on the SFUs instead of double (QLDPC_FLAG_FAST_SPA)
 };
 int flooding_qcx_table_bytes(int brows, int bcols, int nnz);
 int flooding_qcx_smem_bytes(int brows, int bcols, int nnz, int dtype);
 int flooding_qcx_msg_bytes(int dtype);
 int flooding_qcx_post_bytes(int dtype);
-int flooding_qcx_max_clusters(int dtype, int cl, int smem_bytes);   // co-resident clusters of `cl` blocks on the current device
+int flooding_qcx_run_lanes(int Z);                    // stride of a run of Z lanes in the scratch (Z + copy of the first lanes)
+int flooding_qcx_lanes_per_thread(int max_row_degree);
+int flooding_qcx_max_clusters(int dtype, int lanes, int cl, int smem_bytes);   // co-resident clusters of `cl` blocks on the current device
 int launch_flooding_qcx(const FloodQcxParams &p, int n_clusters, int cl, int smem_bytes, cudaStream_t st);
 
 // ---- bit-level helpers ---------------------------------------------------------------------------

@@ -678,11 +678,12 @@ extern "C" int qldpc_decoder_create(const qldpc_code *code, const qldpc_decoder_
             int max_deg = 0;
             for (int r = 0; r < c.m; ++r) max_deg = std::max(max_deg, c.row_ptr[r + 1] - c.row_ptr[r]);
             d->qcx_lanes = flooding_qcx_lanes_per_thread(max_deg);
-            for (int cl = 1; cl <= 8 && c.z % (32 * cl) == 0; cl *= 2) {
+            const char *force_cl = getenv("QLDPC_QCX_CL");   // EXPERIMENT
+            for (int cl = force_cl ? atoi(force_cl) : 1; cl <= 8 && c.z % (32 * cl) == 0; cl *= 2) {
                 const int n = flooding_qcx_max_clusters(cfg->dtype, d->qcx_lanes, cl, smem);
                 if (n < 1) continue;
                 d->qcx_cl = cl; d->qcx_clusters = n; d->qcx_smem = smem;
-                if ((size_t)n * (msg_bytes + post_bytes) <= l2_budget) break;
+                if (force_cl || (size_t)n * (msg_bytes + post_bytes) <= l2_budget) break;
             }
             if (d->qcx_cl > 0) {
                 d->kernel_name = "flooding_qc_cluster";

@@ -47,21 +47,41 @@ constexpr int kMaxDcV2 = 20;         // compiled row degrees; heavier rows take 
 //     batch; 99.99 % of the posteriors are within 1e-3, the rest (saturated messages) within ln 2.
 __device__ __noinline__ float tanh_half_exact(float a) { return (float)tanh((double)(a * 0.5f)); }
 __device__ __noinline__ float two_atanh_exact(float r) { return 2.0f * (float)atanh((double)r); }
-// tanh(a / 2) for a >= 0: 1 - 2 / (e^a + 1) (exact to the last bit near 1, where atanh is ill-conditioned), odd series below 0.25
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x)
+{
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// tanh(a / 2) for a >= 0: 1 - 2 / (e^a + 1) (exact to the last bit near 1, where atanh is ill-conditioned); below 1/16 the
+// difference cancels and the odd series h - h^3 / 3 (next term 2 h^5 / 15 < 1.3e-7 h) takes over.  Five instructions, two
+// of them on the special-function unit; relative error < 2e-5 everywhere.
 __device__ __forceinline__ float tanh_half_fast(float a)
 {
-    const float h = 0.5f * a, h2 = h * h;
-    const float series = h * fmaf(h2, fmaf(h2, fmaf(h2, -0.05396825f, 0.13333334f), -0.33333334f), 1.0f);
-    const float u = __fdividef(2.0f, __expf(a) + 1.0f);      // e^a = +inf for a > 88 -> u = 0
-    return a < 0.25f ? series : 1.0f - u;
+    const float h = 0.5f * a;
+    const float series = h * fmaf(h * h, -0.33333334f, 1.0f);
+    const float e = ex2_approx(a * 1.4426950408889634f);      // +inf for a > 88 -> t = 1
+    const float t = fmaf(rcp_approx(e + 1.0f), -2.0f, 1.0f);
+    return a < 0.0625f ? series : t;
 }
-// 2 * atanh(r) for 0 <= r < 1: ln((1 + r) / (1 - r)), series below 0.25
+// 2 * atanh(r) for 0 <= r < 1: ln(1 + r) - ln(1 - r) (1 - r is exact), series 2 r (1 + r^2 / 3) below 1/16
 __device__ __forceinline__ float two_atanh_fast(float r)
 {
-    const float r2 = r * r;
-    const float series = (r + r) * fmaf(r2, fmaf(r2, fmaf(r2, fmaf(r2, 0.11111111f, 0.14285715f), 0.2f), 0.33333334f), 1.0f);
-    const float lg = __logf(__fdividef(1.0f + r, 1.0f - r));
-    return r < 0.25f ? series : lg;
+    const float series = (r + r) * fmaf(r * r, 0.33333334f, 1.0f);
+    const float lg = 0.6931471805599453f * (lg2_approx(1.0f + r) - lg2_approx(1.0f - r));
+    return r < 0.0625f ? series : lg;
 }
 
 __device__ __forceinline__ int norm8(int v, int k)
@@ -120,8 +140,15 @@ __device__ __forceinline__ int check_item(const Upd p, int e0, const int2 *edges
     for (int i = 0; i < V; ++i) {
         const int synbit = (int)((synbits >> (V - 1 - i)) & 1u);
         int hard = synbit;
+        if constexpr (kFloat) {   // the variable phase never writes -0 (y + (+0 + m ...)): the sign bit is the hard decision
+            unsigned hs = 0;
 #pragma unroll
-        for (int j = 0; j < DC; ++j) hard ^= pv[j][i] < (PostT)0;
+            for (int j = 0; j < DC; ++j) hs ^= fbits((float)pv[j][i]);
+            hard ^= (int)(hs >> 31);
+        } else {
+#pragma unroll
+            for (int j = 0; j < DC; ++j) hard ^= pv[j][i] < (PostT)0;
+        }
         bad |= hard;
         if constexpr (kFloat) {
             unsigned sign = (unsigned)synbit << 31;
@@ -300,6 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
     const int cid = blockIdx.x / CL, n_clusters = gridDim.x / CL;
     const int tid = threadIdx.x, Z = p.Z, Zp = Z + kPad, ZL = Z / CL, lane0 = q * ZL, QL = ZL / V;
     const int R = p.brows, C = p.bcols;
+    const int step_r = kThreads / QL, step_q = kThreads - step_r * QL;   // a thread's next work item: kThreads items further
     typedef Vec<MsgT, V> MV;
     typedef Vec<PostT, V> PV;
     typedef Vec<InT, V> IV;
@@ -347,50 +375,76 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
         int it = 0, depth = 0;
         bool ok = false;
         for (;;) {
-            // ---- variable phase: post[v] = llr[v] + sum of the column's messages in ascending block-row order
-            for (int item = tid; item < C * QL; item += kThreads) {     // (block column, V consecutive variable lanes)
-                const int c = item / QL, m0 = lane0 + (item - c * QL) * V;
-                const IV y = *reinterpret_cast<const IV *>(llr + (c * Z + m0));
-                PostT sum[V];
+            // ---- variable phase: post[v] = llr[v] + sum of the column's messages in ascending block-row order.
+            // A work item is V consecutive variable lanes of kCols block columns side by side: a column of weight 3 alone
+            // keeps only 3 V loads in flight per thread and the phase waits on L2 latency.
+            {
+                constexpr int kCols = 4, kDv = V == 4 ? 3 : 4;   // columns per item, edges of each column in flight at a time
+                const int n_groups = (C + kCols - 1) / kCols;
+                int cgp = tid / QL, qd = tid - cgp * QL;
+                for (; cgp < n_groups; qd += step_q, cgp += step_r + (qd >= QL ? 1 : 0), qd -= (qd >= QL ? QL : 0)) {
+                    const int m0 = lane0 + qd * V;
+                    IV y[kCols];
+                    PostT sum[kCols][V];
+                    int ka[kCols], kn[kCols], kmax = 0;
 #pragma unroll
-                for (int i = 0; i < V; ++i) sum[i] = (PostT)0;
-                if (it > 0) {
-                    const int ka = col_ptr[c], kb = col_ptr[c + 1];
-                    constexpr int kDv = 4;              // edges of the column in flight at a time
-                    for (int k = ka; k < kb; k += kDv) {
-                        MsgT m[kDv][V];
+                    for (int u = 0; u < kCols; ++u) {
+                        const int c = cgp * kCols + u;
+                        const bool valid = c < C;
+                        ka[u] = valid ? col_ptr[c] : 0;
+                        kn[u] = (valid && it > 0) ? col_ptr[c + 1] - ka[u] : 0;
+                        kmax = max(kmax, kn[u]);
+                        if (valid) y[u] = *reinterpret_cast<const IV *>(llr + (c * Z + m0));
 #pragma unroll
-                        for (int u = 0; u < kDv; ++u) {
-                            if (k + u < kb) {
-                                const int2 ce = col_edges[k + u];            // edge id * (Z + 4), shift
-                                int l = m0 - ce.y;
-                                if (l < 0) l += Z;
-                                const MsgT *mp = c2v + (ce.x + l);
+                        for (int i = 0; i < V; ++i) sum[u][i] = (PostT)0;
+                    }
+                    for (int k = 0; k < kmax; k += kDv) {
+                        MsgT m[kCols][kDv][V];
 #pragma unroll
-                                for (int i = 0; i < V; ++i) m[u][i] = mp[i];
+                        for (int u = 0; u < kCols; ++u) {
+#pragma unroll
+                            for (int d = 0; d < kDv; ++d) {
+                                if (k + d < kn[u]) {
+                                    const int2 ce = col_edges[ka[u] + k + d];            // edge id * (Z + 4), shift
+                                    int l = m0 - ce.y;
+                                    if (l < 0) l += Z;
+                                    const MsgT *mp = c2v + (ce.x + l);
+#pragma unroll
+                                    for (int i = 0; i < V; ++i) m[u][d][i] = mp[i];
+                                }
                             }
                         }
 #pragma unroll
-                        for (int u = 0; u < kDv; ++u) {      // ascending block-row order
-                            if (k + u < kb) {
+                        for (int u = 0; u < kCols; ++u) {
 #pragma unroll
-                                for (int i = 0; i < V; ++i) sum[i] += (PostT)m[u][i];
+                            for (int d = 0; d < kDv; ++d) {      // ascending block-row order
+                                if (k + d < kn[u]) {
+#pragma unroll
+                                    for (int i = 0; i < V; ++i) sum[u][i] += (PostT)m[u][d][i];
+                                }
                             }
                         }
                     }
-                }
-                PV o;
 #pragma unroll
-                for (int i = 0; i < V; ++i) o.v[i] = (PostT)y.v[i] + sum[i];
-                *reinterpret_cast<PV *>(post + (c * Zp + m0)) = o;
-                if (m0 < kPad) *reinterpret_cast<PV *>(post + (c * Zp + Z + m0)) = o;
+                    for (int u = 0; u < kCols; ++u) {
+                        const int c = cgp * kCols + u;
+                        if (c < C) {
+                            PV o;
+#pragma unroll
+                            for (int i = 0; i < V; ++i) o.v[i] = (PostT)y[u].v[i] + sum[u][i];
+                            *reinterpret_cast<PV *>(post + (c * Zp + m0)) = o;
+                            if (m0 < kPad) *reinterpret_cast<PV *>(post + (c * Zp + Z + m0)) = o;
+                        }
+                    }
+                }
             }
             cluster.sync();
             const bool last = it >= p.max_iter;
             if (last) {   // final verdict after the last sweep: syndrome of the hard decisions, no update
                 int bad = 0;
-                for (int item = tid; item < R * QL; item += kThreads) {
-                    const int r = item / QL, l0 = lane0 + (item - r * QL) * V;
+                int r = tid / QL, qd = tid - r * QL;
+                for (; r < R; qd += step_q, r += step_r + (qd >= QL ? 1 : 0), qd -= (qd >= QL ? QL : 0)) {
+                    const int l0 = lane0 + qd * V;
                     unsigned s = syn_of(syn, r, l0);
                     const RowMeta ly = rows[r];
                     for (int j = 0; j < ly.degree; ++j) {
@@ -409,8 +463,9 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
             // If it passes the decoder stops here: the messages just written are never used, `it` is not advanced.
             const bool want_check = p.early_stop && it > 0;
             int bad = 0;
-            for (int item = tid; item < R * QL; item += kThreads) {     // (block row, V consecutive check lanes)
-                const int r = item / QL, l0 = lane0 + (item - r * QL) * V;
+            int r = tid / QL, qd = tid - r * QL;                        // work item: (block row, V consecutive check lanes)
+            for (; r < R; qd += step_q, r += step_r + (qd >= QL ? 1 : 0), qd -= (qd >= QL ? QL : 0)) {
+                const int l0 = lane0 + qd * V;
                 const unsigned sb = syn_of(syn, r, l0);
                 bad |= it == 0 ? check_dispatch<MsgT, PostT, FLAVOUR, true, V>(upd, rows[r], edges, post, c2v, l0, Z, sb)
                                : check_dispatch<MsgT, PostT, FLAVOUR, false, V>(upd, rows[r], edges, post, c2v, l0, Z, sb);
@@ -425,17 +480,31 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
             ++it;
         }
 
-        // ---- outputs: lanes of a warp are consecutive variables, 32-aligned (Z % (32 CL) == 0)
+        // ---- outputs: a warp packs kOutW words (32 consecutive variables each, Z % (32 CL) == 0) at a time
         uint32_t *ab = p.allbits + (size_t)f * p.cw_words;
-        for (int item = tid; item < C * ZL; item += kThreads) {
-            const int c = item / ZL, m = lane0 + item - c * ZL;
-            const int v = c * Z + m;
-            const PostT pv = post[c * Zp + m];
-            const unsigned b = __ballot_sync(0xffffffffu, pv < (PostT)0);
-            if ((tid & 31) == 0) ab[v >> 5] = __brev(b);
-            if (p.posterior) {
-                if constexpr (sizeof(PostT) == 4 && sizeof(MsgT) == 4) reinterpret_cast<float *>(p.posterior)[(size_t)f * p.N + v] = (float)pv;
-                else reinterpret_cast<int *>(p.posterior)[(size_t)f * p.N + v] = (int)pv;
+        {
+            constexpr int kOutW = 4;
+            const int wpc = ZL >> 5, n_words = C * wpc, lane = tid & 31;
+            for (int w0 = (tid >> 5) * kOutW; w0 < n_words; w0 += (kThreads >> 5) * kOutW) {
+                PostT pv[kOutW];
+                int vv[kOutW];
+#pragma unroll
+                for (int k = 0; k < kOutW; ++k) {
+                    const int w = min(w0 + k, n_words - 1), c = w / wpc, m = lane0 + ((w - c * wpc) << 5) + lane;
+                    vv[k] = c * Z + m;
+                    pv[k] = post[c * Zp + m];
+                }
+#pragma unroll
+                for (int k = 0; k < kOutW; ++k) {
+                    const unsigned b = __ballot_sync(0xffffffffu, pv[k] < (PostT)0);
+                    if (w0 + k < n_words) {
+                        if (lane == 0) ab[vv[k] >> 5] = __brev(b);
+                        if (p.posterior) {
+                            if constexpr (sizeof(PostT) == 4 && sizeof(MsgT) == 4) reinterpret_cast<float *>(p.posterior)[(size_t)f * p.N + vv[k]] = (float)pv[k];
+                            else reinterpret_cast<int *>(p.posterior)[(size_t)f * p.N + vv[k]] = (int)pv[k];
+                        }
+                    }
+                }
             }
         }
         if (q == 0 && tid == 0) {

@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--qber", type=float, default=0.03)
     ap.add_argument("--max-iter", type=int, default=50)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--only", default="", help="run only the decoders whose name contains this text")
+    ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     q = importlib.import_module("qcrypto-ldpc_b200")
@@ -58,6 +60,8 @@ def main():
              ("NMS 6/8 i16", q.RULE_NMS, q.DTYPE_I16, 0.75, round(mag * 64), torch.int16, 8, 0),
              ("NMS 6/8 i8", q.RULE_NMS, q.DTYPE_I8, 0.75, round(mag * 4), torch.int8, 4, 0))
     for name, rule, dt, norm, m, tdt, bytes_per_edge, flags in cases:
+        if args.only and args.only not in name:
+            continue
         dec = q.Decoder(code, schedule=q.SCHED_FLOODING, rule=rule, dtype=dt, max_iter=args.max_iter, early_stop=True,
                         norm_factor=norm, out_mode=q.OUT_ALL, flags=flags)
         syn = torch.empty((F, dec.syn_words), dtype=torch.int32, device=dev)
@@ -67,7 +71,7 @@ def main():
         out = torch.empty((F, dec.cw_words), dtype=torch.int32, device=dev)
         ok = torch.empty(F, dtype=torch.uint8, device=dev)
         it = torch.empty(F, dtype=torch.int16, device=dev)
-        for _ in range(2):
+        for _ in range(args.warmup):
             dec.decode_device(llr.data_ptr(), syn.data_ptr(), F, out.data_ptr(), ok.data_ptr(), it.data_ptr(), 0, st)
         torch.cuda.synchronize()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.reps + 1)]

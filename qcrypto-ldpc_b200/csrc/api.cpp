@@ -674,12 +674,13 @@ extern "C" int qldpc_decoder_create(const qldpc_code *code, const qldpc_decoder_
             const int smem = flooding_qcx_smem_bytes(c.base_rows, c.base_cols, nnz, cfg->dtype);
             const size_t msg_bytes = (size_t)nnz * zp * flooding_qcx_msg_bytes(cfg->dtype);
             const size_t post_bytes = (size_t)c.base_cols * zp * flooding_qcx_post_bytes(cfg->dtype);
-            const size_t l2_budget = (size_t)prop.l2CacheSize / 2;
+            const size_t l2_budget = (size_t)prop.l2CacheSize / 10 * 7;
             int max_deg = 0;
             for (int r = 0; r < c.m; ++r) max_deg = std::max(max_deg, c.row_ptr[r + 1] - c.row_ptr[r]);
             d->qcx_lanes = flooding_qcx_lanes_per_thread(max_deg);
+            if (c.z % (32 * d->qcx_lanes) != 0) d->qcx_lanes = 2;
             const char *force_cl = getenv("QLDPC_QCX_CL");   // EXPERIMENT
-            for (int cl = force_cl ? atoi(force_cl) : 1; cl <= 8 && c.z % (32 * cl) == 0; cl *= 2) {
+            for (int cl = force_cl ? atoi(force_cl) : 1; cl <= 8 && c.z % (32 * d->qcx_lanes * cl) == 0; cl *= 2) {
                 const int n = flooding_qcx_max_clusters(cfg->dtype, d->qcx_lanes, cl, smem);
                 if (n < 1) continue;
                 d->qcx_cl = cl; d->qcx_clusters = n; d->qcx_smem = smem;

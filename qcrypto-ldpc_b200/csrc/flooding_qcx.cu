@@ -9,20 +9,21 @@
 //     SMs / CL frames are in flight and their messages + posteriors (1.05 MB per frame) stay resident in the 126 MB L2:
 //     the 16 E bytes per sweep are L2 traffic, HBM sees the channel LLRs.  The phases are separated by the
 //     hardware cluster barrier; the early-termination vote crosses the cluster through distributed shared memory;
-//   * a thread works on V = 4 (row degree <= 8) or 2 CONSECUTIVE lanes of a circulant at a time: its own messages are one
-//     aligned 128-bit (float) / 64-bit / 32-bit access per edge, and the table look-up, the cyclic shift and the address
-//     arithmetic of an edge are paid once per V lanes.  The cyclic shift makes the other operand (the posteriors in the
-//     check phase, the messages in the variable phase) a run of V consecutive lanes that starts anywhere; every run of Z
-//     lanes in the scratch is therefore followed by a copy of its first lanes (stride Z + 4), so that such a run never
-//     wraps: one wrapped start index + V loads at immediate offsets;
-//   * the circulant tables sit in shared memory; a work item issues all its loads before the first use (V (dc + dc) values
-//     in flight per thread);
+//   * the Z lanes of a circulant map onto warp lanes: a work item is a chunk of 32 V consecutive lanes (V = 4 for row
+//     degrees <= 8, else 2) of one block row, worked on by one warp; thread `lane` has lanes chunk + lane + 32 k, so every
+//     load and store of the warp is 32 consecutive values (one or two 128-byte lines) whatever the cyclic shift, and the
+//     table look-up, the shift and the address arithmetic of an edge are paid once per V lanes.  A shifted chunk wraps
+//     past the end of the circulant for one chunk per edge only (a warp-uniform branch);
+//   * the circulant tables sit in shared memory; a work item issues all its loads before the first use (2 V dc values
+//     in flight per thread); the variable phase works on four block columns side by side for the same reason;
 //   * the check update is compiled per row degree (no predicated slots), rule and SPA flavour are template parameters;
 //     the first ncu capture of the generic version (profiles/r2_flooding_qcx_v1_ncu_summary.txt) showed the kernel bound
 //     by instruction issue, not by memory: 220 thread instructions per edge and sweep;
 //   * integer tiers keep their messages in 8 / 16 bits (posteriors in 16 / 32), not in 32-bit words;
 //   * sweep 0 reads no messages at all (they are zero), so the scratch is never cleared.
 #include <cooperative_groups.h>
+
+#include <type_traits>
 
 #include "kernels.hpp"
 
@@ -33,7 +34,6 @@ namespace qldpc {
 namespace {
 
 constexpr int kThreads = 512;
-constexpr int kPad = 4;              // lanes appended to every run of Z lanes in the scratch (copy of lanes 0 .. 3)
 constexpr int kMaxDcV4 = 8;          // rows up to this degree: 4 lanes per thread (codes whose heaviest row is heavier: 2)
 constexpr int kMaxDcV2 = 20;         // compiled row degrees; heavier rows take the two-pass loop
 
@@ -107,49 +107,52 @@ enum { kSpaExact = 0, kSpaFast = 1, kMinSum = 2 };
 
 __device__ __forceinline__ unsigned fbits(float x) { return __float_as_uint(x); }
 
-// V consecutive values, aligned as one vector access
-template <typename T, int V> struct alignas(sizeof(T) * V) Vec { T v[V]; };
-
-// ---- one work item of the check phase: block row starting at edge e0 with exactly DC edges, check lanes l0 .. l0 + V - 1
-// (l0 % V == 0).  Reads the posteriors of their variables and their old messages, writes the new ones.  FIRST: sweep 0, the
-// old messages are zero and not read.  synbits: the V syndrome bits, lane l0 in bit V - 1.  Returns the OR of the
-// hard-decision parities (early-stop test).  Offsets are 32-bit (nnz * (Z + 4) and N are far below 2^31).
+// ---- one work item of the check phase: block row starting at edge e0 with exactly DC edges, for a chunk of 32 V check
+// lanes starting at cb (a multiple of 32 V): this thread works on lanes cb + lane + 32 k, k < V, so that every load and
+// store of the warp is 32 consecutive values.  Reads the posteriors of the variables and the old messages, writes the new
+// messages.  A cyclic shift turns the chunk into a run of 32 V variable lanes that starts anywhere; the run wraps past the
+// end of the circulant for one chunk per edge only, a warp-uniform case.  FIRST: sweep 0, the old messages are zero and
+// not read.  synw[k]: syndrome word of lanes cb + 32 k .. + 31 (bit 31 = first lane).  Returns the OR of the
+// hard-decision parities (early-stop test).  Offsets are 32-bit (nnz * Z and N are far below 2^31).
 template <typename MsgT, typename PostT, int FLAVOUR, bool FIRST, int DC, int V>
-__device__ __forceinline__ int check_item(const Upd p, int e0, const int2 *edges, const PostT *post, MsgT *c2v, int l0,
-                                          int Z, unsigned synbits)
+__device__ __forceinline__ int check_item(const Upd p, int e0, const int2 *edges, const PostT *post, MsgT *c2v, int cb, int lane,
+                                          int Z, const unsigned (&synw)[V])
 {
     constexpr bool kFloat = sizeof(PostT) == 4 && sizeof(MsgT) == 4;
-    typedef Vec<MsgT, V> MV;
-    const int Zp = Z + kPad;
-    PostT pv[DC][V];
-    MV old[DC];
-    MsgT *cm = c2v + (e0 * Zp + l0);
+    typedef typename std::conditional<kFloat, float, int>::type XT;
+    XT x[DC][V];                            // variable-to-check messages: posterior - old message
+    unsigned hs[V];                         // XOR of the posteriors' sign bits (hard-decision parity)
 #pragma unroll
-    for (int j = 0; j < DC; ++j) {          // all loads first: (V + 1) x DC requests in flight per thread
-        const int2 e = edges[e0 + j];       // (block column * (Z + 4), shift)
-        int vl = l0 + e.y;
-        if (vl >= Z) vl -= Z;
-        const PostT *pp = post + (e.x + vl);
+    for (int k = 0; k < V; ++k) hs[k] = 0;
+    MsgT *cm = c2v + (e0 * Z + cb + lane);
 #pragma unroll
-        for (int i = 0; i < V; ++i) pv[j][i] = pp[i];
-        if (!FIRST) old[j] = *reinterpret_cast<const MV *>(cm + j * Zp);
-    }
-    int bad = 0;
-    MV out[DC];
+    for (int j = 0; j < DC; ++j) {          // the loads are independent of everything else: up to 2 V DC requests in flight
+        const int2 e = edges[e0 + j];       // (block column * Z, shift)
+        int vb = cb + e.y;                  // variable lane of the chunk's first check lane
+        if (vb >= Z) vb -= Z;
+        const PostT *pp = post + (e.x + vb + lane);
+        PostT pv[V];
+        if (vb + 32 * V <= Z) {             // warp-uniform: the run does not wrap
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-        const int synbit = (int)((synbits >> (V - 1 - i)) & 1u);
-        int hard = synbit;
-        if constexpr (kFloat) {   // the variable phase never writes -0 (y + (+0 + m ...)): the sign bit is the hard decision
-            unsigned hs = 0;
-#pragma unroll
-            for (int j = 0; j < DC; ++j) hs ^= fbits((float)pv[j][i]);
-            hard ^= (int)(hs >> 31);
+            for (int k = 0; k < V; ++k) pv[k] = pp[32 * k];
         } else {
 #pragma unroll
-            for (int j = 0; j < DC; ++j) hard ^= pv[j][i] < (PostT)0;
+            for (int k = 0; k < V; ++k) pv[k] = pp[32 * k - ((vb + lane + 32 * k >= Z) ? Z : 0)];
         }
-        bad |= hard;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            // the variable phase never writes -0 (y + (+0 + m ...)): the sign bit of a float posterior is its hard decision
+            if constexpr (kFloat) hs[k] ^= fbits((float)pv[k]);
+            else hs[k] ^= (unsigned)(int)pv[k];
+            const XT o = FIRST ? (XT)0 : (XT)cm[j * Z + 32 * k];
+            x[j][k] = (XT)pv[k] - o;
+        }
+    }
+    int bad = 0;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const int synbit = (int)((synw[i] >> (31 - lane)) & 1u);
+        bad |= synbit ^ (int)(hs[i] >> 31);
         if constexpr (kFloat) {
             unsigned sign = (unsigned)synbit << 31;
             if constexpr (FLAVOUR != kMinSum) {
@@ -157,28 +160,26 @@ __device__ __forceinline__ int check_item(const Upd p, int e0, const int2 *edges
                 float product = 1.0f;
 #pragma unroll
                 for (int j = 0; j < DC; ++j) {
-                    const float x = pv[j][i] - (FIRST ? 0.0f : (float)old[j].v[i]);
-                    const float tj = FLAVOUR == kSpaFast ? tanh_half_fast(fabsf(x)) : tanh_half_exact(fabsf(x));
+                    const float xv = x[j][i];
+                    const float tj = FLAVOUR == kSpaFast ? tanh_half_fast(fabsf(xv)) : tanh_half_exact(fabsf(xv));
                     const float t = (tj != 0.0f) ? tj : 1e-12f;
                     product *= t;
-                    sign ^= fbits(x);
-                    ts[j] = __uint_as_float(fbits(t) | (fbits(x) & 0x80000000u));
+                    sign ^= fbits(xv);
+                    ts[j] = __uint_as_float(fbits(t) | (fbits(xv) & 0x80000000u));
                 }
 #pragma unroll
                 for (int j = 0; j < DC; ++j) {
                     float rr = product / fabsf(ts[j]);               // IEEE division, as the oracle
                     rr = (rr < 1.0f) ? rr : 1.0f - 1.1920929e-07f;
                     const float mag = FLAVOUR == kSpaFast ? two_atanh_fast(rr) : two_atanh_exact(rr);
-                    out[j].v[i] = (MsgT)__uint_as_float(fbits(mag) ^ ((sign ^ fbits(ts[j])) & 0x80000000u));   // mag >= 0
+                    cm[j * Z + 32 * i] = (MsgT)__uint_as_float(fbits(mag) ^ ((sign ^ fbits(ts[j])) & 0x80000000u));   // mag >= 0
                 }
             } else {
-                float x[DC];
                 float min1 = 3.402823466e+38f, min2 = 3.402823466e+38f;
 #pragma unroll
                 for (int j = 0; j < DC; ++j) {
-                    x[j] = pv[j][i] - (FIRST ? 0.0f : (float)old[j].v[i]);
-                    const float a = fabsf(x[j]);
-                    sign ^= fbits(x[j]);
+                    const float a = fabsf(x[j][i]);
+                    sign ^= fbits(x[j][i]);
                     min2 = fminf(min2, fmaxf(a, min1));
                     min1 = fminf(min1, a);
                 }
@@ -186,18 +187,17 @@ __device__ __forceinline__ int check_item(const Upd p, int e0, const int2 *edges
                 const float cst2 = p.rule == QLDPC_RULE_NMS ? min1 * p.norm : fmaxf(0.0f, min1 - p.offset);
 #pragma unroll
                 for (int j = 0; j < DC; ++j) {
-                    const float mag = (fabsf(x[j]) == min1) ? cst1 : cst2;
-                    out[j].v[i] = (MsgT)__uint_as_float(fbits(mag) ^ ((sign ^ fbits(x[j])) & 0x80000000u));
+                    const float mag = (fabsf(x[j][i]) == min1) ? cst1 : cst2;
+                    cm[j * Z + 32 * i] = (MsgT)__uint_as_float(fbits(mag) ^ ((sign ^ fbits(x[j][i])) & 0x80000000u));
                 }
             }
         } else {
-            int x[DC];
             int sign = synbit, min1 = p.vmax, min2 = p.vmax;
 #pragma unroll
             for (int j = 0; j < DC; ++j) {
-                x[j] = min(max((int)pv[j][i] - (FIRST ? 0 : (int)old[j].v[i]), -p.vmax), p.vmax);
-                const int a = abs(x[j]);
-                sign ^= x[j] < 0;
+                x[j][i] = min(max(x[j][i], -p.vmax), p.vmax);
+                const int a = abs(x[j][i]);
+                sign ^= x[j][i] < 0;
                 min2 = min(min2, max(a, min1));
                 min1 = min(min1, a);
             }
@@ -205,30 +205,24 @@ __device__ __forceinline__ int check_item(const Upd p, int e0, const int2 *edges
             const int cst2 = p.rule == QLDPC_RULE_OMS ? max(min1 - p.offset_int, 0) : norm8(min1, p.norm_eighths);
 #pragma unroll
             for (int j = 0; j < DC; ++j) {
-                const int mag = (abs(x[j]) == min1) ? cst1 : cst2;
-                out[j].v[i] = (MsgT)((sign ^ (x[j] < 0)) ? -mag : mag);
+                const int mag = (abs(x[j][i]) == min1) ? cst1 : cst2;
+                cm[j * Z + 32 * i] = (MsgT)((sign ^ (x[j][i] < 0)) ? -mag : mag);
             }
         }
-    }
-#pragma unroll
-    for (int j = 0; j < DC; ++j) {
-        *reinterpret_cast<MV *>(cm + j * Zp) = out[j];
-        if (l0 < kPad) *reinterpret_cast<MV *>(cm + j * Zp + Z) = out[j];      // the copy of lanes 0 .. 3 behind the run
     }
     return bad;
 }
 
 // any degree: two passes over memory (rows heavier than the compiled degrees)
 template <typename MsgT, typename PostT, int FLAVOUR, bool FIRST, int V>
-__device__ __noinline__ int check_item_any(const Upd p, int e0, int deg, const int2 *edges, const PostT *post, MsgT *c2v,
-                                           int l0, int Z, unsigned synbits)
+__device__ __noinline__ int check_item_any(const Upd p, int e0, int deg, const int2 *edges, const PostT *post, MsgT *c2v, int cb,
+                                           int lane, int Z, const unsigned (&synw)[V])
 {
     constexpr bool kFloat = sizeof(PostT) == 4 && sizeof(MsgT) == 4;
-    const int Zp = Z + kPad;
     int bad = 0;
     for (int i = 0; i < V; ++i) {
-        const int l = l0 + i, synbit = (int)((synbits >> (V - 1 - i)) & 1u);
-        MsgT *cm = c2v + (e0 * Zp + l);
+        const int l = cb + lane + 32 * i, synbit = (int)((synw[i] >> (31 - lane)) & 1u);
+        MsgT *cm = c2v + (e0 * Z + l);
         int sign = synbit, hard = synbit;
         auto v2c = [&](int j, bool count_hard) {
             const int2 e = edges[e0 + j];
@@ -236,13 +230,9 @@ __device__ __noinline__ int check_item_any(const Upd p, int e0, int deg, const i
             if (vl >= Z) vl -= Z;
             const PostT pvj = post[e.x + vl];
             if (count_hard) hard ^= pvj < (PostT)0;
-            const MsgT o = FIRST ? (MsgT)0 : cm[j * Zp];
+            const MsgT o = FIRST ? (MsgT)0 : cm[j * Z];
             if constexpr (kFloat) return (float)pvj - (float)o;
             else return (float)min(max((int)pvj - (int)o, -p.vmax), p.vmax);   // integers up to 2^24 are exact in a float
-        };
-        auto put = [&](int j, MsgT m) {
-            cm[j * Zp] = m;
-            if (l < kPad) cm[j * Zp + Z] = m;
         };
         auto th = [&](float a) { return FLAVOUR == kSpaFast ? tanh_half_fast(a) : tanh_half_exact(a); };
         if (kFloat && FLAVOUR != kMinSum) {
@@ -260,7 +250,7 @@ __device__ __noinline__ int check_item_any(const Upd p, int e0, int deg, const i
                 float rr = product / ((tj != 0.0f) ? tj : 1e-12f);
                 rr = (rr < 1.0f) ? rr : 1.0f - 1.1920929e-07f;
                 const float mag = FLAVOUR == kSpaFast ? two_atanh_fast(rr) : two_atanh_exact(rr);
-                put(j, (MsgT)((sign ^ (signbit(xv) ? 1 : 0)) ? -mag : mag));
+                cm[j * Z] = (MsgT)((sign ^ (signbit(xv) ? 1 : 0)) ? -mag : mag);
             }
             continue;
         }
@@ -285,19 +275,19 @@ __device__ __noinline__ int check_item_any(const Upd p, int e0, int deg, const i
             const float xv = v2c(j, false);
             const float mag = (fabsf(xv) == min1) ? cst1 : cst2;
             const float o = (sign ^ (signbit(xv) ? 1 : 0)) ? -mag : mag;
-            if constexpr (kFloat) put(j, o);
-            else put(j, (MsgT)(int)o);
+            if constexpr (kFloat) cm[j * Z] = o;
+            else cm[j * Z] = (MsgT)(int)o;
         }
     }
     return bad;
 }
 
-// the row's degree is the same for all threads of a warp when Z / CL is a multiple of 32 V (no divergence)
+// the row's degree is the same for all threads of a warp (a work item belongs to one warp)
 template <typename MsgT, typename PostT, int FLAVOUR, bool FIRST, int V>
 __device__ __forceinline__ int check_dispatch(const Upd p, const RowMeta ly, const int2 *edges, const PostT *post, MsgT *c2v,
-                                              int l0, int Z, unsigned synbits)
+                                              int cb, int lane, int Z, const unsigned (&synw)[V])
 {
-#define QL_DC(D) case D: return check_item<MsgT, PostT, FLAVOUR, FIRST, D, V>(p, ly.edge_begin, edges, post, c2v, l0, Z, synbits);
+#define QL_DC(D) case D: return check_item<MsgT, PostT, FLAVOUR, FIRST, D, V>(p, ly.edge_begin, edges, post, c2v, cb, lane, Z, synw);
     if constexpr (V == 4) {
         switch (ly.degree) {
             QL_DC(2) QL_DC(3) QL_DC(4) QL_DC(5) QL_DC(6) QL_DC(7) QL_DC(8)
@@ -311,13 +301,14 @@ __device__ __forceinline__ int check_dispatch(const Upd p, const RowMeta ly, con
         }
     }
 #undef QL_DC
-    return check_item_any<MsgT, PostT, FLAVOUR, FIRST, V>(p, ly.edge_begin, ly.degree, edges, post, c2v, l0, Z, synbits);
+    return check_item_any<MsgT, PostT, FLAVOUR, FIRST, V>(p, ly.edge_begin, ly.degree, edges, post, c2v, cb, lane, Z, synw);
 }
 
-// Shared-memory layout: RowMeta rows[R]; int2 edges[nnz] (block column * (Z + 4), shift); int col_ptr[C + 1]; int2 col_edges[nnz]
-// (edge id * (Z + 4), shift); int vote[2][8].
-// Scratch layout (per cluster): messages c2v[edge][Z + 4] indexed by CHECK lane, posteriors post[block column][Z + 4]; the
-// four lanes behind a run repeat its first four.
+// Shared-memory layout: RowMeta rows[R]; int2 edges[nnz] (block column * Z, shift); int col_ptr[C + 2]; int2 col_edges[nnz]
+// (edge id * Z, shift); int vote[2][8].
+// Scratch layout (per cluster): messages c2v[edge][Z] indexed by CHECK lane, posteriors post[block column][Z].
+// A work item is a chunk of 32 V consecutive lanes of one block row (check phase) or of kCols block columns (variable
+// phase) and belongs to one warp; thread `lane` of the warp works on lanes chunk + lane + 32 k, k < V.
 template <typename MsgT, typename PostT, typename InT, int FLAVOUR, int V>
 __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQcxParams p)
 {
@@ -325,12 +316,12 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
     cg::cluster_group cluster = cg::this_cluster();
     const int CL = (int)cluster.num_blocks(), q = (int)cluster.block_rank();
     const int cid = blockIdx.x / CL, n_clusters = gridDim.x / CL;
-    const int tid = threadIdx.x, Z = p.Z, Zp = Z + kPad, ZL = Z / CL, lane0 = q * ZL, QL = ZL / V;
+    const int tid = threadIdx.x, Z = p.Z, ZL = Z / CL, lane0 = q * ZL;
     const int R = p.brows, C = p.bcols;
-    const int step_r = kThreads / QL, step_q = kThreads - step_r * QL;   // a thread's next work item: kThreads items further
-    typedef Vec<MsgT, V> MV;
-    typedef Vec<PostT, V> PV;
-    typedef Vec<InT, V> IV;
+    constexpr int kWarps = kThreads / 32, kChunk = 32 * V;
+    const int lane = tid & 31, wid = (int)__shfl_sync(0xffffffffu, tid >> 5, 0);   // warp index, on the uniform datapath
+    const int NCH = ZL / kChunk;                                              // chunks per block row / column in this block
+    const int step_r = kWarps / NCH, step_c = kWarps - step_r * NCH;          // a warp's next work item: kWarps items further
 
     RowMeta *rows = reinterpret_cast<RowMeta *>(smem);
     int2 *edges = reinterpret_cast<int2 *>(rows + R);
@@ -339,15 +330,15 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
     int *vote = reinterpret_cast<int *>(col_edges + p.nnz);
     for (int r = tid; r < R; r += kThreads) rows[r] = RowMeta{p.layers[r].edge_begin, p.layers[r].degree};
     for (int e = tid; e < p.nnz; e += kThreads) {
-        edges[e] = make_int2(p.aux[e].col * Zp, p.aux[e].shift);
-        col_edges[e] = make_int2(p.col_edges[e].x * Zp, p.col_edges[e].y);
+        edges[e] = make_int2(p.aux[e].col * Z, p.aux[e].shift);
+        col_edges[e] = make_int2(p.col_edges[e].x * Z, p.col_edges[e].y);
     }
     for (int c = tid; c <= C; c += kThreads) col_ptr[c] = p.col_ptr[c];
     if (tid < 16) vote[tid] = 0;
     cluster.sync();
 
-    MsgT *c2v = reinterpret_cast<MsgT *>(p.c2v) + (size_t)cid * p.nnz * Zp;
-    PostT *post = reinterpret_cast<PostT *>(p.post) + (size_t)cid * C * Zp;
+    MsgT *c2v = reinterpret_cast<MsgT *>(p.c2v) + (size_t)cid * p.nnz * Z;
+    PostT *post = reinterpret_cast<PostT *>(p.post) + (size_t)cid * p.N;
     unsigned vpar = 0;
     const Upd upd{p.rule, p.offset_int, p.norm_eighths, p.vmax, p.norm, p.offset};
 
@@ -362,12 +353,6 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
         vpar ^= 1u;
         return any != 0;
     };
-    // the V syndrome bits of check lanes l0 .. l0 + V - 1 of block row r (one word: V divides 32, l0 % V == 0), lane l0 highest
-    auto syn_of = [&](const uint32_t *syn, int r, int l0) {
-        if (!syn) return 0u;
-        const int mi = r * Z + l0;
-        return (syn[mi >> 5] >> (32 - V - (mi & 31))) & ((1u << V) - 1u);
-    };
 
     for (int f = cid; f < p.F; f += n_clusters) {
         const InT *llr = reinterpret_cast<const InT *>(p.llr) + (size_t)f * p.N;
@@ -376,15 +361,15 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
         bool ok = false;
         for (;;) {
             // ---- variable phase: post[v] = llr[v] + sum of the column's messages in ascending block-row order.
-            // A work item is V consecutive variable lanes of kCols block columns side by side: a column of weight 3 alone
-            // keeps only 3 V loads in flight per thread and the phase waits on L2 latency.
+            // kCols block columns side by side: a column of weight 3 alone keeps only 3 V loads in flight per thread and
+            // the phase waits on L2 latency.
             {
                 constexpr int kCols = 4, kDv = V == 4 ? 3 : 4;   // columns per item, edges of each column in flight at a time
                 const int n_groups = (C + kCols - 1) / kCols;
-                int cgp = tid / QL, qd = tid - cgp * QL;
-                for (; cgp < n_groups; qd += step_q, cgp += step_r + (qd >= QL ? 1 : 0), qd -= (qd >= QL ? QL : 0)) {
-                    const int m0 = lane0 + qd * V;
-                    IV y[kCols];
+                int cgp = wid / NCH, ch = wid - cgp * NCH;
+                for (; cgp < n_groups; ch += step_c, cgp += step_r + (ch >= NCH ? 1 : 0), ch -= (ch >= NCH ? NCH : 0)) {
+                    const int mb = lane0 + ch * kChunk;          // first variable lane of the chunk
+                    InT y[kCols][V];
                     PostT sum[kCols][V];
                     int ka[kCols], kn[kCols], kmax = 0;
 #pragma unroll
@@ -394,9 +379,11 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
                         ka[u] = valid ? col_ptr[c] : 0;
                         kn[u] = (valid && it > 0) ? col_ptr[c + 1] - ka[u] : 0;
                         kmax = max(kmax, kn[u]);
-                        if (valid) y[u] = *reinterpret_cast<const IV *>(llr + (c * Z + m0));
 #pragma unroll
-                        for (int i = 0; i < V; ++i) sum[u][i] = (PostT)0;
+                        for (int i = 0; i < V; ++i) {
+                            y[u][i] = valid ? llr[c * Z + mb + lane + 32 * i] : (InT)0;
+                            sum[u][i] = (PostT)0;
+                        }
                     }
                     for (int k = 0; k < kmax; k += kDv) {
                         MsgT m[kCols][kDv][V];
@@ -405,12 +392,17 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
 #pragma unroll
                             for (int d = 0; d < kDv; ++d) {
                                 if (k + d < kn[u]) {
-                                    const int2 ce = col_edges[ka[u] + k + d];            // edge id * (Z + 4), shift
-                                    int l = m0 - ce.y;
-                                    if (l < 0) l += Z;
-                                    const MsgT *mp = c2v + (ce.x + l);
+                                    const int2 ce = col_edges[ka[u] + k + d];            // edge id * Z, shift
+                                    int lb = mb - ce.y;                                  // check lane of the chunk's first variable lane
+                                    if (lb < 0) lb += Z;
+                                    const MsgT *mp = c2v + (ce.x + lb + lane);
+                                    if (lb + kChunk <= Z) {
 #pragma unroll
-                                    for (int i = 0; i < V; ++i) m[u][d][i] = mp[i];
+                                        for (int i = 0; i < V; ++i) m[u][d][i] = mp[32 * i];
+                                    } else {
+#pragma unroll
+                                        for (int i = 0; i < V; ++i) m[u][d][i] = mp[32 * i - ((lb + lane + 32 * i >= Z) ? Z : 0)];
+                                    }
                                 }
                             }
                         }
@@ -429,11 +421,8 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
                     for (int u = 0; u < kCols; ++u) {
                         const int c = cgp * kCols + u;
                         if (c < C) {
-                            PV o;
 #pragma unroll
-                            for (int i = 0; i < V; ++i) o.v[i] = (PostT)y[u].v[i] + sum[u][i];
-                            *reinterpret_cast<PV *>(post + (c * Zp + m0)) = o;
-                            if (m0 < kPad) *reinterpret_cast<PV *>(post + (c * Zp + Z + m0)) = o;
+                            for (int i = 0; i < V; ++i) post[c * Z + mb + lane + 32 * i] = (PostT)y[u][i] + sum[u][i];
                         }
                     }
                 }
@@ -442,19 +431,22 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
             const bool last = it >= p.max_iter;
             if (last) {   // final verdict after the last sweep: syndrome of the hard decisions, no update
                 int bad = 0;
-                int r = tid / QL, qd = tid - r * QL;
-                for (; r < R; qd += step_q, r += step_r + (qd >= QL ? 1 : 0), qd -= (qd >= QL ? QL : 0)) {
-                    const int l0 = lane0 + qd * V;
-                    unsigned s = syn_of(syn, r, l0);
+                int r = wid / NCH, ch = wid - r * NCH;
+                for (; r < R; ch += step_c, r += step_r + (ch >= NCH ? 1 : 0), ch -= (ch >= NCH ? NCH : 0)) {
+                    const int cb = lane0 + ch * kChunk;
                     const RowMeta ly = rows[r];
-                    for (int j = 0; j < ly.degree; ++j) {
-                        const int2 e = edges[ly.edge_begin + j];
-                        int vl = l0 + e.y;
-                        if (vl >= Z) vl -= Z;
 #pragma unroll
-                        for (int i = 0; i < V; ++i) s ^= (unsigned)(post[e.x + vl + i] < (PostT)0) << (V - 1 - i);
+                    for (int i = 0; i < V; ++i) {
+                        const int l = cb + lane + 32 * i;
+                        unsigned s = syn ? (syn[(r * Z + cb) / 32 + i] >> (31 - lane)) & 1u : 0u;
+                        for (int j = 0; j < ly.degree; ++j) {
+                            const int2 e = edges[ly.edge_begin + j];
+                            int vl = l + e.y;
+                            if (vl >= Z) vl -= Z;
+                            s ^= (unsigned)(post[e.x + vl] < (PostT)0);
+                        }
+                        bad |= (int)s;
                     }
-                    bad |= (int)s;
                 }
                 ok = !cluster_any(bad);
                 break;
@@ -463,12 +455,14 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
             // If it passes the decoder stops here: the messages just written are never used, `it` is not advanced.
             const bool want_check = p.early_stop && it > 0;
             int bad = 0;
-            int r = tid / QL, qd = tid - r * QL;                        // work item: (block row, V consecutive check lanes)
-            for (; r < R; qd += step_q, r += step_r + (qd >= QL ? 1 : 0), qd -= (qd >= QL ? QL : 0)) {
-                const int l0 = lane0 + qd * V;
-                const unsigned sb = syn_of(syn, r, l0);
-                bad |= it == 0 ? check_dispatch<MsgT, PostT, FLAVOUR, true, V>(upd, rows[r], edges, post, c2v, l0, Z, sb)
-                               : check_dispatch<MsgT, PostT, FLAVOUR, false, V>(upd, rows[r], edges, post, c2v, l0, Z, sb);
+            int r = wid / NCH, ch = wid - r * NCH;                        // work item: (block row, chunk of 32 V check lanes)
+            for (; r < R; ch += step_c, r += step_r + (ch >= NCH ? 1 : 0), ch -= (ch >= NCH ? NCH : 0)) {
+                const int cb = lane0 + ch * kChunk;
+                unsigned synw[V];
+#pragma unroll
+                for (int i = 0; i < V; ++i) synw[i] = syn ? syn[(r * Z + cb) / 32 + i] : 0u;
+                bad |= it == 0 ? check_dispatch<MsgT, PostT, FLAVOUR, true, V>(upd, rows[r], edges, post, c2v, cb, lane, Z, synw)
+                               : check_dispatch<MsgT, PostT, FLAVOUR, false, V>(upd, rows[r], edges, post, c2v, cb, lane, Z, synw);
             }
             if (want_check) {
                 ok = !cluster_any(bad);
@@ -484,15 +478,15 @@ __global__ void __launch_bounds__(kThreads, 1) flooding_qcx_kernel(const FloodQc
         uint32_t *ab = p.allbits + (size_t)f * p.cw_words;
         {
             constexpr int kOutW = 4;
-            const int wpc = ZL >> 5, n_words = C * wpc, lane = tid & 31;
-            for (int w0 = (tid >> 5) * kOutW; w0 < n_words; w0 += (kThreads >> 5) * kOutW) {
+            const int wpc = ZL >> 5, n_words = C * wpc;
+            for (int w0 = wid * kOutW; w0 < n_words; w0 += kWarps * kOutW) {
                 PostT pv[kOutW];
                 int vv[kOutW];
 #pragma unroll
                 for (int k = 0; k < kOutW; ++k) {
                     const int w = min(w0 + k, n_words - 1), c = w / wpc, m = lane0 + ((w - c * wpc) << 5) + lane;
                     vv[k] = c * Z + m;
-                    pv[k] = post[c * Zp + m];
+                    pv[k] = post[vv[k]];
                 }
 #pragma unroll
                 for (int k = 0; k < kOutW; ++k) {
@@ -575,7 +569,7 @@ int flooding_qcx_smem_bytes(int brows, int bcols, int nnz, int dtype)
 
 int flooding_qcx_msg_bytes(int dtype) { return dtype == QLDPC_DTYPE_F32 ? 4 : (dtype == QLDPC_DTYPE_I16 ? 2 : 1); }
 int flooding_qcx_post_bytes(int dtype) { return dtype == QLDPC_DTYPE_I8 ? 2 : 4; }
-int flooding_qcx_run_lanes(int Z) { return Z + kPad; }
+int flooding_qcx_run_lanes(int Z) { return Z; }
 int flooding_qcx_lanes_per_thread(int max_row_degree) { return max_row_degree <= kMaxDcV4 ? 4 : 2; }
 
 #define QL_QCX_KERNELS(X, V)                                                                  \

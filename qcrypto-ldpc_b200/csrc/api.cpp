@@ -464,7 +464,7 @@ struct qldpc_decoder_full : qldpc_decoder {
     DevBuf<uint32_t> d_mask_known, d_mask_punct, d_tmp_bits;
     size_t scratch_msg_bytes = 0, scratch_app_bytes = 0;
     DevBuf<uint8_t> d_scratch2;
-    int gen_grid = 0;
+    int gen_grid = 0, gen_beliefs_global = 0;
     int flood_block = 0, flood_smem = 0, flood_use_smem = 0;
     // clustered QC flooding kernel (flooding_qcx.cu): blocks per cluster, co-resident clusters, table bytes
     int qcx_cl = 0, qcx_clusters = 0, qcx_smem = 0, qcx_lanes = 0;
@@ -643,11 +643,19 @@ extern "C" int qldpc_decoder_create(const qldpc_code *code, const qldpc_decoder_
             d->kernel_family = KF_LAYERED_GENERIC;
             d->kernel_name = "layered_generic";
         }
-        // the generic kernel also serves posterior requests of the fast family
-        d->gen_grid = d->sm_count * 2;
-        const size_t esz = 4;
-        d->scratch_msg_bytes = (size_t)d->gen_grid * c.edges * esz;
-        d->scratch_app_bytes = (size_t)d->gen_grid * c.n * esz;
+        // the generic kernel also serves posterior requests of the fast family: beliefs in shared memory (in a global scratch
+        // when a frame's beliefs do not fit), messages in an L2-resident scratch, as many CTAs per SM as fit
+        {
+            const int nnz = c.edges / c.z;
+            int smem = layered_generic_smem_bytes(c.base_rows, nnz, c.n, cfg->dtype);
+            d->gen_beliefs_global = smem > d->max_smem_optin;
+            if (d->gen_beliefs_global) smem = layered_generic_smem_bytes(c.base_rows, nnz, 0, cfg->dtype);
+            const int per_sm = layered_generic_blocks_per_sm(cfg->dtype, c.z, smem);
+            if (per_sm < 1) return bail(QLDPC_ERR_UNSUPPORTED);
+            d->gen_grid = d->sm_count * per_sm;
+            d->scratch_msg_bytes = (size_t)d->gen_grid * c.edges * layered_generic_msg_bytes(cfg->dtype);
+            d->scratch_app_bytes = d->gen_beliefs_global ? (size_t)d->gen_grid * c.n * layered_generic_belief_bytes(cfg->dtype) : 0;
+        }
     } else {
         d->kernel_family = KF_FLOODING;
         d->kernel_name = "flooding_csr";
@@ -679,12 +687,11 @@ extern "C" int qldpc_decoder_create(const qldpc_code *code, const qldpc_decoder_
             for (int r = 0; r < c.m; ++r) max_deg = std::max(max_deg, c.row_ptr[r + 1] - c.row_ptr[r]);
             d->qcx_lanes = flooding_qcx_lanes_per_thread(max_deg);
             if (c.z % (32 * d->qcx_lanes) != 0) d->qcx_lanes = 2;
-            const char *force_cl = getenv("QLDPC_QCX_CL");   // EXPERIMENT
-            for (int cl = force_cl ? atoi(force_cl) : 1; cl <= 8 && c.z % (32 * d->qcx_lanes * cl) == 0; cl *= 2) {
+            for (int cl = 1; cl <= 8 && c.z % (32 * d->qcx_lanes * cl) == 0; cl *= 2) {
                 const int n = flooding_qcx_max_clusters(cfg->dtype, d->qcx_lanes, cl, smem);
                 if (n < 1) continue;
                 d->qcx_cl = cl; d->qcx_clusters = n; d->qcx_smem = smem;
-                if (force_cl || (size_t)n * (msg_bytes + post_bytes) <= l2_budget) break;
+                if ((size_t)n * (msg_bytes + post_bytes) <= l2_budget) break;
             }
             if (d->qcx_cl > 0) {
                 d->kernel_name = "flooding_qc_cluster";
@@ -918,7 +925,7 @@ static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint3
         p.llr = d_llr; p.syn = d_syndrome; p.allbits = allbits; p.ok = d_ok; p.iters = d_iters;
         p.posterior = d_posterior; p.stats = d->d_stats.p;
         p.aux = d->d_qc_aux.p; p.layers = d->d_qc_layers.p;
-        p.msg = d->d_scratch.p; p.app = d->d_scratch2.p;
+        p.msg = d->d_scratch.p; p.app = d->gen_beliefs_global ? d->d_scratch2.p : nullptr;
         p.F = n_frames; p.Z = c.z; p.brows = c.base_rows; p.bcols = c.base_cols; p.nnz = c.edges / c.z;
         p.N = c.n; p.M = c.m; p.cw_words = d->cw_words; p.syn_words = d->syn_words;
         p.max_iter = cfg.max_iter; p.early_stop = cfg.early_stop; p.syndrome_depth = cfg.syndrome_depth;

@@ -89,8 +89,8 @@ struct LayeredGenParams {
     DevStats *stats;
     const QcEdgeAux *aux;
     const QcLayer *layers;
-    void *msg;                // F_resident * nnz * Z messages (global scratch)
-    void *app;                // F_resident * N beliefs (global scratch)
+    void *msg;                // grid * nnz * Z messages (float / int16), L2-resident global scratch
+    void *app;                // null: beliefs in shared memory; else grid * N beliefs (float / int16) in a global scratch
     int F;
     int Z, brows, bcols, nnz, N, M;
     int cw_words, syn_words;
@@ -99,6 +99,10 @@ struct LayeredGenParams {
     float norm, offset;
     int offset_int, norm_eighths, msg_max, app_max;
 };
+int layered_generic_belief_bytes(int dtype);
+int layered_generic_msg_bytes(int dtype);
+int layered_generic_smem_bytes(int brows, int nnz, int N, int dtype);       // N = 0: tables only (beliefs in global memory)
+int layered_generic_blocks_per_sm(int dtype, int Z, int smem_bytes);
 int launch_layered_generic(const LayeredGenParams &p, int grid, cudaStream_t st);
 
 // ---- layered, any H (CSR), float: one thread per frame (layered_csr.cu) ------------------------------------------

@@ -1,7 +1,7 @@
-// Generic layered decoder for quasi-cyclic codes: any lifting size, f32 / i16 / i8 messages,
-// optional posterior output.  One thread per circulant lane, one CTA per frame in flight;
-// beliefs and messages in a per-CTA global scratch (L2-resident).  This is the reference-shaped
-// fallback; the tuned int8 path is layered_i8.cu.
+// Generic layered decoder for quasi-cyclic codes: any lifting size, f32 / i16 / i8 tiers, optional posterior output.
+// This is the kernel behind Decoder_LDPC_BP_horizontal_layered for everything the packed int8 kernels (layered_i8s.cu,
+// layered_i8.cu) do not take: float layered SPA / NMS / OMS, the int16 tier, Z not a multiple of 4 (the 802.11n codes),
+// posterior requests.
 //
 // Integer arithmetic = ML/BPSK_nrldpc_sim_FP.m:35-94 (oracle: ora_decode_layered_fixed):
 //   contrib = L - R_old (:51); t = clip(contrib, -(msg_max+1), msg_max) (:53-56);
@@ -11,6 +11,15 @@
 //   oracle: ora_decode_layered_f32): contrib = var - branch; branch = rule(contrib); var = contrib + branch.
 // A QC block row is one layer: its Z checks touch disjoint variables, so processing them in
 // parallel equals the row-serial order of both references.
+//
+// Placement: one CTA per frame in flight, one thread per circulant lane (the Z lanes of a circulant on consecutive
+// threads; a cyclic shift is a rotated, conflict-free run of shared-memory words).
+//   shared memory: the row / edge tables and the frame's N beliefs (float, or int16 for the integer tiers);
+//   global scratch, L2-resident: the check-to-variable messages R[edge][lane] (float / int16) -- element (e, lane) is
+//     only ever touched by thread `lane`, so no synchronisation covers it and every access of a warp is one line;
+//   registers: L - R_old of the row in flight (and tanh for SPA), the row code is compiled per row degree.
+// A row costs one global round trip (its old messages, all dc loads in flight together) instead of the 2 dc dependent ones
+// of the first version (tables, beliefs and messages all behind L2); several CTAs per SM overlap their round trips.
 #include <type_traits>
 
 #include "kernels.hpp"
@@ -18,6 +27,12 @@
 namespace qldpc {
 
 namespace {
+
+constexpr int kMaxDc = 20;           // compiled row degrees; heavier rows take the two-pass loop
+
+struct RowMeta { int edge_begin, degree; };
+// the update rule's parameters, by value
+struct Upd { int rule, offset_int, norm_eighths, msg_max, app_max; float norm, offset; };
 
 __device__ __forceinline__ int norm8(int v, int k)
 {
@@ -33,25 +48,117 @@ __device__ __forceinline__ int norm8(int v, int k)
     }
 }
 __device__ __forceinline__ int clipi(int x, int lo, int hi) { return min(max(x, lo), hi); }
+__device__ __noinline__ float tanh_half(float a) { return (float)tanh((double)(a * 0.5f)); }
+__device__ __noinline__ float two_atanh(float r) { return 2.0f * (float)atanh((double)r); }
 
-__device__ __forceinline__ int syn_bit(const uint32_t *syn, int m) { return syn ? (int)((syn[m >> 5] >> (31 - (m & 31))) & 1u) : 0; }
-
-template <typename T>
-__device__ __forceinline__ void layer_lane(const LayeredGenParams &p, T *L, T *R, const QcEdgeAux *aux, int e0, int dc,
-                                           int i, int synbit)
+// One check (block row with DC edges starting at `ed`, check lane `lane`): beliefs in shared memory, old messages at
+// Rl[j * Z] (not read when `first`), new messages and beliefs written back.
+template <typename LT, typename MT, int DC>
+__device__ __forceinline__ void row_lane(const Upd u, LT *L, MT *Rl, const int2 *ed, int lane, int Z, int synbit, bool first)
 {
-    const int Z = p.Z;
-    if constexpr (std::is_floating_point<T>::value) {
+    constexpr bool kFloat = std::is_floating_point<LT>::value;
+    typedef typename std::conditional<kFloat, float, int>::type XT;
+    XT x[DC];
+    int idx[DC];
+#pragma unroll
+    for (int j = 0; j < DC; ++j) {
+        const int2 e = ed[j];               // (block column * Z, shift)
+        int l = lane + e.y;
+        if (l >= Z) l -= Z;
+        idx[j] = e.x + l;
+        const XT ro = first ? (XT)0 : (XT)Rl[j * Z];
+        x[j] = (XT)L[idx[j]] - ro;
+    }
+    if constexpr (kFloat) {
+        int sign = synbit;
+        if (u.rule == QLDPC_RULE_SPA) {
+            float t[DC];
+            float product = 1.0f;
+#pragma unroll
+            for (int j = 0; j < DC; ++j) {
+                const float tj = tanh_half(fabsf(x[j]));
+                t[j] = (tj != 0.0f) ? tj : 1e-12f;
+                product *= t[j];
+                sign ^= signbit(x[j]) ? 1 : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < DC; ++j) {
+                float r = product / t[j];
+                r = (r < 1.0f) ? r : 1.0f - 1.1920929e-07f;
+                const float mag = two_atanh(r);
+                const float out = (sign ^ (signbit(x[j]) ? 1 : 0)) ? -mag : mag;
+                Rl[j * Z] = out;
+                L[idx[j]] = x[j] + out;
+            }
+        } else {
+            float min1 = 3.402823466e+38f, min2 = 3.402823466e+38f;
+#pragma unroll
+            for (int j = 0; j < DC; ++j) {
+                const float a = fabsf(x[j]);
+                sign ^= signbit(x[j]) ? 1 : 0;
+                min2 = fminf(min2, fmaxf(a, min1));
+                min1 = fminf(min1, a);
+            }
+            float cst1 = 0.f, cst2 = 0.f;
+            if (u.rule == QLDPC_RULE_NMS) { cst1 = min2 * u.norm; cst2 = min1 * u.norm; }
+            else if (u.rule == QLDPC_RULE_OMS) { cst1 = fmaxf(0.0f, min2 - u.offset); cst2 = fmaxf(0.0f, min1 - u.offset); }
+#pragma unroll
+            for (int j = 0; j < DC; ++j) {
+                const float mag = (fabsf(x[j]) == min1) ? cst1 : cst2;
+                const float out = (sign ^ (signbit(x[j]) ? 1 : 0)) ? -mag : mag;
+                Rl[j * Z] = out;
+                L[idx[j]] = x[j] + out;
+            }
+        }
+    } else {
+        const int lo = -(u.msg_max + 1), hi = u.msg_max;
+        int sign = synbit, min1 = 1 << 30, min2 = 1 << 30;
+#pragma unroll
+        for (int j = 0; j < DC; ++j) {
+            const int t = clipi(x[j], lo, hi);
+            const int a = abs(t);
+            sign ^= (t < 0);
+            min2 = min(min2, max(a, min1));
+            min1 = min(min1, a);
+        }
+        min2 = min(min2, u.msg_max + 1);   // degree-1 row
+        int c1, c2;
+        if (u.rule == QLDPC_RULE_OMS) { c1 = max(min2 - u.offset_int, 0); c2 = max(min1 - u.offset_int, 0); }
+        else { c1 = norm8(min2, u.norm_eighths); c2 = norm8(min1, u.norm_eighths); }
+#pragma unroll
+        for (int j = 0; j < DC; ++j) {
+            const int t = clipi(x[j], lo, hi);
+            const int mag = (abs(t) == min1) ? c1 : c2;
+            const int out = (sign ^ (t < 0)) ? -mag : mag;
+            Rl[j * Z] = (MT)out;
+            L[idx[j]] = (LT)clipi(x[j] + out, -(u.app_max + 1), u.app_max);
+        }
+    }
+}
+
+// any degree: two passes over memory (rows heavier than the compiled degrees)
+template <typename LT, typename MT>
+__device__ __noinline__ void row_lane_any(const Upd u, LT *L, MT *Rl, const int2 *ed, int dc, int lane, int Z, int synbit, bool first)
+{
+    constexpr bool kFloat = std::is_floating_point<LT>::value;
+    auto contrib = [&](int j, int &at) {
+        const int2 e = ed[j];
+        int l = lane + e.y;
+        if (l >= Z) l -= Z;
+        at = e.x + l;
+        if constexpr (kFloat) return (float)L[at] - (first ? 0.0f : (float)Rl[j * Z]);
+        else return (int)L[at] - (first ? 0 : (int)Rl[j * Z]);
+    };
+    int at;
+    if constexpr (kFloat) {
         int sign = synbit;
         float product = 1.0f, min1 = 3.402823466e+38f, min2 = 3.402823466e+38f;
         for (int j = 0; j < dc; ++j) {
-            const QcEdgeAux ax = aux[e0 + j];
-            int l = i + ax.shift; if (l >= Z) l -= Z;
-            const float x = L[ax.col * Z + l] - R[(e0 + j) * Z + i];
+            const float x = contrib(j, at);
             const float a = fabsf(x);
             sign ^= signbit(x) ? 1 : 0;
-            if (p.rule == QLDPC_RULE_SPA) {
-                const float t = (float)tanh((double)(a * 0.5f));
+            if (u.rule == QLDPC_RULE_SPA) {
+                const float t = tanh_half(a);
                 product *= (t != 0.0f) ? t : 1e-12f;
             } else {
                 min2 = fminf(min2, fmaxf(a, min1));
@@ -59,76 +166,115 @@ __device__ __forceinline__ void layer_lane(const LayeredGenParams &p, T *L, T *R
             }
         }
         float cst1 = 0.f, cst2 = 0.f;
-        if (p.rule == QLDPC_RULE_NMS) { cst1 = min2 * p.norm; cst2 = min1 * p.norm; }
-        else if (p.rule == QLDPC_RULE_OMS) { cst1 = fmaxf(0.0f, min2 - p.offset); cst2 = fmaxf(0.0f, min1 - p.offset); }
+        if (u.rule == QLDPC_RULE_NMS) { cst1 = min2 * u.norm; cst2 = min1 * u.norm; }
+        else if (u.rule == QLDPC_RULE_OMS) { cst1 = fmaxf(0.0f, min2 - u.offset); cst2 = fmaxf(0.0f, min1 - u.offset); }
         for (int j = 0; j < dc; ++j) {
-            const QcEdgeAux ax = aux[e0 + j];
-            int l = i + ax.shift; if (l >= Z) l -= Z;
-            const float x = L[ax.col * Z + l] - R[(e0 + j) * Z + i];
+            const float x = contrib(j, at);
             float mag;
-            if (p.rule == QLDPC_RULE_SPA) {
-                const float t = (float)tanh((double)(fabsf(x) * 0.5f));
+            if (u.rule == QLDPC_RULE_SPA) {
+                const float t = tanh_half(fabsf(x));
                 float r = product / ((t != 0.0f) ? t : 1e-12f);
                 r = (r < 1.0f) ? r : 1.0f - 1.1920929e-07f;
-                mag = 2.0f * (float)atanh((double)r);
+                mag = two_atanh(r);
             } else {
                 mag = (fabsf(x) == min1) ? cst1 : cst2;
             }
             const float out = (sign ^ (signbit(x) ? 1 : 0)) ? -mag : mag;
-            R[(e0 + j) * Z + i] = out;
-            L[ax.col * Z + l] = x + out;
+            Rl[j * Z] = out;
+            L[at] = x + out;
         }
     } else {
-        const int lo = -(p.msg_max + 1), hi = p.msg_max;
+        const int lo = -(u.msg_max + 1), hi = u.msg_max;
         int sign = synbit, min1 = 1 << 30, min2 = 1 << 30;
         for (int j = 0; j < dc; ++j) {
-            const QcEdgeAux ax = aux[e0 + j];
-            int l = i + ax.shift; if (l >= Z) l -= Z;
-            const int t = clipi(L[ax.col * Z + l] - R[(e0 + j) * Z + i], lo, hi);
+            const int t = clipi(contrib(j, at), lo, hi);
             const int a = abs(t);
             sign ^= (t < 0);
             min2 = min(min2, max(a, min1));
             min1 = min(min1, a);
         }
-        min2 = min(min2, p.msg_max + 1);   // degree-1 row
+        min2 = min(min2, u.msg_max + 1);
         int c1, c2;
-        if (p.rule == QLDPC_RULE_OMS) { c1 = max(min2 - p.offset_int, 0); c2 = max(min1 - p.offset_int, 0); }
-        else { c1 = norm8(min2, p.norm_eighths); c2 = norm8(min1, p.norm_eighths); }
+        if (u.rule == QLDPC_RULE_OMS) { c1 = max(min2 - u.offset_int, 0); c2 = max(min1 - u.offset_int, 0); }
+        else { c1 = norm8(min2, u.norm_eighths); c2 = norm8(min1, u.norm_eighths); }
         for (int j = 0; j < dc; ++j) {
-            const QcEdgeAux ax = aux[e0 + j];
-            int l = i + ax.shift; if (l >= Z) l -= Z;
-            const int contrib = L[ax.col * Z + l] - R[(e0 + j) * Z + i];
-            const int t = clipi(contrib, lo, hi);
+            const int c = contrib(j, at);
+            const int t = clipi(c, lo, hi);
             const int mag = (abs(t) == min1) ? c1 : c2;
             const int out = (sign ^ (t < 0)) ? -mag : mag;
-            R[(e0 + j) * Z + i] = out;
-            L[ax.col * Z + l] = clipi(contrib + out, -(p.app_max + 1), p.app_max);
+            Rl[j * Z] = (MT)out;
+            L[at] = (LT)clipi(c + out, -(u.app_max + 1), u.app_max);
         }
     }
 }
 
-template <typename T, typename IN>
-__global__ void __launch_bounds__(1024, 1) layered_generic_kernel(const LayeredGenParams p)
+template <typename LT, typename MT>
+__device__ __forceinline__ void row_dispatch(const Upd u, const RowMeta ly, LT *L, MT *Rl, const int2 *ed, int lane, int Z, int synbit,
+                                             bool first)
 {
-    const int tid = threadIdx.x, nt = blockDim.x, Z = p.Z;
-    T *L = reinterpret_cast<T *>(p.app) + (size_t)blockIdx.x * p.N;
-    T *R = reinterpret_cast<T *>(p.msg) + (size_t)blockIdx.x * p.nnz * Z;
-    constexpr bool kFloat = std::is_floating_point<T>::value;
+#define QL_DC(D) case D: row_lane<LT, MT, D>(u, L, Rl, ed, lane, Z, synbit, first); return;
+    switch (ly.degree) {   // block-uniform: no divergence
+        QL_DC(1) QL_DC(2) QL_DC(3) QL_DC(4) QL_DC(5) QL_DC(6) QL_DC(7) QL_DC(8) QL_DC(9) QL_DC(10)
+        QL_DC(11) QL_DC(12) QL_DC(13) QL_DC(14) QL_DC(15) QL_DC(16) QL_DC(17) QL_DC(18) QL_DC(19) QL_DC(20)
+    default: break;
+    }
+#undef QL_DC
+    static_assert(kMaxDc == 20, "row_dispatch lists the compiled degrees");
+    row_lane_any<LT, MT>(u, L, Rl, ed, ly.degree, lane, Z, synbit, first);
+}
+
+__device__ __forceinline__ int syn_bit(const uint32_t *syn, int m) { return syn ? (int)((syn[m >> 5] >> (31 - (m & 31))) & 1u) : 0; }
+
+// Shared memory: RowMeta rows[brows]; int2 edges[nnz]; LT L[N].
+// MAXT / MINB: launch bounds of the instantiation (threads per CTA = Z rounded up to a warp, at most MAXT).
+template <typename LT, typename MT, typename IN, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) layered_generic_kernel(const LayeredGenParams p)
+{
+    extern __shared__ __align__(16) char smem[];
+    constexpr bool kFloat = std::is_floating_point<LT>::value;
+    const int tid = threadIdx.x, nt = blockDim.x, Z = p.Z, R = p.brows;
+    RowMeta *rows = reinterpret_cast<RowMeta *>(smem);
+    int2 *edges = reinterpret_cast<int2 *>(rows + R);
+    LT *L = p.app ? reinterpret_cast<LT *>(p.app) + (size_t)blockIdx.x * p.N : reinterpret_cast<LT *>(edges + p.nnz);
+    for (int r = tid; r < R; r += nt) rows[r] = RowMeta{p.layers[r].edge_begin, p.layers[r].degree};
+    for (int e = tid; e < p.nnz; e += nt) edges[e] = make_int2(p.aux[e].col * Z, p.aux[e].shift);
+    MT *Rg = reinterpret_cast<MT *>(p.msg) + (size_t)blockIdx.x * p.nnz * Z;
+    const Upd upd{p.rule, p.offset_int, p.norm_eighths, p.msg_max, p.app_max, p.norm, p.offset};
+
+    // syndrome of the hard decisions (beliefs in shared memory), OR over the block
+    auto syndrome_bad = [&](const uint32_t *syn) {
+        int bad = 0;
+        for (int r = 0; r < R; ++r) {
+            const RowMeta ly = rows[r];
+            for (int i = tid; i < Z; i += nt) {
+                unsigned s = (unsigned)syn_bit(syn, r * Z + i);
+                for (int j = 0; j < ly.degree; ++j) {
+                    const int2 e = edges[ly.edge_begin + j];
+                    int l = i + e.y;
+                    if (l >= Z) l -= Z;
+                    s ^= (unsigned)(L[e.x + l] < (LT)0);
+                }
+                bad |= (int)(s & 1u);
+            }
+        }
+        return __syncthreads_or(bad) != 0;
+    };
 
     for (int f = blockIdx.x; f < p.F; f += gridDim.x) {
         const IN *llr = reinterpret_cast<const IN *>(p.llr) + (size_t)f * p.N;
         const uint32_t *syn = p.syn ? p.syn + (size_t)f * p.syn_words : nullptr;
-        for (int v = tid; v < p.N; v += nt) L[v] = (T)llr[v];
-        for (int e = tid; e < p.nnz * Z; e += nt) R[e] = (T)0;
+        __syncthreads();                                   // tables written / previous frame's beliefs no longer read
+        for (int v = tid; v < p.N; v += nt) L[v] = (LT)llr[v];
         __syncthreads();
 
         int it = 0, depth = 0;
         bool ok = false, checked = false;
         while (it < p.max_iter) {
-            for (int r = 0; r < p.brows; ++r) {
-                const QcLayer ly = p.layers[r];
+            for (int r = 0; r < R; ++r) {
+                const RowMeta ly = rows[r];
                 for (int i = tid; i < Z; i += nt)
-                    layer_lane<T>(p, L, R, p.aux, ly.edge_begin, ly.degree, i, syn_bit(syn, r * Z + i));
+                    row_dispatch<LT, MT>(upd, ly, L, Rg + ((size_t)ly.edge_begin * Z + i), edges + ly.edge_begin, i, Z,
+                                         syn_bit(syn, r * Z + i), it == 0);
                 __syncthreads();
             }
             ++it;
@@ -137,46 +283,20 @@ __global__ void __launch_bounds__(1024, 1) layered_generic_kernel(const LayeredG
             // float tiers: AFF3CT skips the check after the last iteration and honours syndrome_depth
             const bool want = p.early_stop && (kFloat ? it != p.max_iter : true);
             if (want) {
-                int bad = 0;
-                for (int m = tid; m < p.M; m += nt) {
-                    const int r = m / Z, i = m - r * Z;
-                    const QcLayer ly = p.layers[r];
-                    unsigned s = (unsigned)syn_bit(syn, m);
-                    for (int j = 0; j < ly.degree; ++j) {
-                        const QcEdgeAux ax = p.aux[ly.edge_begin + j];
-                        int l = i + ax.shift; if (l >= Z) l -= Z;
-                        s ^= (unsigned)(L[ax.col * Z + l] < (T)0);
-                    }
-                    bad |= (int)(s & 1u);
-                }
-                ok = __syncthreads_or(bad) == 0;
+                ok = !syndrome_bad(syn);
                 checked = true;
                 if (ok) { if (!kFloat || ++depth >= p.syndrome_depth) break; }
                 else depth = 0;
             }
         }
-        if (!checked) {
-            int bad = 0;
-            for (int m = tid; m < p.M; m += nt) {
-                const int r = m / Z, i = m - r * Z;
-                const QcLayer ly = p.layers[r];
-                unsigned s = (unsigned)syn_bit(syn, m);
-                for (int j = 0; j < ly.degree; ++j) {
-                    const QcEdgeAux ax = p.aux[ly.edge_begin + j];
-                    int l = i + ax.shift; if (l >= Z) l -= Z;
-                    s ^= (unsigned)(L[ax.col * Z + l] < (T)0);
-                }
-                bad |= (int)(s & 1u);
-            }
-            ok = __syncthreads_or(bad) == 0;
-        }
+        if (!checked) ok = !syndrome_bad(syn);
 
         uint32_t *ab = p.allbits + (size_t)f * p.cw_words;
         for (int w = tid; w < p.cw_words; w += nt) {
             uint32_t v = 0;
             for (int b = 0; b < 32; ++b) {
                 const int idx = 32 * w + b;
-                if (idx < p.N && L[idx] < (T)0) v |= 1u << (31 - b);
+                if (idx < p.N && L[idx] < (LT)0) v |= 1u << (31 - b);
             }
             ab[w] = v;
         }
@@ -186,7 +306,7 @@ __global__ void __launch_bounds__(1024, 1) layered_generic_kernel(const LayeredG
                 for (int v = tid; v < p.N; v += nt) po[v] = L[v];
             } else {
                 int *po = reinterpret_cast<int *>(p.posterior) + (size_t)f * p.N;
-                for (int v = tid; v < p.N; v += nt) po[v] = L[v];
+                for (int v = tid; v < p.N; v += nt) po[v] = (int)L[v];
             }
         }
         if (tid == 0) {
@@ -199,25 +319,71 @@ __global__ void __launch_bounds__(1024, 1) layered_generic_kernel(const LayeredG
                 atomicAdd(&p.stats->hist[min(it, QLDPC_ITER_HIST_BINS - 1)], 1ull);
             }
         }
-        __syncthreads();
     }
+}
+
+int block_threads(int Z) { return std::min(1024, std::max(64, (Z + 31) / 32 * 32)); }
+
+// the instantiation for a (tier, block size): 128 threads x 4 blocks, 384 x 2, or 1024 x 1 per SM as the register budget
+#define QL_GEN_KERNELS(X, LT, MT, IN)                                   \
+    X(128, (layered_generic_kernel<LT, MT, IN, 128, 4>))               \
+    X(384, (layered_generic_kernel<LT, MT, IN, 384, 2>))               \
+    X(1024, (layered_generic_kernel<LT, MT, IN, 1024, 1>))
+
+template <typename K>
+int occupancy_k(K kern, int block, int smem_bytes)
+{
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, block, (size_t)smem_bytes) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+template <typename K>
+int launch_k(K kern, const LayeredGenParams &p, int grid, int block, int smem_bytes, cudaStream_t st)
+{
+    QLDPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    kern<<<grid, block, smem_bytes, st>>>(p);
+    QLDPC_CUDA(cudaGetLastError());
+    return QLDPC_OK;
 }
 
 }  // namespace
 
+int layered_generic_belief_bytes(int dtype) { return dtype == QLDPC_DTYPE_F32 ? 4 : 2; }
+int layered_generic_msg_bytes(int dtype) { return dtype == QLDPC_DTYPE_F32 ? 4 : 2; }
+int layered_generic_smem_bytes(int brows, int nnz, int N, int dtype)
+{
+    return (brows * 8 + nnz * 8 + N * layered_generic_belief_bytes(dtype) + 15) / 16 * 16;
+}
+
+// co-resident CTAs per SM of the instantiation that serves (dtype, Z); 0: the beliefs do not fit in shared memory
+int layered_generic_blocks_per_sm(int dtype, int Z, int smem_bytes)
+{
+    const int block = block_threads(Z);
+#define QL_X(T, K) if (block <= T) return occupancy_k(K, block, smem_bytes);
+    switch (dtype) {
+    case QLDPC_DTYPE_F32: QL_GEN_KERNELS(QL_X, float, float, float) break;
+    case QLDPC_DTYPE_I16: QL_GEN_KERNELS(QL_X, int16_t, int16_t, int16_t) break;
+    case QLDPC_DTYPE_I8: QL_GEN_KERNELS(QL_X, int16_t, int16_t, int8_t) break;
+    default: break;
+    }
+#undef QL_X
+    return 0;
+}
+
 int launch_layered_generic(const LayeredGenParams &p, int grid, cudaStream_t st)
 {
-    int block = ((p.Z + 31) / 32) * 32;
-    if (block > 1024) block = 1024;
-    if (block < 64) block = 64;
+    const int block = block_threads(p.Z);
+    const int smem = layered_generic_smem_bytes(p.brows, p.nnz, p.app ? 0 : p.N, p.dtype);
+#define QL_X(T, K) if (block <= T) return launch_k(K, p, grid, block, smem, st);
     switch (p.dtype) {
-    case QLDPC_DTYPE_F32: layered_generic_kernel<float, float><<<grid, block, 0, st>>>(p); break;
-    case QLDPC_DTYPE_I16: layered_generic_kernel<int, int16_t><<<grid, block, 0, st>>>(p); break;
-    case QLDPC_DTYPE_I8: layered_generic_kernel<int, int8_t><<<grid, block, 0, st>>>(p); break;
-    default: return QLDPC_ERR_UNSUPPORTED;
+    case QLDPC_DTYPE_F32: QL_GEN_KERNELS(QL_X, float, float, float) break;
+    case QLDPC_DTYPE_I16: QL_GEN_KERNELS(QL_X, int16_t, int16_t, int16_t) break;
+    case QLDPC_DTYPE_I8: QL_GEN_KERNELS(QL_X, int16_t, int16_t, int8_t) break;
+    default: break;
     }
-    QLDPC_CUDA(cudaGetLastError());
-    return QLDPC_OK;
+#undef QL_X
+    return QLDPC_ERR_UNSUPPORTED;
 }
 
 }  // namespace qldpc

@@ -650,7 +650,7 @@ extern "C" int qldpc_decoder_create(const qldpc_code *code, const qldpc_decoder_
             int smem = layered_generic_smem_bytes(c.base_rows, nnz, c.n, cfg->dtype);
             d->gen_beliefs_global = smem > d->max_smem_optin;
             if (d->gen_beliefs_global) smem = layered_generic_smem_bytes(c.base_rows, nnz, 0, cfg->dtype);
-            const int per_sm = layered_generic_blocks_per_sm(cfg->dtype, c.z, smem);
+            const int per_sm = layered_generic_blocks_per_sm(cfg->dtype, c.z, smem, d->gen_beliefs_global);
             if (per_sm < 1) return bail(QLDPC_ERR_UNSUPPORTED);
             d->gen_grid = d->sm_count * per_sm;
             d->scratch_msg_bytes = (size_t)d->gen_grid * c.edges * layered_generic_msg_bytes(cfg->dtype);

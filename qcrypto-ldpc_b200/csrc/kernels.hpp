@@ -102,7 +102,7 @@ struct LayeredGenParams {
 int layered_generic_belief_bytes(int dtype);
 int layered_generic_msg_bytes(int dtype);
 int layered_generic_smem_bytes(int brows, int nnz, int N, int dtype);       // N = 0: tables only (beliefs in global memory)
-int layered_generic_blocks_per_sm(int dtype, int Z, int smem_bytes);
+int layered_generic_blocks_per_sm(int dtype, int Z, int smem_bytes, int beliefs_global);
 int launch_layered_generic(const LayeredGenParams &p, int grid, cudaStream_t st);
 
 // ---- layered, any H (CSR), float: one thread per frame (layered_csr.cu) ------------------------------------------

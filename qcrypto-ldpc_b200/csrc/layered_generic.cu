@@ -20,6 +20,8 @@
 //   registers: L - R_old of the row in flight (and tanh for SPA), the row code is compiled per row degree.
 // A row costs one global round trip (its old messages, all dc loads in flight together) instead of the 2 dc dependent ones
 // of the first version (tables, beliefs and messages all behind L2); several CTAs per SM overlap their round trips.
+// Measured and dropped: loading a row's old messages one row ahead into a fixed 20-slot register array (predicated slots
+// + spills at 80 registers: BG1 i16 8.5 -> 5.3 Gbit/s), and capping the CTAs per SM so that the scratch fits in L2.
 #include <type_traits>
 
 #include "kernels.hpp"
@@ -227,7 +229,8 @@ __device__ __forceinline__ int syn_bit(const uint32_t *syn, int m) { return syn 
 
 // Shared memory: RowMeta rows[brows]; int2 edges[nnz]; LT L[N].
 // MAXT / MINB: launch bounds of the instantiation (threads per CTA = Z rounded up to a warp, at most MAXT).
-template <typename LT, typename MT, typename IN, int MAXT, int MINB>
+// GL: the beliefs of a frame do not fit in shared memory and live in a global scratch (p.app) instead.
+template <typename LT, typename MT, typename IN, int MAXT, int MINB, bool GL>
 __global__ void __launch_bounds__(MAXT, MINB) layered_generic_kernel(const LayeredGenParams p)
 {
     extern __shared__ __align__(16) char smem[];
@@ -235,7 +238,9 @@ __global__ void __launch_bounds__(MAXT, MINB) layered_generic_kernel(const Layer
     const int tid = threadIdx.x, nt = blockDim.x, Z = p.Z, R = p.brows;
     RowMeta *rows = reinterpret_cast<RowMeta *>(smem);
     int2 *edges = reinterpret_cast<int2 *>(rows + R);
-    LT *L = p.app ? reinterpret_cast<LT *>(p.app) + (size_t)blockIdx.x * p.N : reinterpret_cast<LT *>(edges + p.nnz);
+    LT *L;
+    if constexpr (GL) L = reinterpret_cast<LT *>(p.app) + (size_t)blockIdx.x * p.N;
+    else L = reinterpret_cast<LT *>(edges + p.nnz);     // no select with a global pointer here: the accesses stay LDS / STS
     for (int r = tid; r < R; r += nt) rows[r] = RowMeta{p.layers[r].edge_begin, p.layers[r].degree};
     for (int e = tid; e < p.nnz; e += nt) edges[e] = make_int2(p.aux[e].col * Z, p.aux[e].shift);
     MT *Rg = reinterpret_cast<MT *>(p.msg) + (size_t)blockIdx.x * p.nnz * Z;
@@ -325,10 +330,11 @@ __global__ void __launch_bounds__(MAXT, MINB) layered_generic_kernel(const Layer
 int block_threads(int Z) { return std::min(1024, std::max(64, (Z + 31) / 32 * 32)); }
 
 // the instantiation for a (tier, block size): 128 threads x 4 blocks, 384 x 2, or 1024 x 1 per SM as the register budget
-#define QL_GEN_KERNELS(X, LT, MT, IN)                                   \
-    X(128, (layered_generic_kernel<LT, MT, IN, 128, 4>))               \
-    X(384, (layered_generic_kernel<LT, MT, IN, 384, 2>))               \
-    X(1024, (layered_generic_kernel<LT, MT, IN, 1024, 1>))
+#define QL_GEN_KERNELS(X, LT, MT, IN)                                          \
+    X(128, false, (layered_generic_kernel<LT, MT, IN, 128, 4, false>))        \
+    X(384, false, (layered_generic_kernel<LT, MT, IN, 384, 2, false>))        \
+    X(1024, false, (layered_generic_kernel<LT, MT, IN, 1024, 1, false>))      \
+    X(1024, true, (layered_generic_kernel<LT, MT, IN, 1024, 1, true>))
 
 template <typename K>
 int occupancy_k(K kern, int block, int smem_bytes)
@@ -357,10 +363,11 @@ int layered_generic_smem_bytes(int brows, int nnz, int N, int dtype)
 }
 
 // co-resident CTAs per SM of the instantiation that serves (dtype, Z); 0: the beliefs do not fit in shared memory
-int layered_generic_blocks_per_sm(int dtype, int Z, int smem_bytes)
+int layered_generic_blocks_per_sm(int dtype, int Z, int smem_bytes, int beliefs_global)
 {
     const int block = block_threads(Z);
-#define QL_X(T, K) if (block <= T) return occupancy_k(K, block, smem_bytes);
+    const bool gl = beliefs_global != 0;
+#define QL_X(T, G, K) if (block <= T && gl == G) return occupancy_k(K, block, smem_bytes);
     switch (dtype) {
     case QLDPC_DTYPE_F32: QL_GEN_KERNELS(QL_X, float, float, float) break;
     case QLDPC_DTYPE_I16: QL_GEN_KERNELS(QL_X, int16_t, int16_t, int16_t) break;
@@ -375,7 +382,8 @@ int launch_layered_generic(const LayeredGenParams &p, int grid, cudaStream_t st)
 {
     const int block = block_threads(p.Z);
     const int smem = layered_generic_smem_bytes(p.brows, p.nnz, p.app ? 0 : p.N, p.dtype);
-#define QL_X(T, K) if (block <= T) return launch_k(K, p, grid, block, smem, st);
+    const bool gl = p.app != nullptr;
+#define QL_X(T, G, K) if (block <= T && gl == G) return launch_k(K, p, grid, block, smem, st);
     switch (p.dtype) {
     case QLDPC_DTYPE_F32: QL_GEN_KERNELS(QL_X, float, float, float) break;
     case QLDPC_DTYPE_I16: QL_GEN_KERNELS(QL_X, int16_t, int16_t, int16_t) break;

@@ -52,7 +52,8 @@ def main():
         if not os.path.exists(path):
             continue
         code = q.Code.from_alist(path) if fname.endswith(".alist") else q.Code.from_qc_file(path)
-        N, E, F = code.n, code.edges, args.frames
+        # the layered schedule on a general H is parallel ACROSS frames (one thread per frame): give it a GPU-sized batch
+        N, E, F = code.n, code.edges, (args.frames * 16 if fname.endswith(".alist") else args.frames)
         g = torch.Generator(device=dev)
         g.manual_seed(1)
         Np = (N + 31) // 32 * 32

@@ -118,3 +118,84 @@ def test_n65536_fixed_point_flooding_vs_oracle(q, O, data_dir, dtype, rule):
         assert (post[f] == opost).all()
     assert ok.all()
     dec.close()
+
+
+IRREGULAR = "qkd_irregular_n65536_r34.qc"
+
+
+@pytest.mark.parametrize("tier", ["spa", "nms", "i8", "i16"])
+def test_n65536_irregular_rate34_flooding_vs_oracle(q, O, data_dir, tier):
+    """the irregular rate-3/4 code (Z = 1024, row degrees 17 / 18): heavy rows take the 2-lanes-per-thread instantiation of the
+    clustered kernel, whose per-degree code paths the (3,6) code never reaches"""
+    path = "%s/%s" % (data_dir, IRREGULAR)
+    oc = O.Code.from_qc(path)
+    assert (oc.N, oc.M) == (65536, 16384)
+    code = q.Code.from_qc_file(path)
+    F, qber, n_ite = 3, 0.025, 25
+    rng = np.random.default_rng(34)
+    x = rng.integers(0, 2, (F, oc.N)).astype(np.uint8)
+    y = x ^ (rng.random((F, oc.N)) < qber)
+    if tier in ("spa", "nms"):
+        qr, orr, norm = (q.RULE_SPA, O.RULE_SPA, 1.0) if tier == "spa" else (q.RULE_NMS, O.RULE_NMS, 0.8125)
+        dec = q.Decoder(code, schedule=q.SCHED_FLOODING, rule=qr, dtype=q.DTYPE_F32, max_iter=n_ite, early_stop=True,
+                        norm_factor=norm, out_mode=q.OUT_ALL)
+        assert dec.kernel_name == "flooding_qc_cluster"
+        syn_p = dec.syndrome(q.pack_bits(x))
+        mag = float(np.log((1 - qber) / qber))
+        llr = np.where(y, -mag, mag).astype(np.float32)
+        out, ok, iters, post = dec.decode(llr, syn_p, want_posterior=True)
+        hard, opost, oit, ook, _ = oc.batch_flooding_f32(llr, q.unpack_bits(syn_p, oc.M), rule=orr, n_ite=n_ite, early_stop=True,
+                                                         norm=norm)
+        assert (q.unpack_bits(out, oc.N) == hard).all() and (iters == oit).all() and (ok == ook).all()
+        np.testing.assert_allclose(post, opost, rtol=1e-3, atol=1e-4)
+    else:
+        dt, mag, vmax = (q.DTYPE_I8, 14, 127) if tier == "i8" else (q.DTYPE_I16, 230, 32767)
+        dec = q.Decoder(code, schedule=q.SCHED_FLOODING, rule=q.RULE_NMS, dtype=dt, max_iter=n_ite, early_stop=True,
+                        norm_factor=0.75, out_mode=q.OUT_ALL)
+        assert dec.kernel_name == "flooding_qc_cluster"
+        syn_p = dec.syndrome(q.pack_bits(x))
+        syn = q.unpack_bits(syn_p, oc.M)
+        llr = np.where(y, -mag, mag)
+        out, ok, iters, post = dec.decode(llr.astype(dec.np_dtype), syn_p, want_posterior=True)
+        for f in range(F):
+            hard, opost, oit, ook = oc.decode_flooding_fixed(llr[f], syn[f], rule=O.RULE_NMS, n_ite=n_ite, early_stop=True,
+                                                             norm_eighths=6, vmax=vmax)
+            assert (q.unpack_bits(out[f:f + 1], oc.N)[0] == hard).all() and iters[f] == oit and ok[f] == ook
+            assert (post[f] == opost).all()
+    assert ok.all() and (q.unpack_bits(out, oc.N) == x).all()
+    dec.close()
+
+
+@pytest.mark.parametrize("tier", ["f32", "i16"])
+def test_n65536_layered_schedule_on_the_long_block(q, O, data_dir, tier):
+    """the generic layered kernel outside its comfortable sizes: Z = 2048 lanes on 1024 threads, and (float) a frame whose
+    beliefs (262 KB) do not fit in shared memory and live in the global scratch instead"""
+    path = "%s/%s" % (data_dir, CODE)
+    oc = O.Code.from_qc(path)
+    code = q.Code.from_qc_file(path)
+    F = 2
+    rng = np.random.default_rng(5)
+    x = rng.integers(0, 2, (F, oc.N)).astype(np.uint8)
+    y = x ^ (rng.random((F, oc.N)) < 0.04)
+    syn = np.stack([oc.syndrome(x[f]) for f in range(F)])
+    if tier == "f32":
+        dec = q.Decoder(code, schedule=q.SCHED_LAYERED, rule=q.RULE_NMS, dtype=q.DTYPE_F32, max_iter=12, norm_factor=0.8125,
+                        out_mode=q.OUT_ALL)
+        llr = np.where(y, -3.1, 3.1).astype(np.float32)
+    else:
+        dec = q.Decoder(code, schedule=q.SCHED_LAYERED, rule=q.RULE_OMS, dtype=q.DTYPE_I16, max_iter=12, offset=8.0,
+                        out_mode=q.OUT_ALL)
+        llr = np.where(y, -111, 111).astype(np.int16)
+    assert dec.kernel_name == "layered_generic"
+    out, ok, iters, post = dec.decode(llr, q.pack_bits(syn), want_posterior=True)
+    for f in range(F):
+        if tier == "f32":
+            h, p, it, o = oc.decode_layered_f32(llr[f], syn[f], rule=O.RULE_NMS, n_ite=12, early_stop=True, norm=0.8125)
+            np.testing.assert_allclose(post[f], p, rtol=1e-3, atol=1e-4)
+        else:
+            h, p, it, o = oc.decode_layered_fixed(llr[f].astype(np.int32), syn[f], rule=O.RULE_OMS, n_ite=12, early_stop=True,
+                                                  offset=8, msg_max=511, app_max=8191)
+            assert (post[f] == p).all()
+        assert (q.unpack_bits(out[f:f + 1], oc.N)[0] == h).all() and iters[f] == it and ok[f] == o
+    assert ok.all()
+    dec.close()

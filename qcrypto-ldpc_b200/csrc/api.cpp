@@ -944,6 +944,7 @@ static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint3
         p.offset_int = d->offset_int; p.norm_eighths = d->norm_eighths;
         p.vmax = cfg.dtype == QLDPC_DTYPE_I16 ? 32767 : 127;
         p.use_smem = d->flood_use_smem;
+        p.fast_spa = (cfg.flags & QLDPC_FLAG_FAST_SPA) ? 1 : 0;
         if (d->qcx_cl > 0) {
             FloodQcxParams xp{};
             xp.llr = d_llr; xp.syn = d_syndrome; xp.allbits = allbits; xp.ok = d_ok; xp.iters = d_iters;

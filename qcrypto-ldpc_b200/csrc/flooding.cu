@@ -14,6 +14,7 @@
 #include <type_traits>
 
 #include "kernels.hpp"
+#include "spa_math.cuh"
 
 namespace qldpc {
 
@@ -47,11 +48,14 @@ __device__ __forceinline__ void check_update_f32(const FloodParams &p, const flo
                                                  int synbit, float *tcache, int tstride)
 {
     int sign = synbit;
+    // exact: tanh / atanh in double, rounded once (bit-exact with the oracle); QLDPC_FLAG_FAST_SPA: fp32 on the SFUs
+    auto th = [&](float a) { return p.fast_spa ? tanh_half_fast(a) : (float)tanh((double)(a * 0.5f)); };
+    auto ath2 = [&](float r) { return p.fast_spa ? two_atanh_fast(r) : 2.0f * (float)atanh((double)r); };
     if (p.rule == QLDPC_RULE_SPA) {
         float product = 1.0f;
         for (int e = e0; e < e1; ++e) {
             const float x = post[p.col_idx[e]] - c2v[e];
-            const float t = (float)tanh((double)(fabsf(x) * 0.5f));
+            const float t = th(fabsf(x));
             if (tcache && e - e0 < kTanhCache) tcache[(e - e0) * tstride] = signbit(x) ? -t : t;   // t >= 0; -0.0f keeps the sign
             product *= (t != 0.0f) ? t : 1e-12f;
             sign ^= signbit(x) ? 1 : 0;
@@ -65,12 +69,12 @@ __device__ __forceinline__ void check_update_f32(const FloodParams &p, const flo
                 sx = signbit(ts) ? 1 : 0;
             } else {
                 const float x = post[p.col_idx[e]] - c2v[e];
-                t = (float)tanh((double)(fabsf(x) * 0.5f));
+                t = th(fabsf(x));
                 sx = signbit(x) ? 1 : 0;
             }
             float r = product / ((t != 0.0f) ? t : 1e-12f);
             r = (r < 1.0f) ? r : 1.0f - 1.1920929e-07f;
-            const float mag = 2.0f * (float)atanh((double)r);
+            const float mag = ath2(r);
             c2v[e] = sgn_apply(mag, sign ^ sx);
         }
     } else {

@@ -145,6 +145,7 @@ struct FloodParams {
     int offset_int, norm_eighths, vmax;
     int use_smem;             // messages + posteriors in shared memory
     int tanh_cache;           // !use_smem, float SPA: 8 * block floats of shared memory cache tanh between the two passes
+    int fast_spa;             // SPA transcendentals in fp32 on the SFUs instead of double (QLDPC_FLAG_FAST_SPA)
 };
 int launch_flooding(const FloodParams &p, int grid, int block, int smem_bytes, cudaStream_t st);
 

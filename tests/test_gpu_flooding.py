@@ -192,3 +192,31 @@ def test_config1_n1944_spa_flooding_vs_oracle(q, O, data_dir):
     assert (iters == oit).all() and (ok == ook).all() and ok.all()
     np.testing.assert_allclose(post, opost, rtol=RTOL, atol=1e-4)
     dec.close()
+
+
+@pytest.mark.parametrize("name,qber", [("PEGReg504x1008.alist", 0.05), ("wifi_n1944_r12.qc", 0.03), ("1998.5.3.2665.alist", 0.008)])
+def test_fast_spa_flavour_on_the_general_flooding_kernel(q, O, data_dir, kat, name, qber):
+    """QLDPC_FLAG_FAST_SPA (fp32 tanh / atanh on the special-function units) on flooding_csr: the reference's KAT decodes to
+    the same word after the same 6 sweeps; on random batches the decoded bits, flags and iteration counts equal the exact
+    flavour's (= the oracle's), posteriors within 1e-3 except for saturated messages"""
+    path = "%s/%s" % (data_dir, name)
+    alist = name.endswith(".alist")
+    oc = O.Code.from_alist(path) if alist else O.Code.from_qc(path)
+    code = q.Code.from_alist(path) if alist else q.Code.from_qc_file(path)
+    fast = q.Decoder(code, schedule=q.SCHED_FLOODING, rule=q.RULE_SPA, dtype=q.DTYPE_F32, max_iter=20, early_stop=True,
+                     out_mode=q.OUT_ALL, flags=q.FLAG_FAST_SPA)
+    if name.startswith("PEGReg"):
+        out, ok, iters, _ = fast.decode(np.array([kat["llrs"]], dtype=np.float32))
+        assert ok[0] and iters[0] == 6
+        assert (q.unpack_bits(out, oc.N)[0][oc.N - 504:] == np.array(kat["decoded"], dtype=np.uint8)).all()
+    F = 64
+    llr, syn, x = _bsc_llr_frames(oc, F, qber, seed=11)
+    out, ok, iters, post = fast.decode(llr, q.pack_bits(syn), want_posterior=True)
+    hard, opost, oit, ook, _ = oc.batch_flooding_f32(llr, syn, rule=O.RULE_SPA, n_ite=20, early_stop=True)
+    assert (q.unpack_bits(out, oc.N) == hard).all() and (iters == oit).all() and (ok == ook).all()
+    dev = np.abs(post - opost)
+    outside = dev > 1e-3 * np.abs(opost) + 1e-4
+    # what falls outside 1e-3: saturated messages (one last-bit difference in 1 - r), or a posterior that is the small
+    # difference of large terms (absolute deviation still below 1e-2)
+    assert outside.mean() < 2e-3 and dev.max() < 1.5 and ((np.abs(opost[outside]) > 15) | (dev[outside] < 1e-2)).all()
+    fast.close()

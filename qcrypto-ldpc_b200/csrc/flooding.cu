@@ -49,8 +49,8 @@ __device__ __forceinline__ void check_update_f32(const FloodParams &p, const flo
 {
     int sign = synbit;
     // exact: tanh / atanh in double, rounded once (bit-exact with the oracle); QLDPC_FLAG_FAST_SPA: fp32 on the SFUs
-    auto th = [&](float a) { return p.fast_spa ? tanh_half_fast(a) : (float)tanh((double)(a * 0.5f)); };
-    auto ath2 = [&](float r) { return p.fast_spa ? two_atanh_fast(r) : 2.0f * (float)atanh((double)r); };
+    auto th = [&](float a) { return p.fast_spa ? tanh_half_fast(a) : tanh_half_exact(a); };
+    auto ath2 = [&](float r) { return p.fast_spa ? two_atanh_fast(r) : two_atanh_exact(r); };
     if (p.rule == QLDPC_RULE_SPA) {
         float product = 1.0f;
         for (int e = e0; e < e1; ++e) {

@@ -12,6 +12,7 @@
 // No col_idx / var_edge index loads, no scattered 4-byte gathers.  One CTA per frame in flight; messages and posteriors
 // in shared memory when they fit, else in a per-CTA global scratch.
 #include "kernels.hpp"
+#include "spa_math.cuh"
 
 #ifndef QL_FQ_THREADS
 #define QL_FQ_THREADS 1024
@@ -26,7 +27,7 @@ namespace {
 
 __device__ __forceinline__ float spa_t(float x)
 {
-    const float t = (float)tanh((double)(fabsf(x) * 0.5f));
+    const float t = tanh_half_exact(fabsf(x));
     return (t != 0.0f) ? t : 1e-12f;
 }
 
@@ -69,7 +70,7 @@ __device__ __forceinline__ int check_row(const FloodQcParams &p, const QcLayer l
                 const float xv = MAXD > 0 ? x[j] : v2c(j);
                 float rr = product / spa_t(xv);
                 rr = (rr < 1.0f) ? rr : 1.0f - 1.1920929e-07f;
-                const float mag = 2.0f * (float)atanh((double)rr);
+                const float mag = two_atanh_exact(rr);
                 cm[(size_t)j * Z] = (sign ^ (signbit(xv) ? 1 : 0)) ? -mag : mag;
             }
         }

@@ -47,8 +47,6 @@ constexpr int kMaxDcV2 = 20;         // compiled row degrees; heavier rows take 
 //     within 1e-3 of the reference.
 //   fast: fp32 on the special-function units.  Decoded bits and iteration counts equal the exact flavour's on every test
 //     batch; 99.99 % of the posteriors are within 1e-3, the rest (saturated messages) within ln 2.
-__device__ __noinline__ float tanh_half_exact(float a) { return (float)tanh((double)(a * 0.5f)); }
-__device__ __noinline__ float two_atanh_exact(float r) { return 2.0f * (float)atanh((double)r); }
 __device__ __forceinline__ int norm8(int v, int k)
 {
     switch (k) {

@@ -11,6 +11,7 @@
 // 128-byte line and the row tables are warp-uniform broadcast loads.  A thread leaves the iteration loop when its frame
 // has converged.  tanh / atanh in double, rounded once, as in the other bit-exact float kernels.
 #include "kernels.hpp"
+#include "spa_math.cuh"
 
 namespace qldpc {
 
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(128) layered_csr_kernel(const LayeredCsrParams
                     const float a = fabsf(x);
                     sign ^= signbit(x) ? 1 : 0;
                     if (p.rule == QLDPC_RULE_SPA) {
-                        const float th = (float)tanh((double)(a * 0.5f));
+                        const float th = tanh_half_exact(a);
                         const float r = (th != 0.0f) ? th : 1e-12f;
                         product *= r;
                         vals[j] = r;
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(128) layered_csr_kernel(const LayeredCsrParams
                     if (p.rule == QLDPC_RULE_SPA) {
                         float r = product / vals[j];
                         r = (r < 1.0f) ? r : 1.0f - 1.1920929e-07f;
-                        mag = 2.0f * (float)atanh((double)r);
+                        mag = two_atanh_exact(r);
                     } else {
                         mag = (fabsf(x) == min1) ? cst1 : cst2;
                     }

@@ -25,6 +25,7 @@
 #include <type_traits>
 
 #include "kernels.hpp"
+#include "spa_math.cuh"
 
 namespace qldpc {
 
@@ -50,8 +51,8 @@ __device__ __forceinline__ int norm8(int v, int k)
     }
 }
 __device__ __forceinline__ int clipi(int x, int lo, int hi) { return min(max(x, lo), hi); }
-__device__ __noinline__ float tanh_half(float a) { return (float)tanh((double)(a * 0.5f)); }
-__device__ __noinline__ float two_atanh(float r) { return 2.0f * (float)atanh((double)r); }
+__device__ __forceinline__ float tanh_half(float a) { return tanh_half_exact(a); }       // spa_math.cuh
+__device__ __forceinline__ float two_atanh(float r) { return two_atanh_exact(r); }
 
 // One check (block row with DC edges starting at `ed`, check lane `lane`): beliefs in shared memory, old messages at
 // Rl[j * Z] (not read when `first`), new messages and beliefs written back.

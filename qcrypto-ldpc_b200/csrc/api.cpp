@@ -1,5 +1,6 @@
 // C ABI of libqldpc_b200 (see include/qldpc.h for the reference interface each entry point replaces).
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <vector>
@@ -1431,13 +1432,22 @@ extern "C" int qldpc_version(void) { return QLDPC_VERSION; }
 
 static int select_sm100_device(int device)
 {
+    // the verdict per device is remembered: cudaGetDeviceProperties costs milliseconds, and the post-processing entry
+    // points are called once per key block
+    static std::atomic<int> verdict[64];                 // 0 unknown, 1 ok, 2 not an sm_100 device
+    if (device < 0) return QLDPC_ERR_ARG;
+    if (device < 64 && verdict[device].load(std::memory_order_relaxed) == 1) {
+        QLDPC_CUDA(cudaSetDevice(device));
+        return QLDPC_OK;
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return QLDPC_ERR_NO_DEVICE; }
-    if (device < 0 || device >= ndev) return QLDPC_ERR_ARG;
+    if (device >= ndev) return QLDPC_ERR_ARG;
     QLDPC_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    QLDPC_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) return QLDPC_ERR_NO_DEVICE;
+    int major = 0;
+    QLDPC_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (device < 64) verdict[device].store(major == 10 ? 1 : 2, std::memory_order_relaxed);
+    if (major != 10) return QLDPC_ERR_NO_DEVICE;
     return QLDPC_OK;
 }
 
@@ -1490,7 +1500,10 @@ extern "C" int qldpc_crc32_frames(int32_t device, const uint32_t *bits, int32_t 
     if (n_frames == 0) return QLDPC_OK;
     int rc;
     if ((rc = select_sm100_device(device))) return rc;
-    DevBuf<uint32_t> d_bits, d_crc;
+    // device staging buffers are kept per host thread (the confirmation step calls this once per key block)
+    static thread_local DevBuf<uint32_t> d_bits, d_crc;
+    static thread_local int buf_device = -1;
+    if (buf_device != device) { d_bits.release(); d_crc.release(); buf_device = device; }
     if ((rc = d_bits.ensure((size_t)n_frames * stride_words)) || (rc = d_crc.ensure(n_frames))) return rc;
     QLDPC_CUDA(cudaMemcpy(d_bits.p, bits, (size_t)n_frames * stride_words * 4, cudaMemcpyHostToDevice));
     if ((rc = launch_crc32_frames(d_bits.p, n_frames, words_per_frame, stride_words, d_crc.p, nullptr))) return rc;

@@ -1465,7 +1465,6 @@ extern "C" int qldpc_privacy_amplify(int32_t device, const uint32_t *key, int32_
         max_wb = std::max(max_wb, workbits[b]);
         max_fb = std::max(max_fb, final_bits[b]);
     }
-    if (max_wb > 32 * 50000) return QLDPC_ERR_UNSUPPORTED;   // key words of a block live in shared memory
     int rc;
     if ((rc = select_sm100_device(device))) return rc;
     static thread_local int tables_on = -1;

@@ -1335,8 +1335,16 @@ extern "C" int qldpc_encode_nr_device(qldpc_decoder *dec, const uint32_t *d_msg,
     QLDPC_CUDA(cudaSetDevice(d->cfg.device));
     const HostCode &c = d->code;
     const int kbits = (c.base_cols - c.base_rows) * c.z;
-    const int rc = launch_encode_nr(d_msg, d_cword, n_frames, c.z, c.base_rows, c.base_cols, d->d_base.p, (kbits + 31) / 32,
-                                    d->cw_words, (cudaStream_t)cuda_stream);
+    int rc;
+    if (c.z % 32 == 0 && d->d_qc_layers.p && d->d_qc_aux.p && c.z / 32 <= 1024) {   // packed words
+        const int kb = c.base_cols - c.base_rows;
+        const int p1_sh = c.base[1 * c.base_cols + kb] == -1 ? c.base[2 * c.base_cols + kb] : c.base[1 * c.base_cols + kb];
+        rc = launch_encode_nr_packed(d_msg, d_cword, n_frames, c.z, c.base_rows, c.base_cols, (c.z - p1_sh % c.z) % c.z, kbits / 32,
+                                     d->cw_words, d->d_qc_layers.p, d->d_qc_aux.p, (cudaStream_t)cuda_stream);
+    } else {
+        rc = launch_encode_nr(d_msg, d_cword, n_frames, c.z, c.base_rows, c.base_cols, d->d_base.p, (kbits + 31) / 32, d->cw_words,
+                              (cudaStream_t)cuda_stream);
+    }
     if (!rc && n_frames) d->kernel_launches++;
     return rc;
 }

@@ -214,6 +214,78 @@ __global__ void encode_nr_kernel(const uint32_t *__restrict__ msg, uint32_t *__r
     }
 }
 
+// The same encoder on PACKED words for lifting sizes that are a multiple of 32 (every size the packed decoders take): a block
+// column is Z / 32 MSB-first words, mul_sh (ML/mul_sh.m:9) is a word rotation plus one funnel shift, and a thread owns one
+// word of every vector.  blockDim = (Z / 32, frames per CTA); the message and the four core parity columns of a frame sit in
+// shared memory, the extension parities go straight to the output.  Same steps and the same order of dependencies as
+// encode_nr_kernel above (ML/nrldpc_encode.m:18-45); the byte-per-bit version walks all kb + 4 columns of the base matrix
+// for every parity BIT (18.8 ms for 65 536 BG1 Z=384 frames, slower than decoding them), this one walks the row's edges
+// for every parity WORD.
+__global__ void encode_nr_packed_kernel(const uint32_t *__restrict__ msg, uint32_t *__restrict__ cword, int F, int ZW, int brows,
+                                        int bcols, int p1_rot, int msg_words, int cw_words, const QcLayer *__restrict__ layers,
+                                        const QcEdgeAux *__restrict__ aux)
+{
+    extern __shared__ uint32_t esm[];
+    const int kb = bcols - brows, ncore = kb + 4, w = threadIdx.x, fs = threadIdx.y, FP = blockDim.y;
+    uint32_t *cw = esm + (size_t)fs * (ncore + 1) * ZW, *temp = cw + ncore * ZW;
+    // word w of vector v (ZW words) rotated by `shift` lanes: result lane l = v lane (l + shift) mod Z
+    auto rot = [&](const uint32_t *v, int shift) {
+        int w0 = w + (shift >> 5);
+        if (w0 >= ZW) w0 -= ZW;
+        const int w1 = w0 + 1 == ZW ? 0 : w0 + 1;
+        return __funnelshift_l(v[w1], v[w0], shift & 31);
+    };
+    for (int f0 = blockIdx.x * FP; f0 < F; f0 += gridDim.x * FP) {
+        const int f = f0 + fs;
+        const bool act = f < F;
+        if (act)
+            for (int j = 0; j < kb; ++j) cw[j * ZW + w] = __ldg(msg + (size_t)f * msg_words + j * ZW + w);
+        __syncthreads();
+        uint32_t lam[4] = {0u, 0u, 0u, 0u};           // :18-23 message part of the four core rows
+        if (act) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const QcLayer ly = layers[r];
+                for (int e = 0; e < ly.degree; ++e) {
+                    const QcEdgeAux a = aux[ly.edge_begin + e];
+                    if (a.col < kb) lam[r] ^= rot(cw + a.col * ZW, a.shift);
+                }
+            }
+            temp[w] = lam[0] ^ lam[1] ^ lam[2] ^ lam[3];
+        }
+        __syncthreads();
+        if (act) cw[kb * ZW + w] = rot(temp, p1_rot);   // :24-29 p1 = mul_sh(temp, z - p1_sh)
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {                 // :30-37 p2..p4, each needs the previous one
+            if (act) {
+                uint32_t acc = lam[r];
+                const QcLayer ly = layers[r];
+                for (int e = 0; e < ly.degree; ++e) {
+                    const QcEdgeAux a = aux[ly.edge_begin + e];
+                    if (a.col >= kb && a.col < kb + r + 1) acc ^= rot(cw + a.col * ZW, a.shift);
+                }
+                cw[(kb + r + 1) * ZW + w] = acc;
+            }
+            __syncthreads();
+        }
+        if (act) {
+            uint32_t *of = cword + (size_t)f * cw_words;
+            for (int j = 0; j < ncore; ++j) of[j * ZW + w] = cw[j * ZW + w];
+            for (int r = 4; r < brows; ++r) {         // :38-45 extension parities, independent of each other
+                uint32_t acc = 0;
+                const QcLayer ly = layers[r];
+                for (int e = 0; e < ly.degree; ++e) {
+                    const QcEdgeAux a = aux[ly.edge_begin + e];
+                    if (a.col < ncore) acc ^= rot(cw + a.col * ZW, a.shift);
+                }
+                of[(kb + r) * ZW + w] = acc;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // Per-position LLR magnitudes (one byte each, shared by all frames) for the decoders that synthesise their LLRs from key
 // bits themselves (layered_i8s.cu, bit input): noisy / known / punctured as in make_llr_kernel.
 __global__ void make_mag_i8_kernel(const uint32_t *__restrict__ known, const uint32_t *__restrict__ punct, int noisy,
@@ -310,6 +382,22 @@ int launch_encode_nr(const uint32_t *msg, uint32_t *cword, int F, int Z, int bro
     if (block < 128) block = 128;
     const int grid = F < 148 * 8 ? F : 148 * 8;
     encode_nr_kernel<<<grid, block, smem, st>>>(msg, cword, F, Z, brows, bcols, base, msg_words, cw_words);
+    QLDPC_CUDA(cudaGetLastError());
+    return QLDPC_OK;
+}
+
+// Z % 32 == 0: packed words (p1_rot = (Z - p1_sh) % Z, the rotation that turns the sum of the core rows into p1)
+int launch_encode_nr_packed(const uint32_t *msg, uint32_t *cword, int F, int Z, int brows, int bcols, int p1_rot, int msg_words,
+                            int cw_words, const QcLayer *layers, const QcEdgeAux *aux, cudaStream_t st)
+{
+    if (F <= 0) return QLDPC_OK;
+    const int ZW = Z / 32, ncore = bcols - brows + 4;
+    const int fp = std::max(1, std::min(32, 256 / ZW));
+    const int smem = fp * (ncore + 1) * ZW * 4;
+    if (smem > 48 * 1024) QLDPC_CUDA(cudaFuncSetAttribute(encode_nr_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int groups = (F + fp - 1) / fp;
+    encode_nr_packed_kernel<<<std::min(groups, 148 * 8), dim3(ZW, fp), smem, st>>>(msg, cword, F, ZW, brows, bcols, p1_rot, msg_words,
+                                                                                     cw_words, layers, aux);
     QLDPC_CUDA(cudaGetLastError());
     return QLDPC_OK;
 }

@@ -220,6 +220,8 @@ int launch_make_llr(const uint32_t *bits, const uint32_t *known, const uint32_t 
                     int F, int N, int cw_words, int dtype, void *llr_out, cudaStream_t st);
 int launch_encode_nr(const uint32_t *msg, uint32_t *cword, int F, int Z, int brows, int bcols, const int32_t *base,
                      int msg_words, int cw_words, cudaStream_t st);
+int launch_encode_nr_packed(const uint32_t *msg, uint32_t *cword, int F, int Z, int brows, int bcols, int p1_rot, int msg_words,
+                            int cw_words, const QcLayer *layers, const QcEdgeAux *aux, cudaStream_t st);
 
 
 // ---- post-reconciliation (postproc.cu) -------------------------------------------------------------

@@ -105,7 +105,15 @@ __global__ void __launch_bounds__(kPaThreads) privacy_amplify_kernel(const uint3
 }
 
 // CRC-32 (IEEE 802.3, reflected, the zlib / PNG polynomial 0xEDB88320) of each frame, taken over the frame's bytes in
-// transmission order: MSB-first words -> big-endian byte order.  One thread per frame, table in shared memory.
+// transmission order: MSB-first words -> big-endian byte order.
+__device__ __forceinline__ uint32_t crc_word(const uint32_t *tab, uint32_t c, uint32_t v)
+{
+#pragma unroll
+    for (int k = 3; k >= 0; --k) c = tab[(c ^ (v >> (8 * k))) & 0xffu] ^ (c >> 8);
+    return c;
+}
+
+// One thread per frame, byte-serial (any frame length).
 __global__ void crc32_frames_kernel(const uint32_t *__restrict__ bits, int n_frames, int words_per_frame, int stride_words,
                                     uint32_t *__restrict__ crc_out)
 {
@@ -120,12 +128,50 @@ __global__ void crc32_frames_kernel(const uint32_t *__restrict__ bits, int n_fra
     if (f >= n_frames) return;
     const uint32_t *p = bits + (size_t)f * stride_words;
     uint32_t c = 0xffffffffu;
-    for (int w = 0; w < words_per_frame; ++w) {
-        const uint32_t v = __ldg(p + w);
-#pragma unroll
-        for (int k = 3; k >= 0; --k) c = tab[(c ^ (v >> (8 * k))) & 0xffu] ^ (c >> 8);
-    }
+    for (int w = 0; w < words_per_frame; ++w) c = crc_word(tab, c, __ldg(p + w));
     crc_out[f] = c ^ 0xffffffffu;
+}
+
+// One WARP per frame.  The CRC register is linear in (state, data): with Z_n the map "feed n zero bytes",
+//     crc(A || B, init) = Z_|B|( crc(A, init) ) ^ crc(B, 0),
+// so every lane runs the byte loop over its own contiguous chunk from state 0, advances the result over the bytes that follow
+// its chunk with the binary jump tables Z_(2^b) (constant memory), and the warp XORs the 32 contributions together with the
+// image of the initial state, Z_L(0xffffffff) (the same for every frame: a kernel argument).  The frame is read once, coalesced,
+// through shared memory.  (The thread-per-frame kernel above walks 1 056 dependent table look-ups per frame with a stride of a
+// whole frame between the lanes of a warp: 17 GB/s on 65 536 frames.)
+struct CrcJump { uint32_t col[24][32]; };     // col[b][k] = column k of Z_(2^b bytes)
+__constant__ CrcJump c_crc;
+constexpr int kCrcWarps = 4, kCrcMaxWords = 2048;
+
+__global__ void __launch_bounds__(32 * kCrcWarps) crc32_frames_warp_kernel(const uint32_t *__restrict__ bits, int n_frames,
+                                                                          int words_per_frame, int stride_words, uint32_t init_image,
+                                                                          uint32_t *__restrict__ crc_out)
+{
+    __shared__ uint32_t tab[256];
+    extern __shared__ uint32_t fr[];              // kCrcWarps frames of words_per_frame words
+    for (int n = threadIdx.x; n < 256; n += blockDim.x) {
+        uint32_t c = (uint32_t)n;
+        for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xedb88320u ^ (c >> 1) : c >> 1;
+        tab[n] = c;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t *my = fr + wid * words_per_frame;
+    const int per = (words_per_frame + 31) / 32;
+    const int a = min(words_per_frame, lane * per), b = min(words_per_frame, a + per);
+    for (int f = blockIdx.x * kCrcWarps + wid; f < n_frames; f += gridDim.x * kCrcWarps) {
+        const uint32_t *p = bits + (size_t)f * stride_words;
+        for (int w = lane; w < words_per_frame; w += 32) my[w] = __ldg(p + w);
+        __syncwarp();
+        uint32_t c = 0;
+        for (int w = a; w < b; ++w) c = crc_word(tab, c, my[w]);
+        for (int bit = 0, e = 4 * (words_per_frame - b); e; ++bit, e >>= 1)      // bytes after this lane's chunk
+            if (e & 1) c = matvec(c_crc.col[bit], c);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) c ^= __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) crc_out[f] = c ^ init_image ^ 0xffffffffu;
+        __syncwarp();
+    }
 }
 
 }  // namespace
@@ -163,10 +209,55 @@ int launch_privacy_amplify(const uint32_t *d_key, const int32_t *d_workbits, con
     return QLDPC_OK;
 }
 
+static uint32_t crc_zero_byte(uint32_t c)
+{
+    for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xedb88320u ^ (c >> 1) : c >> 1;    // one zero byte through the reflected register
+    return c;
+}
+
 int launch_crc32_frames(const uint32_t *d_bits, int n_frames, int words_per_frame, int stride_words, uint32_t *d_crc, cudaStream_t st)
 {
     if (n_frames <= 0) return QLDPC_OK;
-    crc32_frames_kernel<<<(n_frames + 127) / 128, 128, 0, st>>>(d_bits, n_frames, words_per_frame, stride_words, d_crc);
+    if (words_per_frame < 32 || words_per_frame > kCrcMaxWords) {
+        crc32_frames_kernel<<<(n_frames + 127) / 128, 128, 0, st>>>(d_bits, n_frames, words_per_frame, stride_words, d_crc);
+        QLDPC_CUDA(cudaGetLastError());
+        return QLDPC_OK;
+    }
+    // jump tables Z_(2^b bytes), once per device; the image of the initial state under Z_L, per call
+    static CrcJump h;
+    static bool built = false;
+    static thread_local int tables_on = -1;
+    if (!built) {
+        for (int k = 0; k < 32; ++k) h.col[0][k] = crc_zero_byte(1u << k);
+        for (int b = 1; b < 24; ++b)
+            for (int k = 0; k < 32; ++k) {
+                uint32_t x = h.col[b - 1][k], y = 0;
+                for (int t = 0; t < 32; ++t)
+                    if ((x >> t) & 1u) y ^= h.col[b - 1][t];
+                h.col[b][k] = y;
+            }
+        built = true;
+    }
+    int dev = 0;
+    QLDPC_CUDA(cudaGetDevice(&dev));
+    if (tables_on != dev) {
+        QLDPC_CUDA(cudaMemcpyToSymbol(c_crc, &h, sizeof(h)));
+        tables_on = dev;
+    }
+    uint32_t init_image = 0xffffffffu;
+    for (int bit = 0, e = 4 * words_per_frame; e; ++bit, e >>= 1)
+        if (e & 1) {
+            uint32_t y = 0;
+            for (int t = 0; t < 32; ++t)
+                if ((init_image >> t) & 1u) y ^= h.col[bit][t];
+            init_image = y;
+        }
+    const int smem = kCrcWarps * words_per_frame * 4;
+    if (smem > 40 * 1024)
+        QLDPC_CUDA(cudaFuncSetAttribute(crc32_frames_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int groups = (n_frames + kCrcWarps - 1) / kCrcWarps;
+    crc32_frames_warp_kernel<<<std::min(groups, 148 * 16), 32 * kCrcWarps, smem, st>>>(d_bits, n_frames, words_per_frame, stride_words,
+                                                                                      init_image, d_crc);
     QLDPC_CUDA(cudaGetLastError());
     return QLDPC_OK;
 }

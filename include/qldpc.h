@@ -125,9 +125,9 @@ typedef struct qldpc_decoder_config {
     float   norm_factor;     /* NMS factor (BOOT/src/main.cpp:98); integer dtypes: k/8, k=1..8 */
     float   offset;          /* OMS offset (BOOT/src/main.cpp:99; BPSK_nrldpc_sim_FP.m:6)      */
     int32_t msg_max;         /* integer dtypes: messages clipped to [-(msg_max+1), msg_max];
-                                0 = default (31 for i8 = maxqr, BPSK_nrldpc_sim_FP.m:4; 511 for i16) */
+                                0 = default (31 for i8 = maxqr, BPSK_nrldpc_sim_FP.m:4; 511 for i16); at most 32766 */
     int32_t app_max;         /* integer dtypes, layered: beliefs clipped to [-(app_max+1), app_max];
-                                0 = default (127 for i8 = maxqL, BPSK_nrldpc_sim_FP.m:5; 8191 for i16) */
+                                0 = default (127 for i8 = maxqL, BPSK_nrldpc_sim_FP.m:5; 8191 for i16); at most 32767 */
     int32_t out_mode;        /* QLDPC_OUT_INFO: k info bits per frame; QLDPC_OUT_ALL: n bits   */
     int32_t device;          /* CUDA device ordinal (used when n_devices <= 1)                 */
     /* Frames are independent (AFF3CT n_frames semantics; ML/BPSK_nrldpc_sim_RM_FP.m:27 `parfor`): with n_devices > 1 the

@@ -89,7 +89,7 @@ struct LayeredGenParams {
     DevStats *stats;
     const QcEdgeAux *aux;
     const QcLayer *layers;
-    void *msg;                // grid * nnz * Z messages (float / int16), L2-resident global scratch
+    void *msg;                // grid * (nnz * Z messages (float / int16) | compressed check states), L2-resident global scratch
     void *app;                // null: beliefs in shared memory; else grid * N beliefs (float / int16) in a global scratch
     int F;
     int Z, brows, bcols, nnz, N, M;
@@ -98,7 +98,10 @@ struct LayeredGenParams {
     int rule, dtype;
     float norm, offset;
     int offset_int, norm_eighths, msg_max, app_max;
+    int compressed;           // min-sum rules, every row within the compiled degrees: {c1, c2, index, signs} per check lane
 };
+int layered_generic_max_compiled_degree();
+size_t layered_generic_msg_scratch_bytes(int dtype, int compressed, int brows, int nnz, int Z);
 int layered_generic_belief_bytes(int dtype);
 int layered_generic_msg_bytes(int dtype);
 int layered_generic_smem_bytes(int brows, int nnz, int N, int dtype);       // N = 0: tables only (beliefs in global memory)

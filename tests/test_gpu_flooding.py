@@ -220,3 +220,27 @@ def test_fast_spa_flavour_on_the_general_flooding_kernel(q, O, data_dir, kat, na
     # difference of large terms (absolute deviation still below 1e-2)
     assert outside.mean() < 2e-3 and dev.max() < 1.5 and ((np.abs(opost[outside]) > 15) | (dev[outside] < 1e-2)).all()
     fast.close()
+
+
+@pytest.mark.parametrize("rule", ["nms", "oms", "spa"])
+def test_layered_f32_bg1_z384_compressed_check_state(q, O, data_dir, rule):
+    """float layered decoding on BG1 Z=384 (rows of 19 edges): the min-sum rules keep {c1, c2, index, signs} per check lane
+    instead of one message per edge (the per-edge messages of the frames in flight would not fit in L2), SPA keeps per-edge
+    messages -- both against the oracle, posteriors included"""
+    path = "%s/NR_1_1_384.qc" % data_dir
+    oc = O.Code.from_qc(path)
+    code = q.Code.from_qc_file(path)
+    F = 3
+    llr, syn, x = _bsc_llr_frames(oc, F, 0.06, seed=21)
+    qr = {"spa": q.RULE_SPA, "nms": q.RULE_NMS, "oms": q.RULE_OMS}[rule]
+    orr = {"spa": O.RULE_SPA, "nms": O.RULE_NMS, "oms": O.RULE_OMS}[rule]
+    dec = q.Decoder(code, schedule=q.SCHED_LAYERED, rule=qr, dtype=q.DTYPE_F32, max_iter=8, norm_factor=0.8125, offset=0.4,
+                    out_mode=q.OUT_ALL)
+    assert dec.kernel_name == "layered_generic"
+    out, ok, iters, post = dec.decode(llr, q.pack_bits(syn), want_posterior=True)
+    for f in range(F):
+        h, p, it, o = oc.decode_layered_f32(llr[f], syn[f], rule=orr, n_ite=8, early_stop=True, norm=0.8125, offset=0.4)
+        assert (q.unpack_bits(out[f:f + 1], oc.N)[0] == h).all() and iters[f] == it and ok[f] == o
+        np.testing.assert_allclose(post[f], p, rtol=RTOL, atol=1e-4)
+    assert ok.all() and (q.unpack_bits(out, oc.N) == x).all()
+    dec.close()

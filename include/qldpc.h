@@ -79,7 +79,7 @@ enum { QLDPC_OUT_INFO = 0, QLDPC_OUT_ALL = 1 };
 #define QLDPC_FLAG_LI8_RESIDENT   2u  /* diagnostics: int8 layered decoding on the previous-generation kernel (layered_i8.cu)  */
 #define QLDPC_FLAG_LI8_STREAM     4u  /*   with its messages resident in shared memory / streamed through an L2 scratch   */
 #define QLDPC_FLAG_NO_FUSED_BITS  8u  /* diagnostics: qldpc_decode_bits runs LLR synthesis and decoding as two kernels      */
-#define QLDPC_FLAG_FAST_SPA      32u  /* float flooding SPA (flooding_qc_cluster, flooding_csr): tanh / atanh in fp32 on the
+#define QLDPC_FLAG_FAST_SPA      32u  /* float SPA (flooding and layered kernels): tanh / atanh in fp32 on the
                                          special-function units instead of double.  Decoded bits are unchanged on all test
                                          batches, iteration counts on all but about one frame in 3e4; posteriors stay within
                                          1e-3 except for saturated messages (|m| > 14), which may move by ln 2 (one last-bit

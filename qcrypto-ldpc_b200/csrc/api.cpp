@@ -930,6 +930,7 @@ static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint3
         p.F = n_frames; p.N = c.n; p.M = c.m; p.E = c.edges; p.cw_words = d->cw_words; p.syn_words = d->syn_words;
         p.max_iter = cfg.max_iter; p.early_stop = cfg.early_stop; p.syndrome_depth = cfg.syndrome_depth;
         p.rule = cfg.rule; p.norm = cfg.norm_factor; p.offset = cfg.offset;
+        p.fast_spa = (cfg.flags & QLDPC_FLAG_FAST_SPA) ? 1 : 0;
         const int threads = std::min(d->gen_grid, (n_frames + 127) / 128 * 128);
         // the state is indexed with the launch's thread count as stride: every launch lays it out afresh
         if ((rc = launch_layered_csr(p, threads, st))) return rc;
@@ -940,6 +941,7 @@ static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint3
         p.aux = d->d_qc_aux.p; p.layers = d->d_qc_layers.p;
         p.msg = d->d_scratch.p; p.app = d->gen_beliefs_global ? d->d_scratch2.p : nullptr;
         p.compressed = d->gen_compressed;
+        p.fast_spa = (cfg.flags & QLDPC_FLAG_FAST_SPA) ? 1 : 0;
         p.F = n_frames; p.Z = c.z; p.brows = c.base_rows; p.bcols = c.base_cols; p.nnz = c.edges / c.z;
         p.N = c.n; p.M = c.m; p.cw_words = d->cw_words; p.syn_words = d->syn_words;
         p.max_iter = cfg.max_iter; p.early_stop = cfg.early_stop; p.syndrome_depth = cfg.syndrome_depth;

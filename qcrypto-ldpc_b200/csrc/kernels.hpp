@@ -99,6 +99,7 @@ struct LayeredGenParams {
     float norm, offset;
     int offset_int, norm_eighths, msg_max, app_max;
     int compressed;           // min-sum rules, every row within the compiled degrees: {c1, c2, index, signs} per check lane
+    int fast_spa;             // QLDPC_FLAG_FAST_SPA
 };
 int layered_generic_max_compiled_degree();
 size_t layered_generic_msg_scratch_bytes(int dtype, int compressed, int brows, int nnz, int Z);
@@ -124,6 +125,7 @@ struct LayeredCsrParams {
     int max_iter, early_stop, syndrome_depth;
     int rule;
     float norm, offset;
+    int fast_spa;             // QLDPC_FLAG_FAST_SPA
 };
 int layered_csr_max_degree();
 int launch_layered_csr(const LayeredCsrParams &p, int threads, cudaStream_t st);   // threads: multiple of 128

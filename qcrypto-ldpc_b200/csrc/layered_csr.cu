@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(128) layered_csr_kernel(const LayeredCsrParams
                     const float a = fabsf(x);
                     sign ^= signbit(x) ? 1 : 0;
                     if (p.rule == QLDPC_RULE_SPA) {
-                        const float th = tanh_half_exact(a);
+                        const float th = p.fast_spa ? tanh_half_fast(a) : tanh_half_exact(a);
                         const float r = (th != 0.0f) ? th : 1e-12f;
                         product *= r;
                         vals[j] = r;
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(128) layered_csr_kernel(const LayeredCsrParams
                     if (p.rule == QLDPC_RULE_SPA) {
                         float r = product / vals[j];
                         r = (r < 1.0f) ? r : 1.0f - 1.1920929e-07f;
-                        mag = two_atanh_exact(r);
+                        mag = p.fast_spa ? two_atanh_fast(r) : two_atanh_exact(r);
                     } else {
                         mag = (fabsf(x) == min1) ? cst1 : cst2;
                     }

@@ -35,7 +35,10 @@ constexpr int kMaxDc = 20;           // compiled row degrees; heavier rows take 
 
 struct RowMeta { int edge_begin, degree; };
 // the update rule's parameters, by value
-struct Upd { int rule, offset_int, norm_eighths, msg_max, app_max; float norm, offset; };
+struct Upd { int rule, offset_int, norm_eighths, msg_max, app_max; float norm, offset; int fast_spa; };
+// the SPA transcendentals (spa_math.cuh): double rounded once, or fp32 on the SFUs with QLDPC_FLAG_FAST_SPA
+__device__ __forceinline__ float tanh_half(const Upd &u, float a) { return u.fast_spa ? tanh_half_fast(a) : tanh_half_exact(a); }
+__device__ __forceinline__ float two_atanh(const Upd &u, float r) { return u.fast_spa ? two_atanh_fast(r) : two_atanh_exact(r); }
 
 __device__ __forceinline__ int norm8(int v, int k)
 {
@@ -51,8 +54,6 @@ __device__ __forceinline__ int norm8(int v, int k)
     }
 }
 __device__ __forceinline__ int clipi(int x, int lo, int hi) { return min(max(x, lo), hi); }
-__device__ __forceinline__ float tanh_half(float a) { return tanh_half_exact(a); }       // spa_math.cuh
-__device__ __forceinline__ float two_atanh(float r) { return two_atanh_exact(r); }
 
 // One check (block row with DC edges starting at `ed`, check lane `lane`): beliefs in shared memory, old messages at
 // Rl[j * Z] (not read when `first`), new messages and beliefs written back.
@@ -79,7 +80,7 @@ __device__ __forceinline__ void row_lane(const Upd u, LT *L, MT *Rl, const int2 
             float product = 1.0f;
 #pragma unroll
             for (int j = 0; j < DC; ++j) {
-                const float tj = tanh_half(fabsf(x[j]));
+                const float tj = tanh_half(u, fabsf(x[j]));
                 t[j] = (tj != 0.0f) ? tj : 1e-12f;
                 product *= t[j];
                 sign ^= signbit(x[j]) ? 1 : 0;
@@ -88,7 +89,7 @@ __device__ __forceinline__ void row_lane(const Upd u, LT *L, MT *Rl, const int2 
             for (int j = 0; j < DC; ++j) {
                 float r = product / t[j];
                 r = (r < 1.0f) ? r : 1.0f - 1.1920929e-07f;
-                const float mag = two_atanh(r);
+                const float mag = two_atanh(u, r);
                 const float out = (sign ^ (signbit(x[j]) ? 1 : 0)) ? -mag : mag;
                 Rl[j * Z] = out;
                 L[idx[j]] = x[j] + out;
@@ -265,7 +266,7 @@ __device__ __noinline__ void row_lane_any(const Upd u, LT *L, MT *Rl, const int2
             const float a = fabsf(x);
             sign ^= signbit(x) ? 1 : 0;
             if (u.rule == QLDPC_RULE_SPA) {
-                const float t = tanh_half(a);
+                const float t = tanh_half(u, a);
                 product *= (t != 0.0f) ? t : 1e-12f;
             } else {
                 min2 = fminf(min2, fmaxf(a, min1));
@@ -279,10 +280,10 @@ __device__ __noinline__ void row_lane_any(const Upd u, LT *L, MT *Rl, const int2
             const float x = contrib(j, at);
             float mag;
             if (u.rule == QLDPC_RULE_SPA) {
-                const float t = tanh_half(fabsf(x));
+                const float t = tanh_half(u, fabsf(x));
                 float r = product / ((t != 0.0f) ? t : 1e-12f);
                 r = (r < 1.0f) ? r : 1.0f - 1.1920929e-07f;
-                mag = two_atanh(r);
+                mag = two_atanh(u, r);
             } else {
                 mag = (fabsf(x) == min1) ? cst1 : cst2;
             }
@@ -349,7 +350,7 @@ __global__ void __launch_bounds__(MAXT, MINB) layered_generic_kernel(const Layer
     for (int r = tid; r < R; r += nt) rows[r] = RowMeta{p.layers[r].edge_begin, p.layers[r].degree};
     for (int e = tid; e < p.nnz; e += nt) edges[e] = make_int2(p.aux[e].col * Z, p.aux[e].shift);
     MT *Rg = reinterpret_cast<MT *>(p.msg) + (size_t)blockIdx.x * p.nnz * Z;
-    const Upd upd{p.rule, p.offset_int, p.norm_eighths, p.msg_max, p.app_max, p.norm, p.offset};
+    const Upd upd{p.rule, p.offset_int, p.norm_eighths, p.msg_max, p.app_max, p.norm, p.offset, p.fast_spa};
 
     // syndrome of the hard decisions (beliefs in shared memory), OR over the block
     auto syndrome_bad = [&](const uint32_t *syn) {

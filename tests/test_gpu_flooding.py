@@ -244,3 +244,26 @@ def test_layered_f32_bg1_z384_compressed_check_state(q, O, data_dir, rule):
         np.testing.assert_allclose(post[f], p, rtol=RTOL, atol=1e-4)
     assert ok.all() and (q.unpack_bits(out, oc.N) == x).all()
     dec.close()
+
+
+@pytest.mark.parametrize("name", ["NR_1_1_24.qc", "PEGReg504x1008.alist"])
+def test_fast_spa_flavour_on_the_layered_kernels(q, O, data_dir, name):
+    """QLDPC_FLAG_FAST_SPA on the float layered kernels (layered_generic on a QC code, layered_csr on an .alist H): decoded bits,
+    flags and iteration counts equal the oracle's, posteriors within 1e-3 outside saturated / cancelling entries"""
+    path = "%s/%s" % (data_dir, name)
+    alist = name.endswith(".alist")
+    oc = O.Code.from_alist(path) if alist else O.Code.from_qc(path)
+    code = q.Code.from_alist(path) if alist else q.Code.from_qc_file(path)
+    F = 24
+    llr, syn, x = _bsc_llr_frames(oc, F, 0.04, seed=13)
+    dec = q.Decoder(code, schedule=q.SCHED_LAYERED, rule=q.RULE_SPA, dtype=q.DTYPE_F32, max_iter=12, out_mode=q.OUT_ALL,
+                    flags=q.FLAG_FAST_SPA)
+    assert dec.kernel_name == ("layered_csr" if alist else "layered_generic")
+    out, ok, iters, post = dec.decode(llr, q.pack_bits(syn), want_posterior=True)
+    for f in range(F):
+        h, p, it, o = oc.decode_layered_f32(llr[f], syn[f], rule=O.RULE_SPA, n_ite=12, early_stop=True)
+        assert (q.unpack_bits(out[f:f + 1], oc.N)[0] == h).all() and iters[f] == it and ok[f] == o
+        dev = np.abs(post[f] - p)
+        outside = dev > 1e-3 * np.abs(p) + 1e-4
+        assert outside.mean() < 5e-3 and ((np.abs(p[outside]) > 15) | (dev[outside] < 1e-2)).all()
+    dec.close()

@@ -40,18 +40,12 @@ struct Upd { int rule, offset_int, norm_eighths, msg_max, app_max; float norm, o
 __device__ __forceinline__ float tanh_half(const Upd &u, float a) { return u.fast_spa ? tanh_half_fast(a) : tanh_half_exact(a); }
 __device__ __forceinline__ float two_atanh(const Upd &u, float r) { return u.fast_spa ? two_atanh_fast(r) : two_atanh_exact(r); }
 
+// AFF3CT's integer normalize: k/8 as a sum of floor(v/2), floor(v/4), floor(v/8); selects, no branch table (k is uniform,
+// the switch cost ~20 instructions per call, two calls per row)
 __device__ __forceinline__ int norm8(int v, int k)
 {
-    switch (k) {
-    case 1: return v >> 3;
-    case 2: return v >> 2;
-    case 3: return (v >> 2) + (v >> 3);
-    case 4: return v >> 1;
-    case 5: return (v >> 1) + (v >> 3);
-    case 6: return (v >> 1) + (v >> 2);
-    case 7: return (v >> 1) + (v >> 2) + (v >> 3);
-    default: return v;
-    }
+    if (k <= 0 || k >= 8) return v;
+    return ((k & 4) ? v >> 1 : 0) + ((k & 2) ? v >> 2 : 0) + ((k & 1) ? v >> 3 : 0);
 }
 __device__ __forceinline__ int clipi(int x, int lo, int hi) { return min(max(x, lo), hi); }
 

@@ -199,3 +199,47 @@ def test_n65536_layered_schedule_on_the_long_block(q, O, data_dir, tier):
         assert (q.unpack_bits(out[f:f + 1], oc.N)[0] == h).all() and iters[f] == it and ok[f] == o
     assert ok.all()
     dec.close()
+
+
+@pytest.mark.parametrize("tier", ["nms", "spa", "i8"])
+def test_clustered_flooding_rows_heavier_than_the_compiled_degrees(q, O, tier):
+    """a synthetic QC code with block rows of 24 edges (the clustered kernel compiles row degrees up to 20): heavy rows take
+    the two-pass loop, the light row a compiled variant; messages + posteriors (295 KB) do not fit in shared memory"""
+    rng = np.random.default_rng(24)
+    rows, cols, Z = 10, 48, 256
+    base = -np.ones((rows, cols), np.int32)
+    for r in range(rows):
+        deg = 6 if r == 0 else 24
+        pick = rng.choice(cols, deg, replace=False)
+        base[r, pick] = rng.integers(0, Z, deg)
+    for c in range(cols):                                     # no empty block column
+        if (base[:, c] < 0).all():
+            base[rng.integers(1, rows), c] = rng.integers(0, Z)
+    oc = O.Code.from_base(base, Z)
+    code = q.Code.from_qc(base, Z)
+    F = 5
+    x = rng.integers(0, 2, (F, oc.N)).astype(np.uint8)
+    y = x ^ (rng.random((F, oc.N)) < 0.004)
+    syn = np.stack([oc.syndrome(x[f]) for f in range(F)])
+    if tier == "i8":
+        dec = q.Decoder(code, schedule=q.SCHED_FLOODING, rule=q.RULE_NMS, dtype=q.DTYPE_I8, max_iter=15, early_stop=True,
+                        norm_factor=0.75, out_mode=q.OUT_ALL)
+        assert dec.kernel_name == "flooding_qc_cluster"
+        llr = np.where(y, -20, 20)
+        out, ok, iters, post = dec.decode(llr.astype(np.int8), q.pack_bits(syn), want_posterior=True)
+        for f in range(F):
+            hard, opost, oit, ook = oc.decode_flooding_fixed(llr[f], syn[f], rule=O.RULE_NMS, n_ite=15, early_stop=True,
+                                                             norm_eighths=6, vmax=127)
+            assert (q.unpack_bits(out[f:f + 1], oc.N)[0] == hard).all() and iters[f] == oit and ok[f] == ook
+            assert (post[f] == opost).all()
+    else:
+        qr, orr, norm = (q.RULE_SPA, O.RULE_SPA, 1.0) if tier == "spa" else (q.RULE_NMS, O.RULE_NMS, 0.75)
+        dec = q.Decoder(code, schedule=q.SCHED_FLOODING, rule=qr, dtype=q.DTYPE_F32, max_iter=15, early_stop=True,
+                        norm_factor=norm, out_mode=q.OUT_ALL)
+        assert dec.kernel_name == "flooding_qc_cluster"
+        llr = np.where(y, -5.5, 5.5).astype(np.float32)
+        out, ok, iters, post = dec.decode(llr, q.pack_bits(syn), want_posterior=True)
+        hard, opost, oit, ook, _ = oc.batch_flooding_f32(llr, syn, rule=orr, n_ite=15, early_stop=True, norm=norm)
+        assert (q.unpack_bits(out, oc.N) == hard).all() and (iters == oit).all() and (ok == ook).all()
+        np.testing.assert_allclose(post, opost, rtol=1e-3, atol=1e-4)
+    dec.close()

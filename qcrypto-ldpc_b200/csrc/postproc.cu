@@ -15,6 +15,8 @@
 // 65 535-bit block instead of the 1e9 of the bit-serial definition (40 000 final bits x 2 048 PRNG words), which the first
 // version of this kernel executed literally (one thread per final bit, 28 ms for 512 blocks; now the call is its copies).
 // Tables: T^(2^b) and its transpose in constant memory (binary jumps), U^(2^b) per block in shared memory.
+#include <mutex>
+
 #include "kernels.hpp"
 
 namespace qldpc {
@@ -225,9 +227,9 @@ int launch_crc32_frames(const uint32_t *d_bits, int n_frames, int words_per_fram
     }
     // jump tables Z_(2^b bytes), once per device; the image of the initial state under Z_L, per call
     static CrcJump h;
-    static bool built = false;
+    static std::once_flag built;
     static thread_local int tables_on = -1;
-    if (!built) {
+    std::call_once(built, [] {
         for (int k = 0; k < 32; ++k) h.col[0][k] = crc_zero_byte(1u << k);
         for (int b = 1; b < 24; ++b)
             for (int k = 0; k < 32; ++k) {
@@ -236,8 +238,7 @@ int launch_crc32_frames(const uint32_t *d_bits, int n_frames, int words_per_fram
                     if ((x >> t) & 1u) y ^= h.col[b - 1][t];
                 h.col[b][k] = y;
             }
-        built = true;
-    }
+    });
     int dev = 0;
     QLDPC_CUDA(cudaGetDevice(&dev));
     if (tables_on != dev) {

@@ -237,5 +237,66 @@ private:
     std::shared_ptr<qldpc_decoder> dec_;
 };
 
+// Encoder_LDPC<B>(K, N, G, n_frames) ("main.cpp (alist)":143, encode at :417) and Encoder_LDPC_from_H<B>(K, N, H, ...)
+// ("main.cpp (alist-v1.0.1)":144): systematic encoders of an arbitrary code -- from a generator matrix file (the reference
+// reads G with LDPC_matrix_handler::read and hands the Sparse_matrix over; here the file path is the argument), or from H by
+// elimination (AFF3CT's "IDENTITY" method).  get_info_bits_pos() is what the reference passes on to the decoder.
+template <typename B = int>
+class Encoder_LDPC {
+public:
+    Encoder_LDPC(int K, int N, const std::string &G_alist_path, int n_frames = 1, int device = 0) : n_frames_(n_frames)
+    {
+        qldpc_encoder *e = nullptr;
+        const int rc = qldpc_encoder_from_g_alist_file(G_alist_path.c_str(), device, &e);
+        if (rc != QLDPC_OK) throw tools::runtime_error(std::string("Encoder_LDPC: ") + qldpc_strerror(rc));
+        adopt(e, K, N);
+    }
+    std::vector<uint32_t> get_info_bits_pos() const
+    {
+        std::vector<int32_t> p((size_t)K_);
+        qldpc_encoder_info_bits_pos(enc_.get(), p.data());
+        return std::vector<uint32_t>(p.begin(), p.end());
+    }
+    void encode(const std::vector<B> &U_K, std::vector<B> &X_N)
+    {
+        if (U_K.size() != (size_t)K_ * n_frames_ || X_N.size() != (size_t)N_ * n_frames_)
+            throw tools::length_error("'U_K.size()' / 'X_N.size()' have to be 'K' / 'N' * 'n_frames'");
+        const int kw = (K_ + 31) / 32, cw = (N_ + 31) / 32;
+        std::vector<uint32_t> msg((size_t)n_frames_ * kw, 0u), cword((size_t)n_frames_ * cw);
+        for (int f = 0; f < n_frames_; ++f)
+            for (int i = 0; i < K_; ++i)
+                if (U_K[(size_t)f * K_ + i]) msg[(size_t)f * kw + i / 32] |= 1u << (31 - i % 32);
+        const int rc = qldpc_encode(enc_.get(), msg.data(), n_frames_, cword.data());
+        if (rc != QLDPC_OK) throw tools::runtime_error(std::string("Encoder_LDPC::encode: ") + qldpc_strerror(rc));
+        for (int f = 0; f < n_frames_; ++f)
+            for (int i = 0; i < N_; ++i) X_N[(size_t)f * N_ + i] = (B)((cword[(size_t)f * cw + i / 32] >> (31 - i % 32)) & 1u);
+    }
+
+protected:
+    explicit Encoder_LDPC(int n_frames) : n_frames_(n_frames) {}
+    void adopt(qldpc_encoder *e, int K, int N)
+    {
+        enc_.reset(e, &qldpc_encoder_free);
+        int32_t k = 0, n = 0;
+        qldpc_encoder_get_info(e, &k, &n);
+        if (K != k || N != n) throw tools::invalid_argument("'K' / 'N' do not match the matrix");
+        K_ = K; N_ = N;
+    }
+    int K_ = 0, N_ = 0, n_frames_;
+    std::shared_ptr<qldpc_encoder> enc_;
+};
+
+template <typename B = int>
+class Encoder_LDPC_from_H : public Encoder_LDPC<B> {
+public:
+    Encoder_LDPC_from_H(int K, int N, const tools::Sparse_matrix &H, int n_frames = 1, int device = 0) : Encoder_LDPC<B>(n_frames)
+    {
+        qldpc_encoder *e = nullptr;
+        const int rc = qldpc_encoder_from_h(H.get(), device, &e);
+        if (rc != QLDPC_OK) throw tools::runtime_error(std::string("Encoder_LDPC_from_H: ") + qldpc_strerror(rc));
+        this->adopt(e, K, N);
+    }
+};
+
 }  // namespace module
 }  // namespace qldpc

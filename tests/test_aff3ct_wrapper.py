@@ -150,3 +150,34 @@ def test_5gqc_driver_reproduces_the_recorded_sweep(driver_5gqc, data_dir):
         lo, hi = refpins.clopper_pearson(row["frame_errors"], row["frames"])
         inside += lo <= int(fe) / 2000 <= hi
     assert inside >= 9
+
+
+@pytest.fixture(scope="module")
+def encoders_exe(tmp_path_factory, q):
+    exe = str(tmp_path_factory.mktemp("enc") / "test_encoders")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-I", HOST,
+                           os.path.join(HOST, "test_encoders.cpp"), "-o", exe, q.LIB_PATH,
+                           "-Wl,-rpath," + os.path.dirname(q.LIB_PATH)])
+    return exe
+
+
+def test_encoder_classes_build_and_fail_loudly_without_gpu(encoders_exe, data_dir, tmp_path, kat):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible here")
+    (tmp_path / "d.txt").write_text(" ".join(str(b) for b in kat["data"]))
+    (tmp_path / "e.txt").write_text(" ".join(str(b) for b in kat["encoded"]))
+    p = subprocess.run([encoders_exe, "%s/PEGReg504x1008.alist" % data_dir, "%s/G_PEGReg504x1008.alist" % data_dir,
+                        str(tmp_path / "d.txt"), str(tmp_path / "e.txt")], capture_output=True, text=True)
+    assert p.returncode == 3 and "no sm_100 CUDA device" in p.stderr
+
+
+@pytest.mark.gpu
+def test_encoder_classes_replay_kat_e(encoders_exe, data_dir, tmp_path, kat):
+    """Encoder_LDPC<B>(K, N, G) and Encoder_LDPC_from_H<B>(K, N, H) of the AFF3CT face reproduce the reference's encoded[1008]
+    ("main.cpp (alist)":443-462) and are systematic at get_info_bits_pos()"""
+    (tmp_path / "d.txt").write_text(" ".join(str(b) for b in kat["data"]))
+    (tmp_path / "e.txt").write_text(" ".join(str(b) for b in kat["encoded"]))
+    p = subprocess.run([encoders_exe, "%s/PEGReg504x1008.alist" % data_dir, "%s/G_PEGReg504x1008.alist" % data_dir,
+                        str(tmp_path / "d.txt"), str(tmp_path / "e.txt")], capture_output=True, text=True)
+    assert p.returncode == 0 and "mismatches 0" in p.stdout, (p.stdout, p.stderr)

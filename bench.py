@@ -74,6 +74,7 @@ def parse_args():
     ap.add_argument("--no-fixed10", action="store_true", help="skip the extra fixed-10-iterations measurement")
     ap.add_argument("--no-fused-bits", action="store_true", help="qldpc_decode_bits as two kernels (LLR synthesis + decode)")
     ap.add_argument("--no-l2-persist", action="store_true", help="do not set QLDPC_FLAG_L2_PERSIST")
+    ap.add_argument("--discard-scratch", action="store_true", help="set QLDPC_FLAG_DISCARD_SCRATCH (less DRAM traffic, -1.4 %)")
     ap.add_argument("--no-zero-copy", action="store_true", help="qldpc_decode_bits stages pinned buffers through device copies")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -341,6 +342,7 @@ def run_ours(args, rank, world, local_rank):
     dec = q.Decoder(code, schedule=q.SCHED_LAYERED, rule=rule, dtype=q.DTYPE_I8, max_iter=MAX_ITER,
                     early_stop=not args.fixed_iters, norm_factor=NORM, offset=2.0, out_mode=q.OUT_INFO, device=local_rank,
                     flags=(0 if args.no_l2_persist else q.FLAG_L2_PERSIST) | (q.FLAG_NO_FUSED_BITS if args.no_fused_bits else 0) |
+                          (q.FLAG_DISCARD_SCRATCH if args.discard_scratch else 0) |
                     (q.FLAG_NO_ZERO_COPY if args.no_zero_copy else 0))
     assert dec.kernel_name == "layered_i8s_zpack4", dec.kernel_name   # the streamed kernel (layered_i8s.cu)
     F, N, K = args.frames, code.n, code.k
@@ -392,7 +394,7 @@ def run_ours(args, rank, world, local_rank):
     if not args.fixed_iters and not args.no_fixed10:
         decf = q.Decoder(code, schedule=q.SCHED_LAYERED, rule=rule, dtype=q.DTYPE_I8, max_iter=MAX_ITER, early_stop=False,
                          norm_factor=NORM, offset=2.0, out_mode=q.OUT_INFO, device=local_rank,
-                         flags=0 if args.no_l2_persist else q.FLAG_L2_PERSIST)
+                         flags=(0 if args.no_l2_persist else q.FLAG_L2_PERSIST) | (q.FLAG_DISCARD_SCRATCH if args.discard_scratch else 0))
         for _ in range(2):
             decf.decode_device(llr.data_ptr(), 0, F, out.data_ptr(), ok.data_ptr(), iters.data_ptr(), 0, st)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

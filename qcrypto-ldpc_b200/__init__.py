@@ -26,6 +26,7 @@ OUT_INFO, OUT_ALL = 0, 1
 ITER_HIST_BINS = 64
 MAX_DEVICES = 8
 FLAG_L2_PERSIST, FLAG_LI8_RESIDENT, FLAG_LI8_STREAM, FLAG_NO_FUSED_BITS, FLAG_NO_ZERO_COPY, FLAG_FAST_SPA = 1, 2, 4, 8, 16, 32
+FLAG_DISCARD_SCRATCH = 64
 
 _NP_DTYPE = {DTYPE_F32: np.float32, DTYPE_I16: np.int16, DTYPE_I8: np.int8}
 

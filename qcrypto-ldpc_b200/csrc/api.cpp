@@ -863,6 +863,7 @@ static int decode_device_impl(qldpc_decoder *dec, const void *d_llr, const uint3
             cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
             cudaGetLastError();
         }
+        p.discard_scratch = (d->cfg.flags & QLDPC_FLAG_DISCARD_SCRATCH) ? 1 : 0;
         if ((rc = launch_layered_i8s(p, grid, smem_bytes, st))) return rc;
         d->kernel_launches++;
         if (!direct) {

@@ -73,6 +73,7 @@ struct LayeredI8sParams {
     int rg_u4;                // uint4 per frame slot in the scratch
     unsigned int *frame_ctr;  // zeroed before the launch: frames beyond the first grid * slots are handed out through it
                               // (null: frame f of a slot is followed by f + grid * slots)
+    int discard_scratch;      // QLDPC_FLAG_DISCARD_SCRATCH: discard.global.L2 of the slot's message scratch when its frame ends
 };
 constexpr int kLi8sSlotBase = 32;   // after the tables: 16 bytes of zero messages, the CTA's iteration mbarrier (8 bytes, padded)
 int launch_layered_i8s(const LayeredI8sParams &p, int grid, int smem_bytes, cudaStream_t st);

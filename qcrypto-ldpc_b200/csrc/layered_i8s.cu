@@ -703,6 +703,11 @@ __global__ void __maxnreg__(kMaxRegs) layered_i8s_kernel(const LayeredI8sParams 
             mbar_wait(mb_full + 8 * (tt & 1u), (tt >> 1) & 1u);
             ++tt;
         }
+        if (p.discard_scratch) {
+            // the messages of the finished frame are dead: drop their (dirty) L2 lines instead of letting them be written back
+            const int rg_bytes = p.rg_u4 * 16;
+            for (int o = i * 128; o < rg_bytes; o += W * 128) asm volatile("discard.global.L2 [%0], 128;" ::"l"(rg_slot + o) : "memory");
+        }
         bar_sync(bar_id, W);   // hd / beliefs / ring are reused by the next frame of this slot
         f = fnext;
         need_load = true;

@@ -240,6 +240,17 @@ def test_bg1_z384_many_frames_per_slot_vs_oracle(q, O, data_dir, mode, qber, mag
     assert len(set(iters.tolist())) >= 2          # a mix of iteration counts inside the batch
 
 
+@pytest.mark.parametrize("name,mode,qber,mag", [("NR_1_1_384.qc", "parity", 0.03, 14), ("NR_1_1_384.qc", "syndrome", 0.07, 11),
+                                                ("NR_2_0_256.qc", "parity", 0.04, 12)])
+def test_discard_scratch_flag_keeps_results(q, O, data_dir, name, mode, qber, mag):
+    """QLDPC_FLAG_DISCARD_SCRATCH drops the L2 lines of a slot's message scratch when its frame ends (discard.global.L2); the
+    slot's next frame rewrites every line before it reads one, so bits / ok / iteration counts still equal the oracle's --
+    checked with several frames per slot and frames that need many iterations (messages re-read after every iteration)"""
+    iters, ok = _run_case(q, O, data_dir, name, 2400, qber, mag, mode, q.RULE_NMS, 10, True, out_all=False, seed=17,
+                          flags=q.FLAG_DISCARD_SCRATCH)
+    assert iters.max() >= 2                        # messages written, discarded and rewritten by the slot's next frame
+
+
 @pytest.mark.parametrize("mode", ["parity", "syndrome"])
 @pytest.mark.parametrize("name", ["NR_1_1_384.qc", "NR_2_0_256.qc", "NR_1_0_128.qc"])
 def test_bit_input_fused_synthesis_equals_two_kernel_path(q, O, data_dir, name, mode):

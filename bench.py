@@ -220,7 +220,8 @@ def synth_frames_cpu(n, seed=1234):
     return llr, oc
 
 
-def kernel_roofline(F, N, out_words, edges, mean_iters, launch_ms, hbm_peak, hbm_src, smem_peak, l2_peak, onchip_src, ncu):
+def kernel_roofline(F, N, out_words, edges, mean_iters, launch_ms, hbm_peak, hbm_src, smem_peak, l2_peak, onchip_src, ncu,
+                    sm_mhz=None, n_sm=148):
     """SURVEY.md 8d for the on-chip layered decoder: achieved = max(B_hbm * fps / BW_hbm, B_smem * fps / BW_smem), both terms
     reported; the larger fraction names the bound.  Algorithmic bytes per frame: HBM = int8 LLRs in + packed information
     bits, ok flag and iteration count out; shared memory = 4 bytes per edge-lane per iteration (read L, read R, write L,
@@ -235,6 +236,16 @@ def kernel_roofline(F, N, out_words, edges, mean_iters, launch_ms, hbm_peak, hbm
                       "peak_source": onchip_src},
              "l2_message_scratch": {"bytes_per_frame": l2_msg_bytes, "achieved": l2_gbps, "peak": l2_peak, "frac": l2_gbps / l2_peak,
                                     "peak_source": onchip_src}}
+    if ncu and ncu.get("warp_inst_per_frame_iteration") and sm_mhz:
+        # what actually binds (not a byte resource, so it never becomes `bound`): warp instructions issued per second against
+        # one per cycle and scheduler; instructions per frame-iteration come from the committed ncu capture, the rate is live
+        ginst = ncu["warp_inst_per_frame_iteration"] * mean_iters * F / sec / 1e9
+        peak = n_sm * 4 * sm_mhz / 1e3
+        terms["issue"] = {"warp_inst_per_frame_iteration": ncu["warp_inst_per_frame_iteration"], "achieved": ginst, "peak": peak,
+                          "unit": "G warp-inst/s", "frac": ginst / peak,
+                          # the row code's own budget: 43 thread instructions per edge and 4 check lanes (layered_i8s.cu header)
+                          "edge_code_share": 43.0 * edges / 4 / 32 / ncu["warp_inst_per_frame_iteration"],
+                          "peak_source": "%d SMs x 4 schedulers x %.0f MHz (clocks sampled in the timed region)" % (n_sm, sm_mhz)}
     bound = "smem" if terms["smem"]["frac"] >= terms["hbm"]["frac"] else "hbm"
     r = {"bound": bound, "kernel": "layered_i8s_kernel", "achieved": terms[bound]["achieved"], "peak": terms[bound]["peak"], "unit": "GB/s",
          "frac": terms[bound]["frac"], "peak_source": terms[bound]["peak_source"], "bytes_per_frame": terms[bound]["bytes_per_frame"],
@@ -482,7 +493,9 @@ def run_ours(args, rank, world, local_rank):
     smem_peak, l2_peak, onchip_src = onchip_peaks()
     ncu = ncu_latest()
     launch_ms = float(np.mean(per_launch_ms))
-    roofline = kernel_roofline(F, N, dec.out_words, code.edges, mean_iters, launch_ms, peak, peak_src, smem_peak, l2_peak, onchip_src, ncu)
+    sm_mhz = (clocks or {}).get("sm_mhz") if isinstance(clocks, dict) else None
+    roofline = kernel_roofline(F, N, dec.out_words, code.edges, mean_iters, launch_ms, peak, peak_src, smem_peak, l2_peak, onchip_src, ncu,
+                               sm_mhz=sm_mhz)
 
     cpu = None
     if not args.no_cpu:
@@ -506,7 +519,9 @@ def run_ours(args, rank, world, local_rank):
         line["fixed10"] = {"value": F * world * K / (fixed10_ms * 1e-3) / 1e6, "unit": "Mbit/s", "ms_per_step": fixed10_ms, "iterations": MAX_ITER,
                            "early_stop": False,
                            "roofline": kernel_roofline(F, N, dec.out_words, code.edges, float(MAX_ITER), fixed10_ms, peak, peak_src, smem_peak,
-                                                       l2_peak, onchip_src, None)}
+                                                       l2_peak, onchip_src,
+                                                       {"warp_inst_per_frame_iteration": (ncu or {}).get("fixed10_warp_inst_per_frame_iteration")},
+                                                       sm_mhz=sm_mhz)}
     if bit_in:
         line["value_bit_input"] = {"value": F * world * K / (bit_in_ms * 1e-3) / 1e6, "unit": "Mbit/s", "ms_per_step": bit_in_ms,
                                    "hbm_bytes_per_frame": dec.cw_words * 4 + dec.out_words * 4 + 3,

@@ -39,6 +39,8 @@ def main():
     ap.add_argument("--kernel", default=None)
     ap.add_argument("--frames", type=int, default=0)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--fixed10-into", default=None, help="merge this (fixed-10-iterations) capture's counters into an existing json")
+    ap.add_argument("--mean-iters", type=float, default=0.0, help="mean decoder iterations per frame in that launch")
     a = ap.parse_args()
     raw = subprocess.run(["ncu", "-i", a.rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
@@ -57,6 +59,18 @@ def main():
     if a.out != '-':
         open(a.out, 'w').write(txt)
     print(txt)
+    if a.fixed10_into:
+        num = lambda k: float(vals[k][0].replace(",", "")) if k in vals else None
+        d = json.load(open(a.fixed10_into))
+        rd, wr = to_bytes(*vals['dram__bytes_read.sum']), to_bytes(*vals['dram__bytes_write.sum'])
+        d.update({"fixed10_summary": os.path.relpath(a.out) if a.out != '-' else None, "fixed10_frames_in_launch": a.frames,
+                  "fixed10_dram_bytes_per_frame": (rd + wr) / a.frames if a.frames else None,
+                  "fixed10_issue_active_pct": num('smsp__issue_active.avg.pct_of_peak_sustained_active'),
+                  "fixed10_l2_hit_rate_pct": num('lts__t_sector_hit_rate.pct'),
+                  "fixed10_warp_inst_per_frame_iteration": (num('smsp__inst_executed.sum') / a.frames / a.mean_iters
+                                                            if a.frames and a.mean_iters else None)})
+        json.dump(d, open(a.fixed10_into, "w"), indent=1)
+        print("merged into", a.fixed10_into)
     if a.json:
         rd, wr = to_bytes(*vals['dram__bytes_read.sum']), to_bytes(*vals['dram__bytes_write.sum'])
         try:
@@ -72,7 +86,12 @@ def main():
              "warps_active_pct": num('sm__warps_active.avg.pct_of_peak_sustained_active'),
              "alu_pipe_pct": num('sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active'),
              "fma_fp16_pipe_pct": num('sm__inst_executed_pipe_fma_type_fp16.avg.pct_of_peak_sustained_active'),
-             "registers_per_thread": num('launch__registers_per_thread')}
+             "registers_per_thread": num('launch__registers_per_thread'),
+             "l2_hit_rate_pct": num('lts__t_sector_hit_rate.pct'),
+             "warp_inst_executed": num('smsp__inst_executed.sum')}
+        if a.frames and a.mean_iters and d["warp_inst_executed"]:
+            d["mean_iters_in_launch"] = a.mean_iters
+            d["warp_inst_per_frame_iteration"] = d["warp_inst_executed"] / a.frames / a.mean_iters
         if vals.get('gpu__time_duration.sum', ("", ""))[1] == "us" and d["gpu_time_ms"]:
             d["gpu_time_ms"] /= 1e3
         json.dump(d, open(a.json, "w"), indent=1)

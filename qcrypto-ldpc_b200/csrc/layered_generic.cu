@@ -51,8 +51,15 @@ __device__ __forceinline__ int clipi(int x, int lo, int hi) { return min(max(x, 
 
 // One check (block row with DC edges starting at `ed`, check lane `lane`): beliefs in shared memory, old messages at
 // Rl[j * Z] (not read when `first`), new messages and beliefs written back.
+// Belief addressing: the edge table holds, per edge, the BYTE offset of belief (column, lane 0 + shift) from the belief base
+// `Lb` and the wrap threshold Z - shift; check lane `lane` reads the belief at  e.x + lane_b - (lane >= e.y ? wrap_b : 0)
+// (lane_b = lane * sizeof(LT), wrap_b = Z * sizeof(LT)): compare, select, one 3-input add -- no index scaling, no modulo.
+struct Lane { int lane, lane_b, wrap_b; };
+__device__ __forceinline__ int bel_off(const int2 e, const Lane &t) { return e.x + t.lane_b - (t.lane >= e.y ? t.wrap_b : 0); }
+template <typename LT> __device__ __forceinline__ LT &bel(char *Lb, int off) { return *reinterpret_cast<LT *>(Lb + off); }
+
 template <typename LT, typename MT, int DC>
-__device__ __forceinline__ void row_lane(const Upd u, LT *L, MT *Rl, const int2 *ed, int lane, int Z, int synbit, bool first)
+__device__ __forceinline__ void row_lane(const Upd u, char *Lb, MT *Rl, const int2 *ed, const Lane t, int Z, int synbit, bool first)
 {
     constexpr bool kFloat = std::is_floating_point<LT>::value;
     typedef typename std::conditional<kFloat, float, int>::type XT;
@@ -60,12 +67,9 @@ __device__ __forceinline__ void row_lane(const Upd u, LT *L, MT *Rl, const int2 
     int idx[DC];
 #pragma unroll
     for (int j = 0; j < DC; ++j) {
-        const int2 e = ed[j];               // (block column * Z, shift)
-        int l = lane + e.y;
-        if (l >= Z) l -= Z;
-        idx[j] = e.x + l;
+        idx[j] = bel_off(ed[j], t);
         const XT ro = first ? (XT)0 : (XT)Rl[j * Z];
-        x[j] = (XT)L[idx[j]] - ro;
+        x[j] = (XT)bel<LT>(Lb, idx[j]) - ro;
     }
     if constexpr (kFloat) {
         int sign = synbit;
@@ -86,14 +90,17 @@ __device__ __forceinline__ void row_lane(const Upd u, LT *L, MT *Rl, const int2 
                 const float mag = two_atanh(u, r);
                 const float out = (sign ^ (signbit(x[j]) ? 1 : 0)) ? -mag : mag;
                 Rl[j * Z] = out;
-                L[idx[j]] = x[j] + out;
+                bel<LT>(Lb, idx[j]) = x[j] + out;
             }
         } else {
+            // min-sum on the raw bits: the sign product is the XOR of the words (bit 31), the new message is the
+            // magnitude's bits with that bit set -- one logic instruction each, no shifts, compares or selects
+            uint32_t sacc = (uint32_t)synbit << 31;
             float min1 = 3.402823466e+38f, min2 = 3.402823466e+38f;
 #pragma unroll
             for (int j = 0; j < DC; ++j) {
                 const float a = fabsf(x[j]);
-                sign ^= signbit(x[j]) ? 1 : 0;
+                sacc ^= __float_as_uint(x[j]);
                 min2 = fminf(min2, fmaxf(a, min1));
                 min1 = fminf(min1, a);
             }
@@ -102,10 +109,10 @@ __device__ __forceinline__ void row_lane(const Upd u, LT *L, MT *Rl, const int2 
             else if (u.rule == QLDPC_RULE_OMS) { cst1 = fmaxf(0.0f, min2 - u.offset); cst2 = fmaxf(0.0f, min1 - u.offset); }
 #pragma unroll
             for (int j = 0; j < DC; ++j) {
-                const float mag = (fabsf(x[j]) == min1) ? cst1 : cst2;
-                const float out = (sign ^ (signbit(x[j]) ? 1 : 0)) ? -mag : mag;
+                const float mag = (fabsf(x[j]) == min1) ? cst1 : cst2;     // >= +0
+                const float out = __uint_as_float(((sacc ^ __float_as_uint(x[j])) & 0x80000000u) | __float_as_uint(mag));
                 Rl[j * Z] = out;
-                L[idx[j]] = x[j] + out;
+                bel<LT>(Lb, idx[j]) = x[j] + out;
             }
         }
     } else {
@@ -129,7 +136,7 @@ __device__ __forceinline__ void row_lane(const Upd u, LT *L, MT *Rl, const int2 
             const int mag = (abs(t) == min1) ? c1 : c2;
             const int out = (sign ^ (t < 0)) ? -mag : mag;
             Rl[j * Z] = (MT)out;
-            L[idx[j]] = (LT)clipi(x[j] + out, -(u.app_max + 1), u.app_max);
+            bel<LT>(Lb, idx[j]) = (LT)clipi(x[j] + out, -(u.app_max + 1), u.app_max);
         }
     }
 }
@@ -140,62 +147,68 @@ __device__ __forceinline__ void row_lane(const Upd u, LT *L, MT *Rl, const int2 
 // +-(j == index ? c1 : c2): exact, because on a tie of the minimum c1 == c2.  Planes: Rc[plane * Z] (one 128-byte line per
 // warp and plane).  BG1 Z=384 float: 212 KB of messages per frame instead of 485 KB, 3 loads + 3 stores per row instead of
 // 2 dc; the scratch of all frames in flight fits in L2 again.
+// Float tier: everything on the raw bits.  meta = imin << 27 | sign bits, the sign of edge j at bit DC-1-j (the word is
+// built by funnel-shifting one sign bit in per edge); the old message of edge j is (j == imin ? c1 : c2) with bit 31 taken
+// from meta << (32 - DC + j); the new one is the magnitude's bits with the sign product's bit 31.
 template <typename LT, int DC>
-__device__ __forceinline__ void row_lane_cmp(const Upd u, LT *L, uint32_t *Rc, const int2 *ed, int lane, int Z, int synbit, bool first)
+__device__ __forceinline__ void row_lane_cmp(const Upd u, char *Lb, uint32_t *Rc, const int2 *ed, const Lane t, int Z, int synbit, bool first)
 {
     constexpr bool kFloat = std::is_floating_point<LT>::value;
     typedef typename std::conditional<kFloat, float, int>::type XT;
     static_assert(DC <= 27, "index (5 bits) + sign bits share one word");
-    XT c1o = 0, c2o = 0;
-    uint32_t meta = 0;
-    if (!first) {
-        if constexpr (kFloat) {
-            c1o = __uint_as_float(Rc[0]); c2o = __uint_as_float(Rc[Z]); meta = Rc[2 * Z];
-        } else {
-            const uint32_t cc = Rc[0];
-            c1o = (int)(cc & 0xffffu); c2o = (int)(cc >> 16); meta = Rc[Z];
-        }
-    }
-    const int idxo = (int)(meta >> 27);
-    XT x[DC];
     int idx[DC];
-#pragma unroll
-    for (int j = 0; j < DC; ++j) {
-        const int2 e = ed[j];               // (block column * Z, shift)
-        int l = lane + e.y;
-        if (l >= Z) l -= Z;
-        idx[j] = e.x + l;
-        const XT m = (j == idxo) ? c1o : c2o;
-        const XT ro = ((meta >> j) & 1u) ? -m : m;          // first iteration: c1o = c2o = 0, meta = 0
-        x[j] = (XT)L[idx[j]] - ro;
-    }
-    uint32_t nmeta = 0;
-    int imin = 0;
     if constexpr (kFloat) {
-        int sign = synbit;
+        uint32_t c1o = 0, c2o = 0, meta = 0;
+        if (!first) { c1o = Rc[0]; c2o = Rc[Z]; meta = Rc[2 * Z]; }
+        const int idxo = (int)(meta >> 27);
+        float x[DC];
+        uint32_t sacc = (uint32_t)synbit << 31;
         float min1 = 3.402823466e+38f, min2 = 3.402823466e+38f;
 #pragma unroll
         for (int j = 0; j < DC; ++j) {
+            idx[j] = bel_off(ed[j], t);
+            const uint32_t m = (j == idxo) ? c1o : c2o;     // first iteration: c1o = c2o = 0, meta = 0 -> +0
+            const float ro = __uint_as_float(m ^ ((meta << (32 - DC + j)) & 0x80000000u));
+            x[j] = bel<LT>(Lb, idx[j]) - ro;
             const float a = fabsf(x[j]);
-            sign ^= signbit(x[j]) ? 1 : 0;
+            sacc ^= __float_as_uint(x[j]);
             min2 = fminf(min2, fmaxf(a, min1));
             min1 = fminf(min1, a);
         }
         float cst1 = 0.f, cst2 = 0.f;
         if (u.rule == QLDPC_RULE_NMS) { cst1 = min2 * u.norm; cst2 = min1 * u.norm; }
         else if (u.rule == QLDPC_RULE_OMS) { cst1 = fmaxf(0.0f, min2 - u.offset); cst2 = fmaxf(0.0f, min1 - u.offset); }
+        uint32_t nmeta = 0;
+        int imin = 0;
 #pragma unroll
         for (int j = 0; j < DC; ++j) {
             const bool is_min = fabsf(x[j]) == min1;
-            const float mag = is_min ? cst1 : cst2;
-            const int neg = sign ^ (signbit(x[j]) ? 1 : 0);
-            const float out = neg ? -mag : mag;
+            const uint32_t s = sacc ^ __float_as_uint(x[j]);                       // bit 31: sign of the new message
+            const float out = __uint_as_float((s & 0x80000000u) | __float_as_uint(is_min ? cst1 : cst2));
             imin = is_min ? j : imin;
-            nmeta |= (uint32_t)neg << j;
-            L[idx[j]] = x[j] + out;
+            nmeta = __funnelshift_l(s, nmeta, 1);                                  // nmeta << 1 | s >> 31
+            bel<LT>(Lb, idx[j]) = x[j] + out;
         }
         Rc[0] = __float_as_uint(cst1); Rc[Z] = __float_as_uint(cst2); Rc[2 * Z] = nmeta | ((uint32_t)imin << 27);
     } else {
+    XT c1o = 0, c2o = 0;
+    uint32_t meta = 0;
+    if (!first) {
+        const uint32_t cc = Rc[0];
+        c1o = (int)(cc & 0xffffu); c2o = (int)(cc >> 16); meta = Rc[Z];
+    }
+    const int idxo = (int)(meta >> 27);
+    XT x[DC];
+#pragma unroll
+    for (int j = 0; j < DC; ++j) {
+        idx[j] = bel_off(ed[j], t);
+        const XT m = (j == idxo) ? c1o : c2o;
+        const XT ro = ((meta >> j) & 1u) ? -m : m;          // first iteration: c1o = c2o = 0, meta = 0
+        x[j] = (XT)bel<LT>(Lb, idx[j]) - ro;
+    }
+    uint32_t nmeta = 0;
+    int imin = 0;
+    {
         const int lo = -(u.msg_max + 1), hi = u.msg_max;
         int sign = synbit, min1 = 1 << 30, min2 = 1 << 30;
 #pragma unroll
@@ -219,17 +232,18 @@ __device__ __forceinline__ void row_lane_cmp(const Upd u, LT *L, uint32_t *Rc, c
             const int out = neg ? -mag : mag;
             imin = is_min ? j : imin;
             nmeta |= (uint32_t)neg << j;
-            L[idx[j]] = (LT)clipi(x[j] + out, -(u.app_max + 1), u.app_max);
+            bel<LT>(Lb, idx[j]) = (LT)clipi(x[j] + out, -(u.app_max + 1), u.app_max);
         }
         Rc[0] = (uint32_t)c1 | ((uint32_t)c2 << 16); Rc[Z] = nmeta | ((uint32_t)imin << 27);
+    }
     }
 }
 
 template <typename LT>
-__device__ __forceinline__ void row_dispatch_cmp(const Upd u, const RowMeta ly, LT *L, uint32_t *Rc, const int2 *ed, int lane, int Z,
+__device__ __forceinline__ void row_dispatch_cmp(const Upd u, const RowMeta ly, char *Lb, uint32_t *Rc, const int2 *ed, const Lane t, int Z,
                                                  int synbit, bool first)
 {
-#define QL_DC(D) case D: row_lane_cmp<LT, D>(u, L, Rc, ed, lane, Z, synbit, first); return;
+#define QL_DC(D) case D: row_lane_cmp<LT, D>(u, Lb, Rc, ed, t, Z, synbit, first); return;
     switch (ly.degree) {   // block-uniform; the host selects this mode only when every row is within the compiled degrees
         QL_DC(1) QL_DC(2) QL_DC(3) QL_DC(4) QL_DC(5) QL_DC(6) QL_DC(7) QL_DC(8) QL_DC(9) QL_DC(10)
         QL_DC(11) QL_DC(12) QL_DC(13) QL_DC(14) QL_DC(15) QL_DC(16) QL_DC(17) QL_DC(18) QL_DC(19) QL_DC(20)
@@ -240,16 +254,13 @@ __device__ __forceinline__ void row_dispatch_cmp(const Upd u, const RowMeta ly, 
 
 // any degree: two passes over memory (rows heavier than the compiled degrees)
 template <typename LT, typename MT>
-__device__ __noinline__ void row_lane_any(const Upd u, LT *L, MT *Rl, const int2 *ed, int dc, int lane, int Z, int synbit, bool first)
+__device__ __noinline__ void row_lane_any(const Upd u, char *Lb, MT *Rl, const int2 *ed, int dc, const Lane t, int Z, int synbit, bool first)
 {
     constexpr bool kFloat = std::is_floating_point<LT>::value;
     auto contrib = [&](int j, int &at) {
-        const int2 e = ed[j];
-        int l = lane + e.y;
-        if (l >= Z) l -= Z;
-        at = e.x + l;
-        if constexpr (kFloat) return (float)L[at] - (first ? 0.0f : (float)Rl[j * Z]);
-        else return (int)L[at] - (first ? 0 : (int)Rl[j * Z]);
+        at = bel_off(ed[j], t);
+        if constexpr (kFloat) return (float)bel<LT>(Lb, at) - (first ? 0.0f : (float)Rl[j * Z]);
+        else return (int)bel<LT>(Lb, at) - (first ? 0 : (int)Rl[j * Z]);
     };
     int at;
     if constexpr (kFloat) {
@@ -283,7 +294,7 @@ __device__ __noinline__ void row_lane_any(const Upd u, LT *L, MT *Rl, const int2
             }
             const float out = (sign ^ (signbit(x) ? 1 : 0)) ? -mag : mag;
             Rl[j * Z] = out;
-            L[at] = x + out;
+            bel<LT>(Lb, at) = x + out;
         }
     } else {
         const int lo = -(u.msg_max + 1), hi = u.msg_max;
@@ -305,16 +316,16 @@ __device__ __noinline__ void row_lane_any(const Upd u, LT *L, MT *Rl, const int2
             const int mag = (abs(t) == min1) ? c1 : c2;
             const int out = (sign ^ (t < 0)) ? -mag : mag;
             Rl[j * Z] = (MT)out;
-            L[at] = (LT)clipi(c + out, -(u.app_max + 1), u.app_max);
+            bel<LT>(Lb, at) = (LT)clipi(c + out, -(u.app_max + 1), u.app_max);
         }
     }
 }
 
 template <typename LT, typename MT>
-__device__ __forceinline__ void row_dispatch(const Upd u, const RowMeta ly, LT *L, MT *Rl, const int2 *ed, int lane, int Z, int synbit,
+__device__ __forceinline__ void row_dispatch(const Upd u, const RowMeta ly, char *Lb, MT *Rl, const int2 *ed, const Lane t, int Z, int synbit,
                                              bool first)
 {
-#define QL_DC(D) case D: row_lane<LT, MT, D>(u, L, Rl, ed, lane, Z, synbit, first); return;
+#define QL_DC(D) case D: row_lane<LT, MT, D>(u, Lb, Rl, ed, t, Z, synbit, first); return;
     switch (ly.degree) {   // block-uniform: no divergence
         QL_DC(1) QL_DC(2) QL_DC(3) QL_DC(4) QL_DC(5) QL_DC(6) QL_DC(7) QL_DC(8) QL_DC(9) QL_DC(10)
         QL_DC(11) QL_DC(12) QL_DC(13) QL_DC(14) QL_DC(15) QL_DC(16) QL_DC(17) QL_DC(18) QL_DC(19) QL_DC(20)
@@ -322,7 +333,7 @@ __device__ __forceinline__ void row_dispatch(const Upd u, const RowMeta ly, LT *
     }
 #undef QL_DC
     static_assert(kMaxDc == 20, "row_dispatch lists the compiled degrees");
-    row_lane_any<LT, MT>(u, L, Rl, ed, ly.degree, lane, Z, synbit, first);
+    row_lane_any<LT, MT>(u, Lb, Rl, ed, ly.degree, t, Z, synbit, first);
 }
 
 __device__ __forceinline__ int syn_bit(const uint32_t *syn, int m) { return syn ? (int)((syn[m >> 5] >> (31 - (m & 31))) & 1u) : 0; }
@@ -341,8 +352,13 @@ __global__ void __launch_bounds__(MAXT, MINB) layered_generic_kernel(const Layer
     LT *L;
     if constexpr (GL) L = reinterpret_cast<LT *>(p.app) + (size_t)blockIdx.x * p.N;
     else L = reinterpret_cast<LT *>(edges + p.nnz);     // no select with a global pointer here: the accesses stay LDS / STS
+    // belief base and edge table for bel_off(): with the beliefs in shared memory the base is the start of the dynamic
+    // shared memory, so that every access is LDS / STS [register + immediate]
+    char *Lb = GL ? reinterpret_cast<char *>(L) : smem;
+    const int l_off = GL ? 0 : (int)(reinterpret_cast<char *>(L) - smem);
     for (int r = tid; r < R; r += nt) rows[r] = RowMeta{p.layers[r].edge_begin, p.layers[r].degree};
-    for (int e = tid; e < p.nnz; e += nt) edges[e] = make_int2(p.aux[e].col * Z, p.aux[e].shift);
+    for (int e = tid; e < p.nnz; e += nt)
+        edges[e] = make_int2(l_off + (int)sizeof(LT) * (p.aux[e].col * Z + p.aux[e].shift), Z - p.aux[e].shift);
     MT *Rg = reinterpret_cast<MT *>(p.msg) + (size_t)blockIdx.x * p.nnz * Z;
     const Upd upd{p.rule, p.offset_int, p.norm_eighths, p.msg_max, p.app_max, p.norm, p.offset, p.fast_spa};
 
@@ -353,12 +369,8 @@ __global__ void __launch_bounds__(MAXT, MINB) layered_generic_kernel(const Layer
             const RowMeta ly = rows[r];
             for (int i = tid; i < Z; i += nt) {
                 unsigned s = (unsigned)syn_bit(syn, r * Z + i);
-                for (int j = 0; j < ly.degree; ++j) {
-                    const int2 e = edges[ly.edge_begin + j];
-                    int l = i + e.y;
-                    if (l >= Z) l -= Z;
-                    s ^= (unsigned)(L[e.x + l] < (LT)0);
-                }
+                const Lane t{i, i * (int)sizeof(LT), Z * (int)sizeof(LT)};
+                for (int j = 0; j < ly.degree; ++j) s ^= (unsigned)(bel<LT>(Lb, bel_off(edges[ly.edge_begin + j], t)) < (LT)0);
                 bad |= (int)(s & 1u);
             }
         }
@@ -381,16 +393,16 @@ __global__ void __launch_bounds__(MAXT, MINB) layered_generic_kernel(const Layer
                 for (int r = 0; r < R; ++r) {
                     const RowMeta ly = rows[r];
                     for (int i = tid; i < Z; i += nt)
-                        row_dispatch_cmp<LT>(upd, ly, L, Rc + ((size_t)r * kPlanes * Z + i), edges + ly.edge_begin, i, Z,
-                                             syn_bit(syn, r * Z + i), it == 0);
+                        row_dispatch_cmp<LT>(upd, ly, Lb, Rc + ((size_t)r * kPlanes * Z + i), edges + ly.edge_begin,
+                                             Lane{i, i * (int)sizeof(LT), Z * (int)sizeof(LT)}, Z, syn_bit(syn, r * Z + i), it == 0);
                     __syncthreads();
                 }
             } else {
                 for (int r = 0; r < R; ++r) {
                     const RowMeta ly = rows[r];
                     for (int i = tid; i < Z; i += nt)
-                        row_dispatch<LT, MT>(upd, ly, L, Rg + ((size_t)ly.edge_begin * Z + i), edges + ly.edge_begin, i, Z,
-                                             syn_bit(syn, r * Z + i), it == 0);
+                        row_dispatch<LT, MT>(upd, ly, Lb, Rg + ((size_t)ly.edge_begin * Z + i), edges + ly.edge_begin,
+                                             Lane{i, i * (int)sizeof(LT), Z * (int)sizeof(LT)}, Z, syn_bit(syn, r * Z + i), it == 0);
                     __syncthreads();
                 }
             }

@@ -56,9 +56,16 @@ __device__ __forceinline__ int clipi(int x, int lo, int hi) { return min(max(x, 
 // (lane_b = lane * sizeof(LT), wrap_b = Z * sizeof(LT)): compare, select, one 3-input add -- no index scaling, no modulo.
 struct Lane { int lane, lane_b, wrap_b; };
 __device__ __forceinline__ int bel_off(const int2 e, const Lane &t) { return e.x + t.lane_b - (t.lane >= e.y ? t.wrap_b : 0); }
-template <typename LT> __device__ __forceinline__ LT &bel(char *Lb, int off) { return *reinterpret_cast<LT *>(Lb + off); }
+// GL = false: the beliefs sit in dynamic shared memory and `off` counts from its start -- addressed through the extern array
+// itself, so that the access is LDS / STS [register + constant] with no pointer arithmetic; GL = true: global scratch at Lb
+extern __shared__ __align__(16) char qldpc_lg_smem[];
+template <typename LT, bool GL> __device__ __forceinline__ LT &bel(char *Lb, int off)
+{
+    if constexpr (GL) return *reinterpret_cast<LT *>(Lb + off);
+    else return *reinterpret_cast<LT *>(qldpc_lg_smem + off);
+}
 
-template <typename LT, typename MT, int DC>
+template <typename LT, typename MT, int DC, bool GL>
 __device__ __forceinline__ void row_lane(const Upd u, char *Lb, MT *Rl, const int2 *ed, const Lane t, int Z, int synbit, bool first)
 {
     constexpr bool kFloat = std::is_floating_point<LT>::value;
@@ -69,7 +76,7 @@ __device__ __forceinline__ void row_lane(const Upd u, char *Lb, MT *Rl, const in
     for (int j = 0; j < DC; ++j) {
         idx[j] = bel_off(ed[j], t);
         const XT ro = first ? (XT)0 : (XT)Rl[j * Z];
-        x[j] = (XT)bel<LT>(Lb, idx[j]) - ro;
+        x[j] = (XT)bel<LT, GL>(Lb, idx[j]) - ro;
     }
     if constexpr (kFloat) {
         int sign = synbit;
@@ -90,7 +97,7 @@ __device__ __forceinline__ void row_lane(const Upd u, char *Lb, MT *Rl, const in
                 const float mag = two_atanh(u, r);
                 const float out = (sign ^ (signbit(x[j]) ? 1 : 0)) ? -mag : mag;
                 Rl[j * Z] = out;
-                bel<LT>(Lb, idx[j]) = x[j] + out;
+                bel<LT, GL>(Lb, idx[j]) = x[j] + out;
             }
         } else {
             // min-sum on the raw bits: the sign product is the XOR of the words (bit 31), the new message is the
@@ -112,7 +119,7 @@ __device__ __forceinline__ void row_lane(const Upd u, char *Lb, MT *Rl, const in
                 const float mag = (fabsf(x[j]) == min1) ? cst1 : cst2;     // >= +0
                 const float out = __uint_as_float(((sacc ^ __float_as_uint(x[j])) & 0x80000000u) | __float_as_uint(mag));
                 Rl[j * Z] = out;
-                bel<LT>(Lb, idx[j]) = x[j] + out;
+                bel<LT, GL>(Lb, idx[j]) = x[j] + out;
             }
         }
     } else {
@@ -136,7 +143,7 @@ __device__ __forceinline__ void row_lane(const Upd u, char *Lb, MT *Rl, const in
             const int mag = (abs(t) == min1) ? c1 : c2;
             const int out = (sign ^ (t < 0)) ? -mag : mag;
             Rl[j * Z] = (MT)out;
-            bel<LT>(Lb, idx[j]) = (LT)clipi(x[j] + out, -(u.app_max + 1), u.app_max);
+            bel<LT, GL>(Lb, idx[j]) = (LT)clipi(x[j] + out, -(u.app_max + 1), u.app_max);
         }
     }
 }
@@ -150,7 +157,7 @@ __device__ __forceinline__ void row_lane(const Upd u, char *Lb, MT *Rl, const in
 // Float tier: everything on the raw bits.  meta = imin << 27 | sign bits, the sign of edge j at bit DC-1-j (the word is
 // built by funnel-shifting one sign bit in per edge); the old message of edge j is (j == imin ? c1 : c2) with bit 31 taken
 // from meta << (32 - DC + j); the new one is the magnitude's bits with the sign product's bit 31.
-template <typename LT, int DC>
+template <typename LT, int DC, bool GL>
 __device__ __forceinline__ void row_lane_cmp(const Upd u, char *Lb, uint32_t *Rc, const int2 *ed, const Lane t, int Z, int synbit, bool first)
 {
     constexpr bool kFloat = std::is_floating_point<LT>::value;
@@ -169,7 +176,7 @@ __device__ __forceinline__ void row_lane_cmp(const Upd u, char *Lb, uint32_t *Rc
             idx[j] = bel_off(ed[j], t);
             const uint32_t m = (j == idxo) ? c1o : c2o;     // first iteration: c1o = c2o = 0, meta = 0 -> +0
             const float ro = __uint_as_float(m ^ ((meta << (32 - DC + j)) & 0x80000000u));
-            x[j] = bel<LT>(Lb, idx[j]) - ro;
+            x[j] = bel<LT, GL>(Lb, idx[j]) - ro;
             const float a = fabsf(x[j]);
             sacc ^= __float_as_uint(x[j]);
             min2 = fminf(min2, fmaxf(a, min1));
@@ -187,7 +194,7 @@ __device__ __forceinline__ void row_lane_cmp(const Upd u, char *Lb, uint32_t *Rc
             const float out = __uint_as_float((s & 0x80000000u) | __float_as_uint(is_min ? cst1 : cst2));
             imin = is_min ? j : imin;
             nmeta = __funnelshift_l(s, nmeta, 1);                                  // nmeta << 1 | s >> 31
-            bel<LT>(Lb, idx[j]) = x[j] + out;
+            bel<LT, GL>(Lb, idx[j]) = x[j] + out;
         }
         Rc[0] = __float_as_uint(cst1); Rc[Z] = __float_as_uint(cst2); Rc[2 * Z] = nmeta | ((uint32_t)imin << 27);
     } else {
@@ -204,7 +211,7 @@ __device__ __forceinline__ void row_lane_cmp(const Upd u, char *Lb, uint32_t *Rc
         idx[j] = bel_off(ed[j], t);
         const XT m = (j == idxo) ? c1o : c2o;
         const XT ro = ((meta >> j) & 1u) ? -m : m;          // first iteration: c1o = c2o = 0, meta = 0
-        x[j] = (XT)bel<LT>(Lb, idx[j]) - ro;
+        x[j] = (XT)bel<LT, GL>(Lb, idx[j]) - ro;
     }
     uint32_t nmeta = 0;
     int imin = 0;
@@ -232,18 +239,18 @@ __device__ __forceinline__ void row_lane_cmp(const Upd u, char *Lb, uint32_t *Rc
             const int out = neg ? -mag : mag;
             imin = is_min ? j : imin;
             nmeta |= (uint32_t)neg << j;
-            bel<LT>(Lb, idx[j]) = (LT)clipi(x[j] + out, -(u.app_max + 1), u.app_max);
+            bel<LT, GL>(Lb, idx[j]) = (LT)clipi(x[j] + out, -(u.app_max + 1), u.app_max);
         }
         Rc[0] = (uint32_t)c1 | ((uint32_t)c2 << 16); Rc[Z] = nmeta | ((uint32_t)imin << 27);
     }
     }
 }
 
-template <typename LT>
+template <typename LT, bool GL>
 __device__ __forceinline__ void row_dispatch_cmp(const Upd u, const RowMeta ly, char *Lb, uint32_t *Rc, const int2 *ed, const Lane t, int Z,
                                                  int synbit, bool first)
 {
-#define QL_DC(D) case D: row_lane_cmp<LT, D>(u, Lb, Rc, ed, t, Z, synbit, first); return;
+#define QL_DC(D) case D: row_lane_cmp<LT, D, GL>(u, Lb, Rc, ed, t, Z, synbit, first); return;
     switch (ly.degree) {   // block-uniform; the host selects this mode only when every row is within the compiled degrees
         QL_DC(1) QL_DC(2) QL_DC(3) QL_DC(4) QL_DC(5) QL_DC(6) QL_DC(7) QL_DC(8) QL_DC(9) QL_DC(10)
         QL_DC(11) QL_DC(12) QL_DC(13) QL_DC(14) QL_DC(15) QL_DC(16) QL_DC(17) QL_DC(18) QL_DC(19) QL_DC(20)
@@ -253,14 +260,14 @@ __device__ __forceinline__ void row_dispatch_cmp(const Upd u, const RowMeta ly, 
 }
 
 // any degree: two passes over memory (rows heavier than the compiled degrees)
-template <typename LT, typename MT>
+template <typename LT, typename MT, bool GL>
 __device__ __noinline__ void row_lane_any(const Upd u, char *Lb, MT *Rl, const int2 *ed, int dc, const Lane t, int Z, int synbit, bool first)
 {
     constexpr bool kFloat = std::is_floating_point<LT>::value;
     auto contrib = [&](int j, int &at) {
         at = bel_off(ed[j], t);
-        if constexpr (kFloat) return (float)bel<LT>(Lb, at) - (first ? 0.0f : (float)Rl[j * Z]);
-        else return (int)bel<LT>(Lb, at) - (first ? 0 : (int)Rl[j * Z]);
+        if constexpr (kFloat) return (float)bel<LT, GL>(Lb, at) - (first ? 0.0f : (float)Rl[j * Z]);
+        else return (int)bel<LT, GL>(Lb, at) - (first ? 0 : (int)Rl[j * Z]);
     };
     int at;
     if constexpr (kFloat) {
@@ -294,7 +301,7 @@ __device__ __noinline__ void row_lane_any(const Upd u, char *Lb, MT *Rl, const i
             }
             const float out = (sign ^ (signbit(x) ? 1 : 0)) ? -mag : mag;
             Rl[j * Z] = out;
-            bel<LT>(Lb, at) = x + out;
+            bel<LT, GL>(Lb, at) = x + out;
         }
     } else {
         const int lo = -(u.msg_max + 1), hi = u.msg_max;
@@ -316,16 +323,16 @@ __device__ __noinline__ void row_lane_any(const Upd u, char *Lb, MT *Rl, const i
             const int mag = (abs(t) == min1) ? c1 : c2;
             const int out = (sign ^ (t < 0)) ? -mag : mag;
             Rl[j * Z] = (MT)out;
-            bel<LT>(Lb, at) = (LT)clipi(c + out, -(u.app_max + 1), u.app_max);
+            bel<LT, GL>(Lb, at) = (LT)clipi(c + out, -(u.app_max + 1), u.app_max);
         }
     }
 }
 
-template <typename LT, typename MT>
+template <typename LT, typename MT, bool GL>
 __device__ __forceinline__ void row_dispatch(const Upd u, const RowMeta ly, char *Lb, MT *Rl, const int2 *ed, const Lane t, int Z, int synbit,
                                              bool first)
 {
-#define QL_DC(D) case D: row_lane<LT, MT, D>(u, Lb, Rl, ed, t, Z, synbit, first); return;
+#define QL_DC(D) case D: row_lane<LT, MT, D, GL>(u, Lb, Rl, ed, t, Z, synbit, first); return;
     switch (ly.degree) {   // block-uniform: no divergence
         QL_DC(1) QL_DC(2) QL_DC(3) QL_DC(4) QL_DC(5) QL_DC(6) QL_DC(7) QL_DC(8) QL_DC(9) QL_DC(10)
         QL_DC(11) QL_DC(12) QL_DC(13) QL_DC(14) QL_DC(15) QL_DC(16) QL_DC(17) QL_DC(18) QL_DC(19) QL_DC(20)
@@ -333,7 +340,7 @@ __device__ __forceinline__ void row_dispatch(const Upd u, const RowMeta ly, char
     }
 #undef QL_DC
     static_assert(kMaxDc == 20, "row_dispatch lists the compiled degrees");
-    row_lane_any<LT, MT>(u, Lb, Rl, ed, ly.degree, t, Z, synbit, first);
+    row_lane_any<LT, MT, GL>(u, Lb, Rl, ed, ly.degree, t, Z, synbit, first);
 }
 
 __device__ __forceinline__ int syn_bit(const uint32_t *syn, int m) { return syn ? (int)((syn[m >> 5] >> (31 - (m & 31))) & 1u) : 0; }
@@ -344,7 +351,7 @@ __device__ __forceinline__ int syn_bit(const uint32_t *syn, int m) { return syn 
 template <typename LT, typename MT, typename IN, int MAXT, int MINB, bool GL>
 __global__ void __launch_bounds__(MAXT, MINB) layered_generic_kernel(const LayeredGenParams p)
 {
-    extern __shared__ __align__(16) char smem[];
+    char *smem = qldpc_lg_smem;
     constexpr bool kFloat = std::is_floating_point<LT>::value;
     const int tid = threadIdx.x, nt = blockDim.x, Z = p.Z, R = p.brows;
     RowMeta *rows = reinterpret_cast<RowMeta *>(smem);
@@ -370,7 +377,7 @@ __global__ void __launch_bounds__(MAXT, MINB) layered_generic_kernel(const Layer
             for (int i = tid; i < Z; i += nt) {
                 unsigned s = (unsigned)syn_bit(syn, r * Z + i);
                 const Lane t{i, i * (int)sizeof(LT), Z * (int)sizeof(LT)};
-                for (int j = 0; j < ly.degree; ++j) s ^= (unsigned)(bel<LT>(Lb, bel_off(edges[ly.edge_begin + j], t)) < (LT)0);
+                for (int j = 0; j < ly.degree; ++j) s ^= (unsigned)(bel<LT, GL>(Lb, bel_off(edges[ly.edge_begin + j], t)) < (LT)0);
                 bad |= (int)(s & 1u);
             }
         }
@@ -386,23 +393,58 @@ __global__ void __launch_bounds__(MAXT, MINB) layered_generic_kernel(const Layer
 
         int it = 0, depth = 0;
         bool ok = false, checked = false;
+        // Instantiations with fewer than 1024 threads serve Z <= blockDim.x only (block_threads): one lane per thread, and the
+        // thread's lane constants, message pointers and -- when the frame has a syndrome and at most 64 block rows -- its R
+        // syndrome bits are set up once per frame, not once per row (the syndrome bit was a dependent global load at the
+        // head of every row).  The 1024-thread instantiations keep the general loop (a thread may own several lanes).
+        // (float tier only: at the 80 registers of the integer instantiations the values kept across the rows spill,
+        // BG1 Z=384 i16 9.8 -> 9.0 Gbit/s)
+        constexpr bool kOnePass = MAXT < 1024 && kFloat;
+        const bool act = tid < Z;
+        const Lane tl{tid, tid * (int)sizeof(LT), Z * (int)sizeof(LT)};
+        const bool syn_in_regs = kOnePass && syn != nullptr && R <= 64;
+        unsigned long long synmask = 0;
+        if (syn_in_regs && act)
+            for (int r = 0; r < R; ++r) synmask |= (unsigned long long)syn_bit(syn, r * Z + tid) << r;
         while (it < p.max_iter) {
             if (p.compressed) {
                 constexpr int kPlanes = kFloat ? 3 : 2;
                 uint32_t *Rc = reinterpret_cast<uint32_t *>(p.msg) + (size_t)blockIdx.x * R * kPlanes * Z;
+                if constexpr (kOnePass) {
+                    uint32_t *Rt = Rc + tid;
+                    const int rstep = kPlanes * Z;
+                    for (int r = 0; r < R; ++r) {
+                        const RowMeta ly = rows[r];
+                        if (act)
+                            row_dispatch_cmp<LT, GL>(upd, ly, Lb, Rt, edges + ly.edge_begin, tl, Z,
+                                                     syn_in_regs ? (int)((synmask >> r) & 1ull) : syn_bit(syn, r * Z + tid), it == 0);
+                        Rt += rstep;
+                        __syncthreads();
+                    }
+                } else {
+                    for (int r = 0; r < R; ++r) {
+                        const RowMeta ly = rows[r];
+                        for (int i = tid; i < Z; i += nt)
+                            row_dispatch_cmp<LT, GL>(upd, ly, Lb, Rc + ((size_t)r * kPlanes * Z + i), edges + ly.edge_begin,
+                                                     Lane{i, i * (int)sizeof(LT), Z * (int)sizeof(LT)}, Z, syn_bit(syn, r * Z + i), it == 0);
+                        __syncthreads();
+                    }
+                }
+            } else if constexpr (kOnePass) {
+                MT *Rt = Rg + tid;
                 for (int r = 0; r < R; ++r) {
                     const RowMeta ly = rows[r];
-                    for (int i = tid; i < Z; i += nt)
-                        row_dispatch_cmp<LT>(upd, ly, Lb, Rc + ((size_t)r * kPlanes * Z + i), edges + ly.edge_begin,
-                                             Lane{i, i * (int)sizeof(LT), Z * (int)sizeof(LT)}, Z, syn_bit(syn, r * Z + i), it == 0);
+                    if (act)
+                        row_dispatch<LT, MT, GL>(upd, ly, Lb, Rt + (size_t)ly.edge_begin * Z, edges + ly.edge_begin, tl, Z,
+                                                 syn_in_regs ? (int)((synmask >> r) & 1ull) : syn_bit(syn, r * Z + tid), it == 0);
                     __syncthreads();
                 }
             } else {
                 for (int r = 0; r < R; ++r) {
                     const RowMeta ly = rows[r];
                     for (int i = tid; i < Z; i += nt)
-                        row_dispatch<LT, MT>(upd, ly, Lb, Rg + ((size_t)ly.edge_begin * Z + i), edges + ly.edge_begin,
-                                             Lane{i, i * (int)sizeof(LT), Z * (int)sizeof(LT)}, Z, syn_bit(syn, r * Z + i), it == 0);
+                        row_dispatch<LT, MT, GL>(upd, ly, Lb, Rg + ((size_t)ly.edge_begin * Z + i), edges + ly.edge_begin,
+                                                 Lane{i, i * (int)sizeof(LT), Z * (int)sizeof(LT)}, Z, syn_bit(syn, r * Z + i), it == 0);
                     __syncthreads();
                 }
             }

@@ -56,13 +56,14 @@ __device__ __forceinline__ int clipi(int x, int lo, int hi) { return min(max(x, 
 // (lane_b = lane * sizeof(LT), wrap_b = Z * sizeof(LT)): compare, select, one 3-input add -- no index scaling, no modulo.
 struct Lane { int lane, lane_b, wrap_b; };
 __device__ __forceinline__ int bel_off(const int2 e, const Lane &t) { return e.x + t.lane_b - (t.lane >= e.y ? t.wrap_b : 0); }
-// GL = false: the beliefs sit in dynamic shared memory and `off` counts from its start -- addressed through the extern array
-// itself, so that the access is LDS / STS [register + constant] with no pointer arithmetic; GL = true: global scratch at Lb
+// GL = false: the beliefs sit in dynamic shared memory and the table offsets are absolute shared-space addresses (the
+// window base is folded into the table), so that an access is LDS / STS [register] with no pointer arithmetic;
+// GL = true: global scratch at Lb
 extern __shared__ __align__(16) char qldpc_lg_smem[];
 template <typename LT, bool GL> __device__ __forceinline__ LT &bel(char *Lb, int off)
 {
     if constexpr (GL) return *reinterpret_cast<LT *>(Lb + off);
-    else return *reinterpret_cast<LT *>(qldpc_lg_smem + off);
+    else return *reinterpret_cast<LT *>(__cvta_shared_to_generic((size_t)(unsigned)off));   // `off` is a shared-space address
 }
 
 template <typename LT, typename MT, int DC, bool GL>
@@ -114,10 +115,12 @@ __device__ __forceinline__ void row_lane(const Upd u, char *Lb, MT *Rl, const in
             float cst1 = 0.f, cst2 = 0.f;
             if (u.rule == QLDPC_RULE_NMS) { cst1 = min2 * u.norm; cst2 = min1 * u.norm; }
             else if (u.rule == QLDPC_RULE_OMS) { cst1 = fmaxf(0.0f, min2 - u.offset); cst2 = fmaxf(0.0f, min1 - u.offset); }
+            // the row's sign product goes into the two magnitudes once; per edge: select, then flip by the edge's own sign
+            const uint32_t c1s = __float_as_uint(cst1) ^ (sacc & 0x80000000u), c2s = __float_as_uint(cst2) ^ (sacc & 0x80000000u);
 #pragma unroll
             for (int j = 0; j < DC; ++j) {
-                const float mag = (fabsf(x[j]) == min1) ? cst1 : cst2;     // >= +0
-                const float out = __uint_as_float(((sacc ^ __float_as_uint(x[j])) & 0x80000000u) | __float_as_uint(mag));
+                const uint32_t ms = (fabsf(x[j]) == min1) ? c1s : c2s;
+                const float out = __uint_as_float(ms ^ (__float_as_uint(x[j]) & 0x80000000u));
                 Rl[j * Z] = out;
                 bel<LT, GL>(Lb, idx[j]) = x[j] + out;
             }
@@ -187,14 +190,16 @@ __device__ __forceinline__ void row_lane_cmp(const Upd u, char *Lb, uint32_t *Rc
         else if (u.rule == QLDPC_RULE_OMS) { cst1 = fmaxf(0.0f, min2 - u.offset); cst2 = fmaxf(0.0f, min1 - u.offset); }
         uint32_t nmeta = 0;
         int imin = 0;
+        // the row's sign product goes into the two magnitudes once; per edge: select, flip by the edge's own sign, and
+        // shift the result's bit 31 into the sign word
+        const uint32_t c1s = __float_as_uint(cst1) ^ (sacc & 0x80000000u), c2s = __float_as_uint(cst2) ^ (sacc & 0x80000000u);
 #pragma unroll
         for (int j = 0; j < DC; ++j) {
             const bool is_min = fabsf(x[j]) == min1;
-            const uint32_t s = sacc ^ __float_as_uint(x[j]);                       // bit 31: sign of the new message
-            const float out = __uint_as_float((s & 0x80000000u) | __float_as_uint(is_min ? cst1 : cst2));
+            const uint32_t ob = (is_min ? c1s : c2s) ^ (__float_as_uint(x[j]) & 0x80000000u);
             imin = is_min ? j : imin;
-            nmeta = __funnelshift_l(s, nmeta, 1);                                  // nmeta << 1 | s >> 31
-            bel<LT, GL>(Lb, idx[j]) = x[j] + out;
+            nmeta = __funnelshift_l(ob, nmeta, 1);                                 // nmeta << 1 | sign of the new message
+            bel<LT, GL>(Lb, idx[j]) = x[j] + __uint_as_float(ob);
         }
         Rc[0] = __float_as_uint(cst1); Rc[Z] = __float_as_uint(cst2); Rc[2 * Z] = nmeta | ((uint32_t)imin << 27);
     } else {
@@ -362,7 +367,7 @@ __global__ void __launch_bounds__(MAXT, MINB) layered_generic_kernel(const Layer
     // belief base and edge table for bel_off(): with the beliefs in shared memory the base is the start of the dynamic
     // shared memory, so that every access is LDS / STS [register + immediate]
     char *Lb = GL ? reinterpret_cast<char *>(L) : smem;
-    const int l_off = GL ? 0 : (int)(reinterpret_cast<char *>(L) - smem);
+    const int l_off = GL ? 0 : (int)(unsigned)__cvta_generic_to_shared(L);
     for (int r = tid; r < R; r += nt) rows[r] = RowMeta{p.layers[r].edge_begin, p.layers[r].degree};
     for (int e = tid; e < p.nnz; e += nt)
         edges[e] = make_int2(l_off + (int)sizeof(LT) * (p.aux[e].col * Z + p.aux[e].shift), Z - p.aux[e].shift);

@@ -389,6 +389,39 @@ __global__ void __launch_bounds__(MAXT, MINB) layered_generic_kernel(const Layer
         return __syncthreads_or(bad) != 0;
     };
 
+    // The same test on bit vectors when Z is a multiple of 32 and a thread owns one lane (every 5G lifting size >= 32): the
+    // hard decisions of a block column are balloted into Z-bit vectors behind the beliefs (N / 8 bytes), and a syndrome word
+    // (row, 32 check lanes) is the XOR of the rotated windows of its columns' vectors -- two loads and a funnel shift per
+    // edge and WORD instead of an address computation, a load and a compare per edge and LANE.
+    uint32_t *hd = reinterpret_cast<uint32_t *>(L + p.N);
+    const bool packed_syn = !GL && (Z & 31) == 0 && nt >= Z;
+    auto syndrome_bad_packed = [&](const uint32_t *syn) {
+        const int ZW = Z >> 5;
+        for (int c = 0; c < p.bcols; ++c) {
+            const bool neg = tid < Z && L[c * Z + tid] < (LT)0;
+            const unsigned b = __ballot_sync(0xffffffffu, neg);
+            if ((tid & 31) == 0 && tid < Z) hd[c * ZW + (tid >> 5)] = b;      // bit k of word w = lane 32 w + k
+        }
+        __syncthreads();
+        int bad = 0;
+        for (int item = tid; item < R * ZW; item += nt) {
+            const int r = item / ZW, w = item - r * ZW;
+            const RowMeta ly = rows[r];
+            uint32_t acc = syn ? __brev(syn[r * ZW + w]) : 0u;                  // the input packs check m at bit 31 - m % 32
+            for (int j = 0; j < ly.degree; ++j) {
+                const int col = p.aux[ly.edge_begin + j].col, shift = p.aux[ly.edge_begin + j].shift;
+                int q = 32 * w + shift;                                         // check lane l reads variable lane (l + shift) mod Z
+                if (q >= Z) q -= Z;
+                const int qw = q >> 5, qn = qw + 1 == ZW ? 0 : qw + 1;
+                const uint32_t *h = hd + col * ZW;
+                acc ^= __funnelshift_r(h[qw], h[qn], q & 31);
+            }
+            bad |= (int)(acc != 0u);
+        }
+        return __syncthreads_or(bad) != 0;
+    };
+    auto frame_bad = [&](const uint32_t *syn) { return packed_syn ? syndrome_bad_packed(syn) : syndrome_bad(syn); };
+
     for (int f = blockIdx.x; f < p.F; f += gridDim.x) {
         const IN *llr = reinterpret_cast<const IN *>(p.llr) + (size_t)f * p.N;
         const uint32_t *syn = p.syn ? p.syn + (size_t)f * p.syn_words : nullptr;
@@ -459,13 +492,13 @@ __global__ void __launch_bounds__(MAXT, MINB) layered_generic_kernel(const Layer
             // float tiers: AFF3CT skips the check after the last iteration and honours syndrome_depth
             const bool want = p.early_stop && (kFloat ? it != p.max_iter : true);
             if (want) {
-                ok = !syndrome_bad(syn);
+                ok = !frame_bad(syn);
                 checked = true;
                 if (ok) { if (!kFloat || ++depth >= p.syndrome_depth) break; }
                 else depth = 0;
             }
         }
-        if (!checked) ok = !syndrome_bad(syn);
+        if (!checked) ok = !frame_bad(syn);
 
         uint32_t *ab = p.allbits + (size_t)f * p.cw_words;
         for (int w = tid; w < p.cw_words; w += nt) {
@@ -537,7 +570,8 @@ int layered_generic_belief_bytes(int dtype) { return dtype == QLDPC_DTYPE_F32 ? 
 int layered_generic_msg_bytes(int dtype) { return dtype == QLDPC_DTYPE_F32 ? 4 : 2; }
 int layered_generic_smem_bytes(int brows, int nnz, int N, int dtype)
 {
-    return (brows * 8 + nnz * 8 + N * layered_generic_belief_bytes(dtype) + 15) / 16 * 16;
+    // tables, beliefs, and N / 8 bytes of hard-decision bit vectors for the packed syndrome test
+    return (brows * 8 + nnz * 8 + N * layered_generic_belief_bytes(dtype) + (N + 31) / 32 * 4 + 15) / 16 * 16;
 }
 
 // co-resident CTAs per SM of the instantiation that serves (dtype, Z); 0: the beliefs do not fit in shared memory

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--only", default="")
+    ap.add_argument("--early-stop", action="store_true", help="syndrome test after every iteration (the usual mode of operation)")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     q = importlib.import_module("qcrypto-ldpc_b200")
@@ -67,7 +68,7 @@ def main():
             return torch.where(v >= 2**31, v - 2**32, v).to(torch.int32).contiguous()
 
         xb, yb = pack(x), pack(x ^ e)
-        dec = q.Decoder(code, schedule=q.SCHED_LAYERED, rule=rule, dtype=dt, max_iter=args.iters, early_stop=False,
+        dec = q.Decoder(code, schedule=q.SCHED_LAYERED, rule=rule, dtype=dt, max_iter=args.iters, early_stop=args.early_stop,
                         norm_factor=norm, offset=0.5, out_mode=q.OUT_ALL)
         syn = torch.empty((F, dec.syn_words), dtype=torch.int32, device=dev)
         dec.syndrome_device(xb.data_ptr(), F, syn.data_ptr(), st)

@@ -426,7 +426,16 @@ __global__ void __launch_bounds__(MAXT, MINB) layered_generic_kernel(const Layer
         const IN *llr = reinterpret_cast<const IN *>(p.llr) + (size_t)f * p.N;
         const uint32_t *syn = p.syn ? p.syn + (size_t)f * p.syn_words : nullptr;
         __syncthreads();                                   // tables written / previous frame's beliefs no longer read
-        for (int v = tid; v < p.N; v += nt) L[v] = (LT)llr[v];
+        if (std::is_same<IN, LT>::value && !GL && ((p.N * (int)sizeof(LT)) & 15) == 0 && (reinterpret_cast<size_t>(llr) & 15) == 0 &&
+            (((R + p.nnz) & 1) == 0)) {   // the beliefs start 8 (R + nnz) bytes into the 16-byte aligned shared memory
+            // input and belief type agree (float, int16): 128-bit copies, a quarter / an eighth of the dependent global round
+            // trips of the frame load (with early termination a frame lasts ~2 iterations and its load was a third of it)
+            const uint4 *src = reinterpret_cast<const uint4 *>(llr);
+            uint4 *dst = reinterpret_cast<uint4 *>(L);
+            for (int v = tid; v < ((p.N * (int)sizeof(LT)) >> 4); v += nt) dst[v] = src[v];
+        } else {
+            for (int v = tid; v < p.N; v += nt) L[v] = (LT)llr[v];
+        }
         __syncthreads();
 
         int it = 0, depth = 0;
@@ -501,13 +510,19 @@ __global__ void __launch_bounds__(MAXT, MINB) layered_generic_kernel(const Layer
         if (!checked) ok = !frame_bad(syn);
 
         uint32_t *ab = p.allbits + (size_t)f * p.cw_words;
-        for (int w = tid; w < p.cw_words; w += nt) {
-            uint32_t v = 0;
-            for (int b = 0; b < 32; ++b) {
-                const int idx = 32 * w + b;
-                if (idx < p.N && L[idx] < (LT)0) v |= 1u << (31 - b);
+        if (packed_syn) {
+            // the bit vectors of the last syndrome test ARE the hard decisions of the final beliefs: word w of the output
+            // (MSB first) is the bit reversal of vector word w (N is a multiple of 32 here)
+            for (int w = tid; w < p.cw_words; w += nt) ab[w] = __brev(hd[w]);
+        } else {
+            for (int w = tid; w < p.cw_words; w += nt) {
+                uint32_t v = 0;
+                for (int b = 0; b < 32; ++b) {
+                    const int idx = 32 * w + b;
+                    if (idx < p.N && L[idx] < (LT)0) v |= 1u << (31 - b);
+                }
+                ab[w] = v;
             }
-            ab[w] = v;
         }
         if (p.posterior) {
             if constexpr (kFloat) {

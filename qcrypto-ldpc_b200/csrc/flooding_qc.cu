@@ -194,13 +194,12 @@ __global__ void __launch_bounds__(QL_FQ_THREADS, 1) flooding_qc_kernel(const Flo
 
         // ---- outputs
         uint32_t *ab = p.allbits + (size_t)f * p.cw_words;
-        for (int w = tid; w < p.cw_words; w += nt) {
-            uint32_t v = 0;
-            for (int b = 0; b < 32; ++b) {
-                const int idx = 32 * w + b;
-                if (idx < p.N && post[idx] < 0.0f) v |= 1u << (31 - b);
-            }
-            ab[w] = v;
+        // one variable per thread, one ballot per warp and output word (was: 32 serial loads and compares per word on the
+        // first cw_words threads)
+        for (int v0 = 0; v0 < p.cw_words * 32; v0 += nt) {
+            const int v = v0 + tid;
+            const unsigned b = __ballot_sync(0xffffffffu, v < p.N && post[v] < 0.0f);
+            if ((tid & 31) == 0 && (v >> 5) < p.cw_words) ab[v >> 5] = __brev(b);   // bit 31 - k of word w = variable 32 w + k
         }
         if (p.posterior) {
             float *po = p.posterior + (size_t)f * p.N;

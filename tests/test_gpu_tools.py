@@ -48,6 +48,16 @@ def test_layered_probe_covers_every_layered_kernel():
     assert all(r["all_reconciled"] for r in rows if "f32" in r["case"] or "i16" in r["case"])
 
 
+def test_layered_probe_with_early_termination():
+    """the usual mode of operation: syndrome test after every iteration (bit-vector test in layered_generic for Z % 32 == 0,
+    per-lane test otherwise); every float / int16 frame still reconciles, in fewer iterations than the fixed count"""
+    rows = _run(["tools/layered_bench.py", "--frames", "128", "--reps", "1", "--iters", "10", "--early-stop", "--only", "Z="])
+    gen = [r for r in rows if r["kernel"] == "layered_generic"]
+    assert len(gen) >= 4
+    assert all(r["all_reconciled"] for r in gen if "f32" in r["case"] or "i16" in r["case"])
+    assert all(1.0 <= r["iterations"] < 6.0 for r in gen), [(r["case"], r["iterations"]) for r in gen]
+
+
 def test_stream_tool_counts_every_frame():
     rows = _run(["tools/stream_10gbit.py", "--gbit", "0.2", "--chunk", "8192"])
     r = rows[-1]

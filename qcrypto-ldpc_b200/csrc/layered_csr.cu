@@ -82,6 +82,19 @@ __device__ __forceinline__ void csr_rows(const LayeredCsrParams &p, float *var, 
     }
 }
 
+// parity of the hard decisions of one check of degree D: the D loads are in flight together
+template <int D>
+__device__ __forceinline__ unsigned csr_row_parity(const LayeredCsrParams &p, const float *var, int e0, size_t T)
+{
+    float v[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) v[j] = var[(size_t)__ldg(p.col_idx + e0 + j) * T];
+    unsigned s = 0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) s ^= (unsigned)(v[j] < 0.0f);
+    return s;
+}
+
 __global__ void __launch_bounds__(128, 4) layered_csr_kernel(const LayeredCsrParams p)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x, T = gridDim.x * blockDim.x;
@@ -96,7 +109,16 @@ __global__ void __launch_bounds__(128, 4) layered_csr_kernel(const LayeredCsrPar
             unsigned bad = 0;
             for (int m = 0; m < p.M; ++m) {
                 unsigned s = syn ? (syn[m >> 5] >> (31 - (m & 31))) & 1u : 0u;
-                for (int e = p.row_ptr[m]; e < p.row_ptr[m + 1]; ++e) s ^= (unsigned)(var[(size_t)p.col_idx[e] * T] < 0.0f);
+                const int e0 = p.row_ptr[m], d = p.row_ptr[m + 1] - e0;
+#define QL_D(D) case D: s ^= csr_row_parity<D>(p, var, e0, (size_t)T); break;
+                switch (d) {   // warp-uniform
+                    QL_D(1) QL_D(2) QL_D(3) QL_D(4) QL_D(5) QL_D(6) QL_D(7) QL_D(8)
+                    QL_D(9) QL_D(10) QL_D(11) QL_D(12) QL_D(13) QL_D(14) QL_D(15) QL_D(16)
+                default:
+                    for (int e = e0; e < e0 + d; ++e) s ^= (unsigned)(var[(size_t)p.col_idx[e] * T] < 0.0f);
+                    break;
+                }
+#undef QL_D
                 bad |= s;
             }
             return bad == 0;
